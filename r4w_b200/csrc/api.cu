@@ -1,0 +1,257 @@
+// api.cu — the extern "C" boundary of libr4w_b200.so (include/r4w_b200.h).
+// Every entry point converts internal failures into r4wb_error + a thread-local message; nothing unwinds.
+#include <cmath>
+#include <cstring>
+#include <new>
+
+#include "acq.cuh"
+#include "synth.cuh"
+
+namespace r4wb {
+
+std::atomic<uint64_t> g_kernel_launches{0};
+static thread_local cudaStream_t t_stream = nullptr;
+static thread_local std::string t_error;
+
+cudaStream_t current_stream() { return t_stream; }
+void e1_code_chips(uint32_t channel, uint32_t prn, int8_t* out);
+
+template <typename F>
+static r4wb_error guard(F&& body)
+{
+    try {
+        body();
+        return R4WB_OK;
+    } catch (const Failure& f) {
+        t_error = f.what;
+        return f.code;
+    } catch (const std::bad_alloc&) {
+        t_error = "host allocation failed";
+        return R4WB_ERR_ALLOCATION_FAILED;
+    } catch (const std::exception& e) {
+        t_error = e.what();
+        return R4WB_ERR_INVALID_PARAMETER;
+    } catch (...) {
+        t_error = "unknown failure";
+        return R4WB_ERR_INVALID_PARAMETER;
+    }
+}
+
+static void require_device()
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0)
+        fail(R4WB_ERR_CUDA, "no CUDA device available (%s); libr4w_b200 has no CPU fallback",
+             e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+}
+
+}  // namespace r4wb
+
+using namespace r4wb;
+
+struct r4wb_scenario { Scenario impl; explicit r4wb_scenario(const r4wb_scenario_cfg& c) : impl(c) {} };
+struct r4wb_pcps { Pcps impl; r4wb_pcps(uint64_t n, double fs) : impl(n, fs) {} };
+
+extern "C" {
+
+const char* r4wb_version(void) { return "r4w_b200 0.1.0 (sm_100a)"; }
+const char* r4wb_last_error(void) { return t_error.c_str(); }
+
+r4wb_error r4wb_init(int device)
+{
+    return guard([&] {
+        require_device();
+        if (device >= 0) R4WB_CUDA(cudaSetDevice(device));
+        R4WB_CUDA(cudaFree(nullptr));
+    });
+}
+
+r4wb_error r4wb_device_count(int* n)
+{
+    if (!n) { t_error = "n is NULL"; return R4WB_ERR_NULL_POINTER; }
+    *n = 0;
+    cudaError_t e = cudaGetDeviceCount(n);
+    if (e != cudaSuccess) { *n = 0; t_error = cudaGetErrorString(e); cudaGetLastError(); return R4WB_ERR_CUDA; }
+    return R4WB_OK;
+}
+
+r4wb_error r4wb_set_stream(void* cuda_stream)
+{
+    t_stream = reinterpret_cast<cudaStream_t>(cuda_stream);
+    return R4WB_OK;
+}
+
+r4wb_error r4wb_host_alloc(void** p, size_t bytes)
+{
+    if (!p) { t_error = "p is NULL"; return R4WB_ERR_NULL_POINTER; }
+    return guard([&] {
+        require_device();
+        cudaError_t e = cudaHostAlloc(p, bytes ? bytes : 1, cudaHostAllocDefault);
+        if (e != cudaSuccess) fail(R4WB_ERR_ALLOCATION_FAILED, "cudaHostAlloc(%zu): %s", bytes, cudaGetErrorString(e));
+    });
+}
+
+r4wb_error r4wb_host_free(void* p)
+{
+    if (!p) return R4WB_OK;
+    return guard([&] { R4WB_CUDA(cudaFreeHost(p)); });
+}
+
+uint64_t r4wb_kernel_launches(void) { return g_kernel_launches.load(); }
+
+/* ---------------------------------------------------------------- scenario */
+r4wb_error r4wb_scenario_create(const r4wb_scenario_cfg* cfg, r4wb_scenario** out)
+{
+    if (!cfg || !out) { t_error = "cfg/out is NULL"; return R4WB_ERR_NULL_POINTER; }
+    *out = nullptr;
+    return guard([&] {
+        require_device();
+        *out = new r4wb_scenario(*cfg);
+    });
+}
+
+void r4wb_scenario_destroy(r4wb_scenario* h) { delete h; }
+uint64_t r4wb_scenario_total_samples(const r4wb_scenario* h) { return h ? h->impl.total_samples() : 0; }
+uint64_t r4wb_scenario_block_size(const r4wb_scenario* h) { return h ? h->impl.block_size() : 0; }
+int r4wb_scenario_is_done(const r4wb_scenario* h) { return h ? (h->impl.is_done() ? 1 : 0) : 1; }
+double r4wb_scenario_progress(const r4wb_scenario* h) { return h ? h->impl.progress() : 1.0; }
+uint64_t r4wb_scenario_current_sample(const r4wb_scenario* h) { return h ? h->impl.current_sample() : 0; }
+
+r4wb_error r4wb_scenario_reset(r4wb_scenario* h)
+{
+    if (!h) { t_error = "handle is NULL"; return R4WB_ERR_NULL_POINTER; }
+    return guard([&] { h->impl.reset(); });
+}
+
+r4wb_error r4wb_scenario_generate_block(r4wb_scenario* h, uint64_t n, void* dst, r4wb_mem where, r4wb_fmt fmt,
+                                        uint64_t* written)
+{
+    if (!h || !written) { t_error = "handle/written is NULL"; return R4WB_ERR_NULL_POINTER; }
+    *written = 0;
+    return guard([&] { *written = h->impl.generate_block(n, dst, where, fmt); });
+}
+
+r4wb_error r4wb_scenario_generate(r4wb_scenario* h, uint64_t first, uint64_t n, void* dst, r4wb_mem where, r4wb_fmt fmt)
+{
+    if (!h) { t_error = "handle is NULL"; return R4WB_ERR_NULL_POINTER; }
+    return guard([&] { h->impl.generate(first, n, dst, where, fmt); });
+}
+
+r4wb_error r4wb_scenario_last_power_sum(const r4wb_scenario* h, double* power_sum)
+{
+    if (!h || !power_sum) { t_error = "handle/power_sum is NULL"; return R4WB_ERR_NULL_POINTER; }
+    return guard([&] { *power_sum = const_cast<r4wb_scenario*>(h)->impl.last_power_sum(); });
+}
+
+r4wb_error r4wb_scenario_status(const r4wb_scenario* h, r4wb_sat_status* out, uint32_t cap, uint32_t* n)
+{
+    if (!h || !out) { t_error = "handle/out is NULL"; return R4WB_ERR_NULL_POINTER; }
+    return guard([&] { h->impl.status(out, cap, n); });
+}
+
+/* test hook (not part of the drop-in surface): prologue entry of a canonical block */
+r4wb_error r4wb_debug_block_params(r4wb_scenario* h, uint64_t block, uint32_t sat, double* out12)
+{
+    if (!h || !out12) { t_error = "handle/out is NULL"; return R4WB_ERR_NULL_POINTER; }
+    return guard([&] { h->impl.debug_block(block, sat, out12); });
+}
+
+/* ---------------------------------------------------------------- codes */
+r4wb_error r4wb_e1_code(uint32_t channel, uint8_t prn, int8_t* out, uint64_t cap)
+{
+    if (!out) { t_error = "out is NULL"; return R4WB_ERR_NULL_POINTER; }
+    if (channel > 1 || prn < 1 || prn > 50) { t_error = "Galileo PRN must be 1-50, channel 0/1"; return R4WB_ERR_INVALID_PARAMETER; }
+    if (cap < 4092) { t_error = "code buffer needs 4092 entries"; return R4WB_ERR_INVALID_SIZE; }
+    e1_code_chips(channel, prn, out);
+    return R4WB_OK;
+}
+
+r4wb_error r4wb_e1c_secondary(int8_t* out, uint64_t cap)
+{
+    static const int8_t sec[25] = {1, 1, -1, -1, -1, 1, 1, 1, 1, 1, 1, 1, 1, -1, 1, -1, 1, -1, -1, -1, -1, 1, 1, 1, -1};
+    if (!out) { t_error = "out is NULL"; return R4WB_ERR_NULL_POINTER; }
+    if (cap < 25) { t_error = "secondary code needs 25 entries"; return R4WB_ERR_INVALID_SIZE; }
+    std::memcpy(out, sec, 25);
+    return R4WB_OK;
+}
+
+r4wb_error r4wb_e1c_replica(uint8_t prn, double sample_rate, int8_t* out, uint64_t n)
+{
+    if (!out) { t_error = "out is NULL"; return R4WB_ERR_NULL_POINTER; }
+    if (prn < 1 || prn > 50 || !(sample_rate > 0.0)) { t_error = "bad PRN / sample rate"; return R4WB_ERR_INVALID_PARAMETER; }
+    int8_t code[4092];
+    e1_code_chips(1, prn, code);
+    // same index expression as the emitter with zero delay (gnss/satellite_emitter.rs:245, 268-270, 303-305)
+    const double spc = sample_rate / 1023000.0;
+    for (uint64_t i = 0; i < n; ++i) {
+        const double cf = (double)i / spc;
+        const double cm = std::fmod(cf, 4092.0);
+        uint32_t c = cm > 0.0 ? (uint32_t)cm : 0u;
+        if (c > 4091u) c = 4091u;
+        const double cp = cf - std::floor(cf);
+        out[i] = (int8_t)(std::fmod(cp * 2.0, 2.0) < 1.0 ? code[c] : -code[c]);
+    }
+    return R4WB_OK;
+}
+
+/* ---------------------------------------------------------------- PCPS */
+r4wb_error r4wb_pcps_create(uint64_t code_length, double sample_rate, r4wb_pcps** out)
+{
+    if (!out) { t_error = "out is NULL"; return R4WB_ERR_NULL_POINTER; }
+    *out = nullptr;
+    return guard([&] {
+        require_device();
+        *out = new r4wb_pcps(code_length, sample_rate);
+    });
+}
+
+void r4wb_pcps_destroy(r4wb_pcps* h) { delete h; }
+
+r4wb_error r4wb_pcps_set_doppler_range(r4wb_pcps* h, double max_hz, double step_hz)
+{
+    if (!h) { t_error = "handle is NULL"; return R4WB_ERR_NULL_POINTER; }
+    return guard([&] { h->impl.set_doppler_range(max_hz, step_hz); });
+}
+
+r4wb_error r4wb_pcps_set_threshold(r4wb_pcps* h, double threshold)
+{
+    if (!h) { t_error = "handle is NULL"; return R4WB_ERR_NULL_POINTER; }
+    h->impl.set_threshold(threshold);
+    return R4WB_OK;
+}
+
+r4wb_error r4wb_pcps_set_coherent_periods(r4wb_pcps* h, uint64_t periods)
+{
+    if (!h) { t_error = "handle is NULL"; return R4WB_ERR_NULL_POINTER; }
+    h->impl.set_coherent_periods(periods);
+    return R4WB_OK;
+}
+
+uint64_t r4wb_pcps_fft_size(const r4wb_pcps* h) { return h ? h->impl.fft_size() : 0; }
+uint32_t r4wb_pcps_num_doppler_bins(const r4wb_pcps* h) { return h ? h->impl.num_bins() : 0; }
+uint64_t r4wb_pcps_guard_count(const r4wb_pcps* h) { return h ? h->impl.guard_count() : 0; }
+
+r4wb_error r4wb_pcps_acquire(r4wb_pcps* h, const void* input, r4wb_fmt fmt, uint64_t n_input, const int8_t* code,
+                             uint64_t code_len, uint8_t prn, r4wb_acq_result* out)
+{
+    if (!h || !input || !code || !out) { t_error = "NULL argument"; return R4WB_ERR_NULL_POINTER; }
+    return guard([&] { h->impl.acquire_batch(input, fmt, R4WB_MEM_HOST, 1, 0, n_input, code, code_len, &prn, 1, out); });
+}
+
+r4wb_error r4wb_pcps_acquire_batch(r4wb_pcps* h, const void* input, r4wb_fmt fmt, r4wb_mem where, uint64_t n_snapshots,
+                                   uint64_t snapshot_stride, uint64_t n_input, const int8_t* codes, uint64_t code_len,
+                                   const uint8_t* prns, uint32_t n_codes, r4wb_acq_result* out)
+{
+    if (!h || !input || !codes || !out) { t_error = "NULL argument"; return R4WB_ERR_NULL_POINTER; }
+    return guard([&] { h->impl.acquire_batch(input, fmt, where, n_snapshots, snapshot_stride, n_input, codes, code_len, prns, n_codes, out); });
+}
+
+r4wb_error r4wb_pcps_acquire_grid(r4wb_pcps* h, const void* input, r4wb_fmt fmt, uint64_t n_input, const int8_t* code,
+                                  uint64_t code_len, double* power_out, uint64_t cap)
+{
+    if (!h || !input || !code || !power_out) { t_error = "NULL argument"; return R4WB_ERR_NULL_POINTER; }
+    return guard([&] { h->impl.acquire_grid(input, fmt, n_input, code, code_len, power_out, cap); });
+}
+
+}  // extern "C"

@@ -1,0 +1,162 @@
+// synth.cuh — data structures of the scenario-synthesis path (host model + kernel arguments).
+#pragma once
+#include <cstdint>
+#include <vector>
+
+#include "common.hpp"
+#include "geom.hpp"
+
+namespace r4wb {
+
+constexpr int kOversample = 8;        // BASEBAND_OVERSAMPLE, gnss/scenario.rs:47
+constexpr int kTaps = 63;             // FirFilter::lowpass(.., 63), gnss/scenario.rs:216
+constexpr int kCodeLen = 4092;        // Galileo E1 primary code
+constexpr int kSecLen = 25;           // E1C secondary code
+constexpr uint32_t kHalfChipsPerSec = 2u * kCodeLen * kSecLen;   // 204 600 half-chips = 100 ms
+constexpr int kFracBits = 46;         // fixed-point fraction of the half-chip position
+constexpr int kTBits = 24;            // fraction bits of "oversamples since boundary" (8 integer bits: up to 256 oversamples)
+constexpr int kMaxSats = 64;
+constexpr int kMaxSegments = 512;
+
+// One piece of the reference's sequential f64 `phase += phase_inc` (gnss/scenario.rs:518-527) for a
+// constant-Doppler satellite: from visible-sample count i0 on, phase = x0 + (m - i0) * step EXACTLY
+// (x0 and step are multiples of the binade's ulp), until the next segment starts.
+struct PhaseSegment {
+    uint64_t i0;
+    double x0;
+    double step;
+};
+
+// per-satellite constants (device copy lives in Scenario::d_sat)
+struct SatConst {
+    Orbit orbit;
+    double carrier_hz;
+    uint32_t has;
+    uint32_t orbital_dynamics;
+    uint32_t needs_orbit;        // geometry must be evaluated per block
+    uint32_t static_phase;       // constant Doppler + constant visibility: emulate the f64 accumulation via segments
+    double tx_power_dbw;
+    double elevation_deg, range_m, range_rate_mps, doppler_hz, doppler_rate_hz_per_s, cn0_dbhz;
+    double iono_delay_m, tropo_delay_m;
+    double orb_doppler_t0, orb_range_t0;
+    int32_t seg_begin, seg_count;   // into Scenario::d_segments
+};
+
+// scenario-wide constants handed to kernels by value
+struct ScenConst {
+    double fs, t0_gps, duration_s;
+    uint64_t total, B;
+    uint32_t n_sats, flags;
+    RxModel rx;
+    uint32_t antenna;
+    double ant_peak, ant_bw, elev_mask_deg;
+    double chip_rate, spc;          // spc = (8 fs) / chip_rate exactly as the reference computes it (f64)
+    uint64_t ratA, ratB;            // (8 fs) / chip_rate == ratA / ratB as exact integers
+    double delta;                   // spc == (ratA/ratB) * (1 + delta)
+    uint64_t delta46;               // half-chips per oversample, 2^-46 units (floor)
+    uint64_t lattice_den;           // D: half-chip fractions of a block lie on offset + k/D (0 = dense)
+    uint32_t kmul;                  // round(S * 2^24), S = oversamples per half-chip
+    uint32_t cj[8];                 // round(j * S * 2^24)
+    float noise_std;
+    uint64_t seed;
+};
+
+// per-(block, satellite) entry produced by the prologue and consumed by the synthesis kernel
+struct BlockSat {
+    uint64_t U;        // half-chip position (18.46 fixed, mod 204600) of the block's first oversample
+    uint64_t phi;      // carrier phase before the block's first increment, cycles 0.64
+    int64_t f;         // first per-sample increment, cycles 0.64
+    int64_t df;        // growth of the increment per sample
+    double phase0;     // initial_code_phase (chips), gnss/satellite_emitter.rs:235
+    uint64_t G;        // global oversample index of the block's first oversample
+    uint32_t n;        // samples in the block
+    uint32_t e0;       // initial_epoch_offset, gnss/satellite_emitter.rs:242
+    float amp;         // rx_amplitude
+    uint32_t flags;    // bit0 visible, bit1 lattice comes within eps of a half-chip boundary
+    int32_t prev;      // flat entry index whose tail fills the FIR history (-1: zeros)
+    uint32_t eps46;    // ambiguity half-width in 2^-46 half-chips
+    uint32_t eps_t;    // same in 2^-24 oversamples
+    uint32_t pad;
+};
+static_assert(sizeof(BlockSat) == 80, "BlockSat layout");
+
+struct BlockHdr { uint64_t first; uint32_t n; uint32_t pad; };
+
+struct SynthArgs {
+    const BlockSat* tab;       // [n_tab_blocks][n_sats]
+    const BlockHdr* hdr;       // [n_tab_blocks]
+    const uint32_t* codebits;  // [n_sats][128] packed primary code, bit=1 -> chip -1
+    const float* taps;         // [64] h[k] (f32), [63] = 0
+    const float* etab;         // [64] E[d] = sum_{k<=d} h[k]  (E[62] = E[63] = 1)
+    void* out;                 // cf32 or cf64, out[0] <-> sample out_first
+    double* power_sum;         // optional accumulator of |s|^2
+    uint64_t out_first, out_n; // only samples in [out_first, out_first + out_n) are written
+    uint32_t tb_begin, tb_count;   // table blocks to render
+    uint32_t tiles_per_block;
+    uint32_t n_sats;
+    uint32_t nw64;             // 64-bit words of the per-satellite half-chip sign table
+    uint32_t flags;
+    uint64_t delta46;
+    uint32_t kmul;
+    uint32_t cj[8];
+    double spc;
+    float noise_std;
+    uint64_t seed;
+};
+
+class Scenario {
+public:
+    explicit Scenario(const r4wb_scenario_cfg& cfg);
+    ~Scenario();
+
+    uint64_t total_samples() const { return sc_.total; }
+    uint64_t block_size() const { return sc_.B; }
+    uint64_t current_sample() const { return current_; }
+    bool is_done() const { return current_ >= sc_.total; }
+    double progress() const { return sc_.total == 0 ? 1.0 : (double)current_ / (double)sc_.total; }
+    void reset();
+
+    // canonical-partition random access; dst is device or host memory
+    void generate(uint64_t first, uint64_t n, void* dst, r4wb_mem where, r4wb_fmt fmt);
+    // one reference block of min(n, remaining) samples at current_sample
+    uint64_t generate_block(uint64_t n, void* dst, r4wb_mem where, r4wb_fmt fmt);
+    double last_power_sum();
+    void status(r4wb_sat_status* out, uint32_t cap, uint32_t* n) const;
+    // test hook: entry of canonical block `block`, satellite `sat` -> 12 doubles
+    void debug_block(uint64_t block, uint32_t sat, double* out12);
+
+private:
+    void launch_synth(const BlockSat* tab, const BlockHdr* hdr, uint32_t tb_begin, uint32_t tb_count,
+                      uint64_t out_first, uint64_t out_n, void* d_out, r4wb_fmt fmt, uint64_t max_block_n);
+    void build_canonical_table(uint64_t blk_begin, uint64_t blk_end);   // fills d_tab_/d_hdr_ for [blk_begin, blk_end)
+    void render_to(uint64_t first, uint64_t n, void* dst, r4wb_mem where, r4wb_fmt fmt);
+
+    ScenConst sc_{};
+    std::vector<SatConst> sats_;
+    std::vector<r4wb_sat_cfg> cfg_sats_;
+    r4wb_scenario_cfg cfg_{};
+    std::vector<PhaseSegment> segments_;
+    uint64_t current_ = 0;
+    int tile_k_ = 5;
+    uint32_t nw64_ = 0;
+    bool any_dynamic_ = false, any_var_visibility_ = false;
+
+    // sequential-API state (generate_block)
+    std::vector<uint64_t> seq_m_;       // visible samples so far (static-phase satellites)
+    std::vector<uint64_t> seq_phi_;     // carrier phase, cycles 0.64 (dynamic satellites)
+    std::vector<BlockSat> seq_prev_;    // last visible block per satellite
+    std::vector<uint8_t> seq_has_prev_;
+
+    // device state
+    DevBuf<SatConst> d_sat_;
+    DevBuf<PhaseSegment> d_segments_;
+    DevBuf<uint32_t> d_codebits_;
+    DevBuf<float> d_taps_, d_etab_;
+    DevBuf<BlockSat> d_tab_, d_seq_tab_;
+    DevBuf<BlockHdr> d_hdr_, d_seq_hdr_;
+    DevBuf<double> d_power_;
+    DevBuf<unsigned char> d_stage_;
+    uint64_t tab_blk0_ = 0;             // canonical index of d_tab_'s first block
+};
+
+}  // namespace r4wb
