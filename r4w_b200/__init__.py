@@ -1,0 +1,9 @@
+"""r4w_b200 — B200 (sm_100a) drop-in for r4w's GNSS hot path: multi-satellite IQ scenario synthesis and
+FFT-based PCPS acquisition.  Host-side mirror of the reference's `GnssScenarioConfig` / `GnssScenario` /
+`PcpsAcquisition` surface over the C-ABI library libr4w_b200.so (include/r4w_b200.h)."""
+from .config import (GnssScenarioConfig, SatelliteConfig, ReceiverConfig, EnvironmentConfig, OutputConfig,  # noqa: F401
+                     LlaPosition, AntennaPattern, ReceiverTrajectory, load_config, loads_config)
+from ._lib import R4wB200Error, init, kernel_launches, device_count, version, build  # noqa: F401
+from .scenario import GnssScenario, SatelliteStatus  # noqa: F401
+from .acquisition import (PcpsAcquisition, AcquisitionResult, AcquisitionGrid, e1_code, e1c_secondary,  # noqa: F401
+                          e1c_replica)

@@ -1,0 +1,194 @@
+// acq_host.cu — host side of PcpsAcquisition (gnss/acquisition.rs:40-255): batches (snapshot, code) searches
+// through the FFT kernels, re-runs near-ties in f64, and finishes the AcquisitionResult in f64 on the host.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "acq.cuh"
+
+namespace r4wb {
+
+// launchers (acq_kernels.cu)
+template <typename T> void launch_twiddles(cx<T>* W, uint32_t N, cudaStream_t st);
+template <typename T>
+void launch_fwd_input(const AcqGeom& g, uint32_t rows, const void* input, uint32_t in64, uint64_t stride, uint32_t take,
+                      const cx<T>* W, cx<T>* out, cudaStream_t st);
+template <typename T>
+void launch_fwd_codes(const AcqGeom& g, uint32_t n_codes, const int8_t* codes, uint64_t code_len, uint32_t take, const cx<T>* W,
+                      cx<T>* out, cudaStream_t st);
+template <typename T>
+void launch_inv_peak(const AcqGeom& g, uint32_t rows, const cx<T>* X, const cx<T>* C, const cx<T>* W, RowPeak* peaks, double* grid,
+                     cudaStream_t st);
+void launch_pair_reduce(const AcqGeom& g, uint32_t n_snap, const RowPeak* peaks, PairPeak* out, cudaStream_t st);
+
+// f32 results whose two best cells are closer than this (relative) are re-run in f64 so the reported
+// (lag, Doppler bin) is the one an f64 evaluation (the reference's arithmetic) picks
+static constexpr double kNearTie = 1e-4;
+static constexpr double kNearThreshold = 1e-3;
+static constexpr size_t kSpectraChunkBytes = 96u << 20;   // forward spectra kept per chunk: stays inside the 126 MB L2
+
+Pcps::Pcps(uint64_t code_length, double sample_rate) : code_length_(code_length), fs_(sample_rate)
+{
+    if (!(sample_rate > 0.0)) fail(R4WB_ERR_INVALID_PARAMETER, "sample_rate must be positive");
+    if (code_length > (1ull << 17)) fail(R4WB_ERR_NOT_SUPPORTED, "code_length %llu: fft_size above 131072 is not supported", (unsigned long long)code_length);
+    uint64_t f = 1;                       // usize::next_power_of_two (acquisition.rs:64)
+    while (f < code_length) f <<= 1;
+    fft_size_ = f;
+    logn_ = 0;
+    while ((1ull << logn_) < f) ++logn_;
+}
+
+Pcps::~Pcps() {}
+
+void Pcps::set_doppler_range(double max_hz, double step_hz)
+{
+    if (!(step_hz > 0.0) || !(max_hz >= 0.0) || !std::isfinite(max_hz) || 2.0 * max_hz / step_hz > 1.0e6)
+        fail(R4WB_ERR_INVALID_PARAMETER, "doppler range +-%g Hz step %g Hz", max_hz, step_hz);
+    dmax_ = max_hz;
+    dstep_ = step_hz;
+}
+
+uint32_t Pcps::num_bins() const { return (uint32_t)((int32_t)(2.0 * dmax_ / dstep_) + 1); }   // acquisition.rs:126
+
+AcqGeom Pcps::geom(int max_logM) const
+{
+    AcqGeom g{};
+    g.logN = logn_;
+    g.logM = std::min(logn_, max_logM);
+    g.logF = g.logN - g.logM;
+    if (g.logF > 3) fail(R4WB_ERR_NOT_SUPPORTED, "fft_size %llu too large", (unsigned long long)fft_size_);
+    g.N = (uint32_t)fft_size_;
+    g.L = (uint32_t)code_length_;
+    g.D = num_bins();
+    g.P = 0;
+    g.fs = fs_; g.dmax = dmax_; g.dstep = dstep_;
+    return g;
+}
+
+template <typename T>
+void Pcps::run(AcqWork<T>& w, const void* d_input, r4wb_fmt fmt, uint64_t s0, uint64_t ns, uint64_t stride, uint64_t n_input,
+               const int8_t* d_codes, uint64_t code_len, uint32_t c0, uint32_t nc, PairPeak* d_out, double* d_grid)
+{
+    cudaStream_t st = current_stream();
+    AcqGeom g = geom(fft_max_logM<T>());
+    g.P = nc;
+    const uint32_t F = 1u << g.logF;
+    if (!w.tw_ready) {
+        launch_twiddles<T>(w.tw.reserve(g.N), g.N, st);
+        w.tw_ready = true;
+    }
+    const uint32_t take = (uint32_t)std::min<uint64_t>(n_input, g.L);               // input.iter().take(samples_per_code)
+    const uint32_t code_take = (uint32_t)std::min<uint64_t>(code_len, g.N);         // code_fft.resize(fft_size)
+    launch_fwd_codes<T>(g, nc, d_codes + (size_t)c0 * code_len, code_len, code_take, w.tw.p, w.c.reserve((size_t)nc * g.N), st);
+
+    const size_t row_bytes = (size_t)g.N * sizeof(cx<T>);
+    uint64_t chunk = std::max<uint64_t>(1, kSpectraChunkBytes / (row_bytes * std::max(1u, g.D)));
+    chunk = std::min<uint64_t>(chunk, std::max<uint64_t>(1, 0x3fffffffull / ((uint64_t)std::max(1u, g.D) * nc * F)));
+    chunk = std::min(chunk, ns);
+    w.x.reserve((size_t)chunk * g.D * g.N);
+    d_rowpeaks_.reserve((size_t)chunk * g.D * nc * F);
+    const size_t bps = fmt == R4WB_FMT_CF64 ? 16 : 8;
+    for (uint64_t s = 0; s < ns; s += chunk) {
+        const uint32_t cs = (uint32_t)std::min<uint64_t>(chunk, ns - s);
+        const unsigned char* in = static_cast<const unsigned char*>(d_input) + (s0 + s) * stride * bps;
+        launch_fwd_input<T>(g, cs * g.D, in, fmt == R4WB_FMT_CF64 ? 1u : 0u, stride, take, w.tw.p, w.x.p, st);
+        launch_inv_peak<T>(g, cs * g.D, w.x.p, w.c.p, w.tw.p, d_rowpeaks_.p, d_grid, st);
+        launch_pair_reduce(g, cs, d_rowpeaks_.p, d_out + s * nc, st);
+    }
+}
+
+// acquisition.rs:167-194
+void Pcps::finish(const PairPeak& pk, uint8_t prn, r4wb_acq_result& r) const
+{
+    const uint64_t L = code_length_;
+    const uint64_t total_bins = (uint64_t)num_bins() * L;
+    double best = pk.best, phase = 0.0, doppler = 0.0;
+    if (!(best > 0.0) || pk.lin == 0xffffffffu) {
+        best = 0.0;                                        // `mag > best_peak` never fired: initial values survive
+    } else {
+        const uint64_t d = pk.lin / L;
+        phase = (double)(pk.lin - d * L);
+        doppler = -dmax_ + (double)d * dstep_;
+    }
+    const uint64_t denom = total_bins > 1 ? total_bins - 1 : 1;
+    const double noise_floor = (pk.sum - best) / (double)denom;
+    const double metric = noise_floor > 0.0 ? best / noise_floor : best;
+    std::memset(&r, 0, sizeof r);
+    r.prn = prn;
+    r.detected = metric > threshold_ ? 1 : 0;
+    r.code_phase = phase;
+    r.doppler_hz = doppler;
+    r.peak_metric = metric;
+    r.threshold = threshold_;
+    if (r.detected) {
+        r.has_cn0 = 1;
+        r.cn0_estimate = 10.0 * std::log10(metric / ((double)L / fs_));
+    }
+}
+
+void Pcps::acquire_batch(const void* input, r4wb_fmt fmt, r4wb_mem where, uint64_t S, uint64_t stride, uint64_t n_input,
+                         const int8_t* codes, uint64_t code_len, const uint8_t* prns, uint32_t P, r4wb_acq_result* out)
+{
+    if (S == 0 || P == 0) return;
+    if (S * (uint64_t)P > 0x7fffffffull) fail(R4WB_ERR_INVALID_SIZE, "too many (snapshot, code) pairs in one call");
+    if (fmt != R4WB_FMT_CF32 && fmt != R4WB_FMT_CF64) fail(R4WB_ERR_INVALID_PARAMETER, "unknown sample format");
+    if (code_length_ == 0) fail(R4WB_ERR_INVALID_SIZE, "code_length is 0");
+    cudaStream_t st = current_stream();
+    const size_t bps = fmt == R4WB_FMT_CF64 ? 16 : 8;
+    const void* d_input = input;
+    if (where == R4WB_MEM_HOST) {
+        const size_t bytes = ((S - 1) * stride + n_input) * bps;
+        d_in_.reserve(std::max<size_t>(bytes, 16));
+        if (bytes) R4WB_CUDA(cudaMemcpyAsync(d_in_.p, input, bytes, cudaMemcpyHostToDevice, st));
+        d_input = d_in_.p;
+    }
+    d_codes_.reserve(std::max<size_t>((size_t)P * code_len, 16));
+    if (code_len) R4WB_CUDA(cudaMemcpyAsync(d_codes_.p, codes, (size_t)P * code_len, cudaMemcpyHostToDevice, st));
+    const size_t pairs = (size_t)S * P;
+    d_pairpeaks_.reserve(pairs + 1);
+
+    run<float>(w32_, d_input, fmt, 0, S, stride, n_input, d_codes_.p, code_len, 0, P, d_pairpeaks_.p, nullptr);
+    std::vector<PairPeak> pk(pairs);
+    R4WB_CUDA(cudaMemcpyAsync(pk.data(), d_pairpeaks_.p, pairs * sizeof(PairPeak), cudaMemcpyDeviceToHost, st));
+    R4WB_CUDA(cudaStreamSynchronize(st));
+
+    guard_count_ = 0;
+    for (size_t i = 0; i < pairs; ++i) {
+        const uint64_t s = i / P;
+        const uint32_t c = (uint32_t)(i % P);
+        const uint8_t prn = prns ? prns[c] : 0;
+        finish(pk[i], prn, out[i]);
+        const bool near_tie = pk[i].best > 0.0 && (pk[i].best - pk[i].second) <= kNearTie * pk[i].best;
+        const bool near_thr = threshold_ > 0.0 && std::fabs(out[i].peak_metric / threshold_ - 1.0) < kNearThreshold;
+        if (near_tie || near_thr) {
+            PairPeak* d_g = d_pairpeaks_.p + pairs;
+            run<double>(w64_, d_input, fmt, s, 1, stride, n_input, d_codes_.p, code_len, c, 1, d_g, nullptr);
+            PairPeak g;
+            R4WB_CUDA(cudaMemcpyAsync(&g, d_g, sizeof g, cudaMemcpyDeviceToHost, st));
+            R4WB_CUDA(cudaStreamSynchronize(st));
+            finish(g, prn, out[i]);
+            ++guard_count_;
+        }
+    }
+}
+
+void Pcps::acquire_grid(const void* input, r4wb_fmt fmt, uint64_t n_input, const int8_t* code, uint64_t code_len,
+                        double* power_out, uint64_t cap)
+{
+    const uint64_t cells = (uint64_t)num_bins() * code_length_;
+    if (cap < cells) fail(R4WB_ERR_INVALID_SIZE, "grid buffer holds %llu of %llu cells", (unsigned long long)cap, (unsigned long long)cells);
+    if (cells == 0) return;
+    cudaStream_t st = current_stream();
+    const size_t bps = fmt == R4WB_FMT_CF64 ? 16 : 8;
+    d_in_.reserve(std::max<size_t>(n_input * bps, 16));
+    if (n_input) R4WB_CUDA(cudaMemcpyAsync(d_in_.p, input, n_input * bps, cudaMemcpyHostToDevice, st));
+    d_codes_.reserve(std::max<size_t>(code_len, 16));
+    if (code_len) R4WB_CUDA(cudaMemcpyAsync(d_codes_.p, code, code_len, cudaMemcpyHostToDevice, st));
+    d_grid_.reserve(cells);
+    d_pairpeaks_.reserve(2);
+    run<double>(w64_, d_in_.p, fmt, 0, 1, 0, n_input, d_codes_.p, code_len, 0, 1, d_pairpeaks_.p, d_grid_.p);
+    R4WB_CUDA(cudaMemcpyAsync(power_out, d_grid_.p, cells * sizeof(double), cudaMemcpyDeviceToHost, st));
+    R4WB_CUDA(cudaStreamSynchronize(st));
+}
+
+}  // namespace r4wb

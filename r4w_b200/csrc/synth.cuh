@@ -96,6 +96,7 @@ struct SynthArgs {
     uint32_t n_sats;
     uint32_t nw64;             // 64-bit words of the per-satellite half-chip sign table
     uint32_t flags;
+    uint32_t out_aligned16;    // out is 16-byte aligned: sample pairs may be stored as one float4
     uint64_t delta46;
     uint32_t kmul;
     uint32_t cj[8];
@@ -104,16 +105,54 @@ struct SynthArgs {
     uint64_t seed;
 };
 
+// Host-only model of a scenario: everything GnssScenario::new derives from the config (gnss/scenario.rs:78-237)
+// plus the constant tables the kernels read.  No CUDA calls — tests/emu/ builds it without a GPU.
+struct ScenarioModel {
+    explicit ScenarioModel(const r4wb_scenario_cfg& cfg);
+
+    ScenConst sc{};
+    std::vector<SatConst> sats;
+    std::vector<r4wb_sat_cfg> cfg_sats;
+    r4wb_scenario_cfg cfg{};
+    std::vector<PhaseSegment> segments;
+    std::vector<uint32_t> codebits;     // [n_sats][128]
+    float taps_f[64];
+    float etab_f[64];
+    int tile_k = 10;                    // samples per tile = 256 threads * 2 * tile_k
+    uint32_t nw64 = 0;
+    bool any_dynamic = false, any_var_visibility = false;
+
+    uint64_t n_blocks() const { return sc.B ? (sc.total + sc.B - 1) / sc.B : 0; }
+    // first canonical block a table must start at so that block b0's entries are complete
+    uint64_t table_begin(uint64_t b0) const { return (any_dynamic || any_var_visibility) ? 0 : (b0 > 0 ? b0 - 1 : 0); }
+    void status(uint64_t current, r4wb_sat_status* out, uint32_t cap, uint32_t* n) const;
+};
+
+// sequential-API state (generate_block with caller-chosen block sizes)
+struct SeqState {
+    std::vector<uint64_t> m;            // visible samples so far (static-phase satellites)
+    std::vector<uint64_t> phi;          // carrier phase, cycles 0.64 (dynamic satellites)
+    std::vector<BlockSat> prev;         // last visible block per satellite
+    std::vector<uint8_t> has_prev;
+    void reset(size_t n_sats);
+    // two-row table (row 0 = each satellite's last visible block, row 1 = the block [first, first+n))
+    void make_table(const ScenarioModel& md, uint64_t first, uint32_t n, std::vector<BlockSat>& tab, BlockHdr hdr[2]) const;
+    void advance(const ScenarioModel& md, const std::vector<BlockSat>& tab, uint32_t n);
+};
+
+size_t synth_smem_bytes(uint32_t n_sats, uint32_t nw64);
+int synth_tile_samples(int K);
+
 class Scenario {
 public:
     explicit Scenario(const r4wb_scenario_cfg& cfg);
     ~Scenario();
 
-    uint64_t total_samples() const { return sc_.total; }
-    uint64_t block_size() const { return sc_.B; }
+    uint64_t total_samples() const { return md_.sc.total; }
+    uint64_t block_size() const { return md_.sc.B; }
     uint64_t current_sample() const { return current_; }
-    bool is_done() const { return current_ >= sc_.total; }
-    double progress() const { return sc_.total == 0 ? 1.0 : (double)current_ / (double)sc_.total; }
+    bool is_done() const { return current_ >= md_.sc.total; }
+    double progress() const { return md_.sc.total == 0 ? 1.0 : (double)current_ / (double)md_.sc.total; }
     void reset();
 
     // canonical-partition random access; dst is device or host memory
@@ -121,7 +160,7 @@ public:
     // one reference block of min(n, remaining) samples at current_sample
     uint64_t generate_block(uint64_t n, void* dst, r4wb_mem where, r4wb_fmt fmt);
     double last_power_sum();
-    void status(r4wb_sat_status* out, uint32_t cap, uint32_t* n) const;
+    void status(r4wb_sat_status* out, uint32_t cap, uint32_t* n) const { md_.status(current_, out, cap, n); }
     // test hook: entry of canonical block `block`, satellite `sat` -> 12 doubles
     void debug_block(uint64_t block, uint32_t sat, double* out12);
 
@@ -131,21 +170,9 @@ private:
     void build_canonical_table(uint64_t blk_begin, uint64_t blk_end);   // fills d_tab_/d_hdr_ for [blk_begin, blk_end)
     void render_to(uint64_t first, uint64_t n, void* dst, r4wb_mem where, r4wb_fmt fmt);
 
-    ScenConst sc_{};
-    std::vector<SatConst> sats_;
-    std::vector<r4wb_sat_cfg> cfg_sats_;
-    r4wb_scenario_cfg cfg_{};
-    std::vector<PhaseSegment> segments_;
+    ScenarioModel md_;
     uint64_t current_ = 0;
-    int tile_k_ = 5;
-    uint32_t nw64_ = 0;
-    bool any_dynamic_ = false, any_var_visibility_ = false;
-
-    // sequential-API state (generate_block)
-    std::vector<uint64_t> seq_m_;       // visible samples so far (static-phase satellites)
-    std::vector<uint64_t> seq_phi_;     // carrier phase, cycles 0.64 (dynamic satellites)
-    std::vector<BlockSat> seq_prev_;    // last visible block per satellite
-    std::vector<uint8_t> seq_has_prev_;
+    SeqState seq_;
 
     // device state
     DevBuf<SatConst> d_sat_;
@@ -156,7 +183,8 @@ private:
     DevBuf<BlockHdr> d_hdr_, d_seq_hdr_;
     DevBuf<double> d_power_;
     DevBuf<unsigned char> d_stage_;
-    uint64_t tab_blk0_ = 0;             // canonical index of d_tab_'s first block
+    uint64_t tab_blk0_ = 0, tab_blk1_ = 0;   // canonical block range currently held by d_tab_
+    bool tab_valid_ = false;
 };
 
 }  // namespace r4wb

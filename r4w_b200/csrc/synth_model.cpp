@@ -1,0 +1,296 @@
+// synth_model.cpp — host-only model of GnssScenario::new (gnss/scenario.rs:78-237): constants, code bits,
+// filter tables, the piecewise-exact Doppler phase table, sequential-block bookkeeping, satellite_status.
+// No CUDA runtime calls in this file.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "synth_math.cuh"
+
+namespace r4wb {
+
+static const uint8_t kE1Packed[2 * 50 * 512] = {
+#include "../../data/galileo_e1_codes.inc"
+};
+
+// chip i of PRN `prn` on `channel` (0 = E1B, 1 = E1C) as a sign bit (1 <=> -1):
+// MSB-first packing, bit 0 -> +1 (gnss/galileo_e1_codes.rs:17-25)
+static inline uint32_t e1_sign_bit(uint32_t channel, uint32_t prn, uint32_t i)
+{
+    const uint8_t* p = kE1Packed + ((size_t)channel * 50 + (prn - 1)) * 512;
+    return (p[i >> 3] >> (7 - (i & 7))) & 1u;
+}
+
+void e1_code_chips(uint32_t channel, uint32_t prn, int8_t* out)
+{
+    for (uint32_t i = 0; i < (uint32_t)kCodeLen; ++i) out[i] = e1_sign_bit(channel, prn, i) ? -1 : 1;
+}
+
+// 63-tap Blackman windowed-sinc low-pass, unity DC gain (core/filters/fir.rs:458-499, windows.rs:137-151)
+static void design_lowpass(double cutoff_hz, double rate_hz, double* h /*[63]*/)
+{
+    const double fc = cutoff_hz / rate_hz, mid = (kTaps - 1) / 2.0;
+    double sum = 0.0;
+    for (int i = 0; i < kTaps; ++i) {
+        const double x = 2.0 * kPi * (double)i / (double)(kTaps - 1);
+        const double w = 0.42 - 0.5 * cos(x) + 0.08 * cos(2.0 * x);
+        const double n = (double)i - mid;
+        const double sinc = fabs(n) < 1e-10 ? 2.0 * kPi * fc : sin(2.0 * kPi * fc * n) / n;
+        h[i] = sinc * w;
+    }
+    for (int i = 0; i < kTaps; ++i) sum += h[i];
+    if (fabs(sum) > 1e-10)
+        for (int i = 0; i < kTaps; ++i) h[i] /= sum;
+}
+
+// Piecewise-exact model of `phase += inc` repeated `steps` times in f64 (gnss/scenario.rs:518-527):
+// inside one binade every add moves the phase by the same multiple of the binade's ulp.
+static void build_phase_segments(double inc, uint64_t steps, std::vector<PhaseSegment>& out)
+{
+    double x = 0.0;
+    uint64_t i = 0;
+    auto push = [&](uint64_t i0, double x0, double step) { out.push_back(PhaseSegment{i0, x0, step}); };
+    if (inc == 0.0 || steps == 0) { out.push_back(PhaseSegment{0, 0.0, inc}); return; }
+    while (i < steps) {
+        const double x1 = x + inc, s1 = x1 - x;
+        const double x2 = x1 + inc, s2 = x2 - x1;
+        if (x != 0.0 && s1 == s2 && std::ilogb(x) == std::ilogb(x1) && std::ilogb(x1) == std::ilogb(x2)) {
+            const int e = std::ilogb(x);
+            const long double limit = std::ldexp(1.0L, e + 1);
+            const long double room = (limit - fabsl((long double)x)) / fabsl((long double)s1);
+            long long fit = (long long)floorl(room) - 2;
+            if (fit >= 3) {
+                const uint64_t n = std::min<uint64_t>((uint64_t)fit, steps - i);
+                push(i, x, s1);
+                const long long X0 = (long long)std::scalbn(x, 52 - e), S = (long long)std::scalbn(s1, 52 - e);
+                x = std::scalbn((double)(X0 + (long long)n * S), e - 52);
+                i += n;
+                continue;
+            }
+        }
+        push(i, x, s1);
+        x = x1;
+        i += 1;
+    }
+    if ((int)out.size() > kMaxSegments) fail(R4WB_ERR_NOT_SUPPORTED, "phase model needs %zu segments", out.size());
+}
+
+static inline uint64_t gcd_u64(uint64_t a, uint64_t b) { while (b) { uint64_t t = a % b; a = b; b = t; } return a; }
+
+ScenarioModel::ScenarioModel(const r4wb_scenario_cfg& c_in) : cfg(c_in)
+{
+    if (cfg.n_sats > (uint32_t)kMaxSats) fail(R4WB_ERR_NOT_SUPPORTED, "at most %d satellites per scenario", kMaxSats);
+    if (cfg.n_sats && !c_in.sats) fail(R4WB_ERR_NULL_POINTER, "sats is NULL");
+    cfg_sats.assign(c_in.sats, c_in.sats + c_in.n_sats);
+    cfg.sats = cfg_sats.data();
+    const r4wb_output_cfg& oc = cfg.output;
+    if (!(oc.sample_rate > 0.0) || !(oc.duration_s >= 0.0)) fail(R4WB_ERR_INVALID_PARAMETER, "sample_rate/duration_s");
+
+    sc.fs = oc.sample_rate;
+    sc.t0_gps = oc.start_time_gps_s;
+    sc.duration_s = oc.duration_s;
+    sc.total = (uint64_t)std::ceil(oc.duration_s * oc.sample_rate);                       // scenario.rs:80
+    sc.B = oc.block_size > 0 ? oc.block_size : (uint64_t)std::ceil(oc.sample_rate * 0.001);   // scenario.rs:667-674
+    if (sc.B < 8 || sc.B > 65536) fail(R4WB_ERR_NOT_SUPPORTED, "block size %llu outside [8, 65536]", (unsigned long long)sc.B);
+    sc.n_sats = cfg.n_sats;
+    sc.flags = cfg.flags;
+    sc.antenna = cfg.receiver.antenna;
+    sc.ant_peak = cfg.receiver.antenna_peak_gain_dbi;
+    sc.ant_bw = cfg.receiver.antenna_beamwidth_deg;
+    sc.elev_mask_deg = cfg.receiver.elevation_mask_deg;
+    sc.seed = oc.seed;
+
+    // receiver model (scenario.rs:160-183, 320-353)
+    RxModel& rx = sc.rx;
+    rx.position = Lla{cfg.receiver.position.lat_deg, cfg.receiver.position.lon_deg, cfg.receiver.position.alt_m};
+    rx.has_trajectory = cfg.receiver.has_trajectory ? 1 : 0;
+    rx.traj_start = Lla{cfg.receiver.traj_start.lat_deg, cfg.receiver.traj_start.lon_deg, cfg.receiver.traj_start.alt_m};
+    rx.traj_end = Lla{cfg.receiver.traj_end.lat_deg, cfg.receiver.traj_end.lon_deg, cfg.receiver.traj_end.alt_m};
+    rx.travel_time_s = 1.0;
+    rx.fd_dt = 0.01;
+    if (rx.has_trajectory) {
+        const double dist = 6371000.0 * gc_angle(rx.traj_start, rx.traj_end);           // scenario_config.rs:358-368
+        const double speed = cfg.receiver.traj_has_speed ? cfg.receiver.traj_speed_mps : dist / oc.duration_s;
+        rx.travel_time_s = dist / speed;
+        rx.fd_dt = std::min(0.01, rx.travel_time_s * 0.001);
+    }
+
+    // code NCO constants.  The reference computes samples_per_chip = (8 fs) / chipping_rate in f64.
+    sc.chip_rate = 1023000.0;
+    const double os_rate = oc.sample_rate * (double)kOversample;
+    sc.spc = os_rate / sc.chip_rate;
+    if (os_rate != std::floor(os_rate) || os_rate >= 9007199254740992.0)
+        fail(R4WB_ERR_NOT_SUPPORTED, "sample_rate must be an integer number of Hz");
+    const uint64_t os_i = (uint64_t)os_rate, cr_i = 1023000ull, g = gcd_u64(os_i, cr_i);
+    sc.ratA = os_i / g;
+    sc.ratB = cr_i / g;
+    if (sc.ratA >= (1ull << 40)) fail(R4WB_ERR_NOT_SUPPORTED, "sample_rate / chip rate ratio too fine");
+    sc.delta = (double)((long double)sc.spc * (long double)sc.ratB / (long double)sc.ratA - 1.0L);
+    sc.delta46 = (uint64_t)floorl(140737488355328.0L / (long double)sc.spc);
+    const double S = sc.spc * 0.5;   // oversamples per half-chip
+    if (S * 4.0 < (double)(kTaps - 1) || S >= 60.0)
+        fail(R4WB_ERR_NOT_SUPPORTED, "sample_rate %.0f Hz outside the supported 3.97-15.3 MHz span", oc.sample_rate);
+    sc.kmul = (uint32_t)llround(S * 16777216.0);
+    for (int j = 0; j < 8; ++j) sc.cj[j] = (uint32_t)std::min<long long>(llround((double)j * S * 16777216.0), 0xffffffffll);
+    {
+        const uint64_t D = sc.ratA / gcd_u64(2 * sc.ratB, sc.ratA);
+        sc.lattice_den = D <= (1ull << 17) ? D : 0;
+    }
+    {
+        const double nf_lin = std::pow(10.0, cfg.receiver.noise_figure_db / 10.0);       // scenario.rs:532-537
+        const double n0 = 1.380649e-23 * 290.0 * nf_lin;
+        sc.noise_std = (float)(std::sqrt(n0 * oc.sample_rate / 2.0) * 1e8);
+    }
+
+    // satellites
+    const RxState rx0 = rx_at(rx, 0.0);
+    sats.resize(cfg.n_sats);
+    codebits.assign((size_t)std::max(1u, cfg.n_sats) * 128, 0u);
+    for (uint32_t k = 0; k < cfg.n_sats; ++k) {
+        const r4wb_sat_cfg& c = cfg_sats[k];
+        if (c.signal != R4WB_SIG_GALILEO_E1C)
+            fail(R4WB_ERR_NOT_SUPPORTED, "satellite %u: only GalileoE1C is implemented on the GPU path", k);
+        if (c.prn < 1 || c.prn > 50) fail(R4WB_ERR_INVALID_PARAMETER, "Galileo PRN must be 1-50, got %u", c.prn);
+        if (c.plane >= 3 || c.slot >= 10) fail(R4WB_ERR_INVALID_PARAMETER, "Galileo plane 0-2 / slot 0-9");
+        if (!(c.has & R4WB_HAS_IONO) && cfg.environment.ionosphere_enabled)
+            fail(R4WB_ERR_NOT_SUPPORTED, "satellite %u: Klobuchar model needed (no iono_delay_m override)", k);
+        if (!(c.has & R4WB_HAS_TROPO) && cfg.environment.troposphere_enabled)
+            fail(R4WB_ERR_NOT_SUPPORTED, "satellite %u: Saastamoinen model needed (no tropo_delay_m override)", k);
+        SatConst& s = sats[k];
+        std::memset(&s, 0, sizeof s);
+        s.orbit = nominal_orbit(c.signal, c.plane, c.slot);
+        s.carrier_hz = 1575420000.0;
+        s.has = c.has;
+        s.orbital_dynamics = c.orbital_dynamics ? 1u : 0u;
+        s.tx_power_dbw = c.tx_power_dbw;
+        s.elevation_deg = c.elevation_deg; s.range_m = c.range_m; s.range_rate_mps = c.range_rate_mps;
+        s.doppler_hz = c.doppler_hz; s.doppler_rate_hz_per_s = c.doppler_rate_hz_per_s; s.cn0_dbhz = c.cn0_dbhz;
+        s.iono_delay_m = c.iono_delay_m; s.tropo_delay_m = c.tropo_delay_m;
+        const bool doppler_from_orbit = c.orbital_dynamics || (!(c.has & R4WB_HAS_DOPPLER) && !(c.has & R4WB_HAS_RANGE_RATE));
+        const bool range_from_orbit = c.orbital_dynamics || !(c.has & R4WB_HAS_RANGE);
+        s.needs_orbit = (doppler_from_orbit || range_from_orbit || !(c.has & R4WB_HAS_ELEVATION)) ? 1u : 0u;
+        const bool const_doppler = !c.orbital_dynamics && (((c.has & R4WB_HAS_DOPPLER) && !(c.has & R4WB_HAS_DOPPLER_RATE)) ||
+                                                            (!(c.has & R4WB_HAS_DOPPLER) && (c.has & R4WB_HAS_RANGE_RATE)));
+        s.static_phase = (const_doppler && (c.has & R4WB_HAS_ELEVATION)) ? 1u : 0u;
+        if (!(c.has & R4WB_HAS_ELEVATION)) any_var_visibility = true;
+        if (!s.static_phase) any_dynamic = true;
+        // orbital anchors at t0 (scenario.rs:195-204)
+        Vec3 sp, sv;
+        orbit_state(s.orbit, sc.t0_gps, sp, sv);
+        s.orb_range_t0 = look_from(rx0.pos, rx0.lla, sp).range_m;
+        s.orb_doppler_t0 = -los_rate(rx0.pos, rx0.vel, sp, sv) * s.carrier_hz / kC;
+        // constant-Doppler satellites: segments of the sequential f64 phase accumulation
+        s.seg_begin = (int32_t)segments.size();
+        if (s.static_phase) {
+            const double dop = (c.has & R4WB_HAS_DOPPLER) ? c.doppler_hz : -c.range_rate_mps * s.carrier_hz / kC;
+            const double inc = 2.0 * kPi * dop / sc.fs;                                  // scenario.rs:522
+            std::vector<PhaseSegment> segs;
+            build_phase_segments(inc, sc.total, segs);
+            segments.insert(segments.end(), segs.begin(), segs.end());
+        }
+        s.seg_count = (int32_t)segments.size() - s.seg_begin;
+        for (uint32_t i = 0; i < (uint32_t)kCodeLen; ++i)
+            codebits[(size_t)k * 128 + (i >> 5)] |= e1_sign_bit(1, c.prn, i) << (i & 31);
+    }
+    if (segments.empty()) segments.push_back(PhaseSegment{0, 0.0, 0.0});
+
+    // filter: FirFilter::lowpass(lpf_cutoff or fs/2, 8 fs, 63)  (scenario.rs:209-217)
+    double h[kTaps];
+    design_lowpass(oc.lpf_cutoff_hz > 0.0 ? oc.lpf_cutoff_hz : oc.sample_rate / 2.0, os_rate, h);
+    double run = 0.0;
+    for (int d = 0; d < 64; ++d) {
+        taps_f[d] = 0.0f;
+        if (d < kTaps) { taps_f[d] = (float)h[d]; run += h[d]; }
+        etab_f[d] = d >= kTaps - 1 ? 1.0f : (float)run;      // window fully covered -> sum h = 1
+    }
+
+    tile_k = 10;
+    {
+        const double span = std::ceil((double)synth_tile_samples(tile_k) * kOversample * (2.0 / sc.spc)) + 2.0;
+        nw64 = (uint32_t)std::ceil((span + 8.0) / 32.0) + 1u;
+    }
+}
+
+// GnssScenario::satellite_status (scenario.rs:564-633): static receiver position, zero receiver velocity
+void ScenarioModel::status(uint64_t current, r4wb_sat_status* out, uint32_t cap, uint32_t* n_out) const
+{
+    if (cap < sc.n_sats) fail(R4WB_ERR_INVALID_SIZE, "status buffer holds %u of %u satellites", cap, sc.n_sats);
+    const double t = sc.t0_gps + (double)current / sc.fs;
+    const Lla rx_lla = sc.rx.position;
+    const Vec3 rx_pos = ecef_of(rx_lla), zero{0.0, 0.0, 0.0};
+    for (uint32_t k = 0; k < sc.n_sats; ++k) {
+        const r4wb_sat_cfg& c = cfg_sats[k];
+        Vec3 sp, sv;
+        orbit_state(sats[k].orbit, t, sp, sv);
+        const Look la = look_from(rx_pos, rx_lla, sp);
+        r4wb_sat_status& o = out[k];
+        std::memset(&o, 0, sizeof o);
+        o.signal = c.signal; o.prn = c.prn;
+        o.range_m = (c.has & R4WB_HAS_RANGE) ? c.range_m : la.range_m;
+        o.elevation_deg = (c.has & R4WB_HAS_ELEVATION) ? c.elevation_deg : la.elevation_deg;
+        o.azimuth_deg = (c.has & R4WB_HAS_AZIMUTH) ? c.azimuth_deg : la.azimuth_deg;
+        o.range_rate_mps = (c.has & R4WB_HAS_RANGE_RATE) ? c.range_rate_mps : los_rate(rx_pos, zero, sp, sv);
+        o.doppler_hz = (c.has & R4WB_HAS_DOPPLER) ? c.doppler_hz : -o.range_rate_mps * sats[k].carrier_hz / kC;
+        o.antenna_gain_dbi = antenna_gain_dbi(sc.antenna, sc.ant_peak, sc.ant_bw, o.elevation_deg);
+        o.cn0_dbhz = (c.has & R4WB_HAS_CN0) ? c.cn0_dbhz
+                                            : c.tx_power_dbw - fspl_db(o.range_m, sats[k].carrier_hz) + o.antenna_gain_dbi + 204.0;
+        o.iono_delay_m = (c.has & R4WB_HAS_IONO) ? c.iono_delay_m : 0.0;
+        o.tropo_delay_m = (c.has & R4WB_HAS_TROPO) ? c.tropo_delay_m : 0.0;
+        o.visible = o.elevation_deg > 0.0 ? 1 : 0;
+        o.clock_correction_s = 0.0;
+    }
+    if (n_out) *n_out = sc.n_sats;
+}
+
+// ---------------------------------------------------------------------------------------------- sequential API
+void SeqState::reset(size_t n_sats)
+{
+    m.assign(n_sats, 0);
+    phi.assign(n_sats, 0);
+    prev.assign(n_sats, BlockSat{});
+    has_prev.assign(n_sats, 0);
+}
+
+void SeqState::make_table(const ScenarioModel& md, uint64_t first, uint32_t n, std::vector<BlockSat>& tab, BlockHdr hdr[2]) const
+{
+    const uint32_t ns = md.sc.n_sats;
+    tab.assign((size_t)2 * std::max(1u, ns), BlockSat{});
+    for (uint32_t s = 0; s < ns; ++s) {
+        BlockSat cur;
+        fill_block_sat(md.sc, md.sats[s], md.segments.data(), first, n, md.sats[s].static_phase ? m[s] : phi[s], cur);
+        cur.prev = has_prev[s] ? (int32_t)s : -1;
+        tab[s] = prev[s];
+        tab[ns + s] = cur;
+    }
+    hdr[0] = BlockHdr{0, 0, 0};
+    hdr[1] = BlockHdr{first, n, 0};
+}
+
+void SeqState::advance(const ScenarioModel& md, const std::vector<BlockSat>& tab, uint32_t n)
+{
+    const uint32_t ns = md.sc.n_sats;
+    for (uint32_t s = 0; s < ns; ++s) {
+        const BlockSat& cur = tab[ns + s];
+        if (!(cur.flags & 1u)) continue;
+        m[s] += n;
+        if (!md.sats[s].static_phase) phi[s] += block_advance(cur);
+        prev[s] = cur;
+        prev[s].prev = -1;
+        has_prev[s] = 1;
+    }
+}
+
+size_t synth_smem_bytes(uint32_t n_sats, uint32_t nw64)
+{
+    size_t b = 63 * 32 * 4 + 32 * 8 * 16 + 64 * 4;
+    b += (size_t)n_sats * 128 * 4;
+    b += (size_t)n_sats * sizeof(TileSat);
+    b += (size_t)n_sats * nw64 * 8;
+    b += (size_t)n_sats * (nw64 + 1) * 4;
+    b += (size_t)n_sats * 8 * 4;
+    return (b + 15) & ~(size_t)15;
+}
+
+int synth_tile_samples(int K) { return 256 * 2 * K; }
+
+}  // namespace r4wb

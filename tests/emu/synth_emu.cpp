@@ -1,0 +1,228 @@
+// synth_emu.cpp — HOST REPLAY of the synthesis kernels' per-sample arithmetic (r4w_b200/csrc/synth_math.cuh).
+//
+// TEST INFRASTRUCTURE ONLY.  This container has no GPU; this file lets `-m "not gpu"` tests check the device
+// index arithmetic (code NCO, collapsed FIR, carrier NCO, Philox noise) against the oracle by calling the same
+// __host__ __device__ functions the sm_100a kernels call, in plain loops that mirror k_block_params,
+// k_phase_scan and k_synth.  It is never linked into or loaded by libr4w_b200.so / r4w_b200/.
+#include <algorithm>
+#include <cstring>
+#include <memory>
+#include <vector>
+
+#include "../../r4w_b200/csrc/synth_math.cuh"
+
+using namespace r4wb;
+
+namespace {
+
+struct Emu {
+    ScenarioModel md;
+    SeqState seq;
+    uint64_t current = 0;
+    std::vector<BlockSat> tab;
+    std::vector<BlockHdr> hdr;
+    uint64_t tab_blk0 = 0, tab_blk1 = 0;
+    bool tab_valid = false;
+    explicit Emu(const r4wb_scenario_cfg& c) : md(c) { seq.reset(md.sc.n_sats); }
+
+    // k_block_params + k_phase_scan
+    void build_table(uint64_t blk_begin, uint64_t blk_end)
+    {
+        if (tab_valid && blk_begin >= tab_blk0 && blk_end <= tab_blk1 && (blk_begin == tab_blk0 || !(md.any_dynamic || md.any_var_visibility))) return;
+        const ScenConst& sc = md.sc;
+        const uint32_t ns = sc.n_sats;
+        const uint64_t nblk = blk_end - blk_begin;
+        tab.assign((size_t)nblk * std::max(1u, ns), BlockSat{});
+        hdr.assign(nblk, BlockHdr{});
+        for (uint64_t tb = 0; tb < nblk; ++tb) {
+            const uint64_t first = (blk_begin + tb) * sc.B;
+            const uint64_t rem = sc.total - first;
+            const uint32_t n = (uint32_t)(rem < sc.B ? rem : sc.B);
+            hdr[tb] = BlockHdr{first, n, 0};
+            for (uint32_t s = 0; s < ns; ++s) {
+                BlockSat o;
+                fill_block_sat(sc, md.sats[s], md.segments.data(), first, n, first, o);
+                o.prev = tb > 0 ? (int32_t)((tb - 1) * ns + s) : -1;
+                if (!md.sats[s].static_phase) o.phi = (o.flags & 1u) ? block_advance(o) : 0ull;
+                tab[tb * ns + s] = o;
+            }
+        }
+        if (md.any_dynamic || md.any_var_visibility) {
+            for (uint32_t s = 0; s < ns; ++s) {
+                const bool dynamic = !md.sats[s].static_phase;
+                uint64_t run = 0;
+                int prev = -1;
+                for (uint64_t b = 0; b < nblk; ++b) {
+                    BlockSat& e = tab[b * ns + s];
+                    const uint64_t adv = e.phi;
+                    if (dynamic) { e.phi = run; run += adv; }
+                    e.prev = prev >= 0 ? (int32_t)((uint32_t)prev * ns + s) : -1;
+                    if (e.flags & 1u) prev = (int)b;
+                }
+            }
+        }
+        tab_blk0 = blk_begin; tab_blk1 = blk_end; tab_valid = true;
+    }
+
+    // k_synth, thread loops flattened.  only_sat >= 0 renders that satellite alone.
+    void render(const BlockSat* tb_tab, const BlockHdr* tb_hdr, uint32_t tb_begin, uint32_t tb_count, uint64_t out_first,
+                uint64_t out_n, float* out, uint64_t max_block_n, int only_sat, uint64_t* n_ambiguous)
+    {
+        const ScenConst& sc = md.sc;
+        const uint32_t ns = sc.n_sats, nw64 = md.nw64;
+        const int K = md.tile_k, kThreads = 256;
+        const uint32_t TILE = (uint32_t)synth_tile_samples(K);
+        const uint32_t tiles_per_block = (uint32_t)((max_block_n + TILE - 1) / TILE);
+        std::vector<float> erep(63 * 32);
+        std::vector<float4> coef(32 * 8);
+        for (uint32_t k = 0; k < 63 * 32; ++k) erep[k] = md.etab_f[k >> 5];
+        for (uint32_t k = 0; k < 32 * 8; ++k) coef[k] = coef_entry(k >> 3);
+        const uint64_t d8 = sc.delta46 * (uint64_t)kOversample;
+        std::vector<TileSat> tsat(std::max(1u, ns));
+        std::vector<uint32_t> w32((size_t)std::max(1u, ns) * (nw64 + 1));
+        std::vector<uint2> t64((size_t)std::max(1u, ns) * nw64);
+        std::vector<float> yfix((size_t)std::max(1u, ns) * 8);
+        const bool noise = !(sc.flags & R4WB_FLAG_NOISE_OFF);
+
+        for (uint32_t tile = 0; tile < tb_count * tiles_per_block; ++tile) {
+            const uint32_t tb = tb_begin + tile / tiles_per_block, chunk = tile % tiles_per_block;
+            const BlockHdr hd = tb_hdr[tb];
+            const uint32_t i_begin = chunk * TILE;
+            if (i_begin >= hd.n) continue;
+            const uint32_t i_end = std::min(hd.n, i_begin + TILE);
+            if (hd.first + i_end <= out_first || hd.first + i_begin >= out_first + out_n) continue;
+            const BlockSat* row = tb_tab + (size_t)tb * ns;
+            for (uint32_t s = 0; s < ns; ++s) tsat[s] = tile_sat(row[s], i_begin, d8);
+            for (uint32_t k = 0; k < ns * (nw64 + 1); ++k) {
+                const uint32_t s = k / (nw64 + 1), w = k - s * (nw64 + 1);
+                w32[k] = sign_word(md.codebits.data() + s * 128, tsat[s].hb, w);
+            }
+            for (uint32_t k = 0; k < ns * nw64; ++k) {
+                const uint32_t s = k / nw64, w = k - s * nw64;
+                t64[k] = make_uint2(w32[s * (nw64 + 1) + w], w32[s * (nw64 + 1) + w + 1]);
+            }
+            if (chunk == 0)
+                for (uint32_t k = 0; k < ns * 8; ++k) {
+                    const uint32_t s = k >> 3, i = k & 7u;
+                    float y = 0.0f;
+                    if ((row[s].flags & 1u) && i < hd.n)
+                        y = fir_direct(row[s], tb_tab, md.codebits.data() + s * 128, md.taps_f, (int)i, sc.delta46, sc.spc);
+                    yfix[k] = y;
+                }
+            for (uint32_t tid = 0; tid < (uint32_t)kThreads; ++tid) {
+                const uint32_t lane = tid & 31u;
+                for (int k = 0; k < K; ++k) {
+                    const uint32_t ia = i_begin + 2 * tid + 2 * kThreads * k;
+                    if (ia >= i_end) continue;
+                    float2 v[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+                    for (uint32_t s = 0; s < ns; ++s) {
+                        if (only_sat >= 0 && (int)s != only_sat) continue;
+                        const TileSat ts = tsat[s];
+                        if (!(ts.flags & 1u)) continue;
+                        for (uint32_t j = 0; j < 2; ++j) {
+                            const uint32_t i = ia + j;
+                            if (i >= i_end) continue;
+                            const uint64_t u = ts.u0 + (uint64_t)(i - i_begin) * d8;
+                            bool amb = false;
+                            float y = fir_fast(u, ts, t64.data() + s * nw64, erep.data(), coef.data(), sc.kmul, sc.cj, lane, amb);
+                            if (amb) {
+                                y = fir_direct(row[s], tb_tab, md.codebits.data() + s * 128, md.taps_f, (int)i, sc.delta46, sc.spc);
+                                if (n_ambiguous) ++*n_ambiguous;
+                            }
+                            if (chunk == 0 && i < 8) y = yfix[s * 8 + i];
+                            rotate_acc(y * ts.amp, carrier_phase(ts, i), v[j].x, v[j].y);
+                        }
+                    }
+                    for (uint32_t j = 0; j < 2; ++j) {
+                        const uint32_t i = ia + j;
+                        if (i >= i_end) continue;
+                        const uint64_t m = hd.first + i;
+                        if (m < out_first || m >= out_first + out_n) continue;
+                        float2 val = v[j];
+                        if (noise && only_sat < 0) {
+                            const float2 g = noise_of_sample(m, sc.seed);
+                            val.x = fmaf(g.x, sc.noise_std, val.x);
+                            val.y = fmaf(g.y, sc.noise_std, val.y);
+                        }
+                        out[2 * (m - out_first)] = val.x;
+                        out[2 * (m - out_first) + 1] = val.y;
+                    }
+                }
+            }
+        }
+    }
+};
+
+thread_local std::string g_err;
+
+template <typename F>
+int guard(F&& f)
+{
+    try { f(); return 0; }
+    catch (const Failure& e) { g_err = e.what; return (int)e.code; }
+    catch (const std::exception& e) { g_err = e.what(); return -1; }
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* emu_last_error(void) { return g_err.c_str(); }
+
+int emu_scenario_create(const r4wb_scenario_cfg* cfg, void** out)
+{
+    *out = nullptr;
+    return guard([&] { *out = new Emu(*cfg); });
+}
+void emu_scenario_destroy(void* h) { delete static_cast<Emu*>(h); }
+uint64_t emu_scenario_total_samples(void* h) { return static_cast<Emu*>(h)->md.sc.total; }
+uint64_t emu_scenario_block_size(void* h) { return static_cast<Emu*>(h)->md.sc.B; }
+uint32_t emu_scenario_segments(void* h) { return (uint32_t)static_cast<Emu*>(h)->md.segments.size(); }
+
+// canonical-partition random access (mirror of Scenario::generate)
+int emu_scenario_generate(void* h, uint64_t first, uint64_t n, float* out_cf32, int only_sat, uint64_t* n_ambiguous)
+{
+    Emu* e = static_cast<Emu*>(h);
+    return guard([&] {
+        const ScenConst& sc = e->md.sc;
+        if (first > sc.total || n > sc.total - first) fail(R4WB_ERR_INVALID_SIZE, "range exceeds total_samples");
+        if (n == 0) return;
+        if (n_ambiguous) *n_ambiguous = 0;
+        const uint64_t b0 = first / sc.B, b1 = (first + n - 1) / sc.B;
+        e->build_table(e->md.table_begin(b0), b1 + 1);
+        e->render(e->tab.data(), e->hdr.data(), (uint32_t)(b0 - e->tab_blk0), (uint32_t)(b1 - b0 + 1), first, n, out_cf32, sc.B,
+                  only_sat, n_ambiguous);
+    });
+}
+
+// sequential API (mirror of Scenario::generate_block)
+int emu_scenario_generate_block(void* h, uint64_t n_req, float* out_cf32, uint64_t* written)
+{
+    Emu* e = static_cast<Emu*>(h);
+    *written = 0;
+    return guard([&] {
+        const ScenConst& sc = e->md.sc;
+        const uint64_t remaining = sc.total > e->current ? sc.total - e->current : 0;
+        const uint64_t n = std::min(remaining, n_req);
+        if (n == 0) return;
+        std::vector<BlockSat> tab;
+        BlockHdr hdr[2];
+        e->seq.make_table(e->md, e->current, (uint32_t)n, tab, hdr);
+        e->render(tab.data(), hdr, 1, 1, e->current, n, out_cf32, n, -1, nullptr);
+        e->seq.advance(e->md, tab, (uint32_t)n);
+        e->current += n;
+        *written = n;
+    });
+}
+
+int emu_block_params(void* h, uint64_t block, uint32_t sat, double* out12)
+{
+    Emu* e = static_cast<Emu*>(h);
+    return guard([&] {
+        if (block >= e->md.n_blocks() || sat >= e->md.sc.n_sats) fail(R4WB_ERR_INVALID_PARAMETER, "block/sat out of range");
+        e->build_table(e->md.table_begin(block), block + 1);
+        block_sat_debug(e->tab[(size_t)(block - e->tab_blk0) * e->md.sc.n_sats + sat], out12);
+    });
+}
+
+}  // extern "C"
