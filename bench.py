@@ -1,0 +1,367 @@
+#!/usr/bin/env python
+"""bench.py — GNSS IQ synthesis Msamples/s + PCPS acquisition cells/s on N B200s (BASELINE.json's metric).
+
+One STEP = one pass of the hot path over one batch of synthetic input on every rank:
+  (1) synthesise the rank's 20 s time segment of e1c_8prn_20s_clean.yaml (8 Galileo E1C PRNs, noise on,
+      1e8 samples, cf32) straight into HBM, then
+  (2) run PCPS over consecutive 4 ms snapshots of that segment for the config's 8 PRNs on the
+      20 000-lag x 41-Doppler grid (+-5 kHz / 250 Hz) and gather the peak table.
+Weak scaling: with N ranks the scenario is N x 20 s long and rank r owns segment r (time sharding, no data-path
+collective; one all-gather of the peak table).  `value` is synthesis throughput (the metric's first half) and
+the `acq` object carries the cells/s half with its own roofline / e2e / cpu_baseline.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path
+  python bench.py --impl reference [...]                         # the reference algorithm on the host cores
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOAD = "e1c_8prn_20s_clean.yaml"
+SEGMENT_S = 20.0
+CODE_LENGTH = 20000            # samples per E1C primary-code period at 5 MHz
+DOPPLER_MAX, DOPPLER_STEP = 5000.0, 250.0
+FLOP_PER_CELL = 264.6          # reference-equivalent flop per (PRN, Doppler, lag) cell
+FP32_PEAK_TFLOPS = 74.4        # 148 SM x 128 lanes x 2 x 1.965 GHz (nominal; MEASURED_PEAKS.json has no FP32 figure)
+HBM_FALLBACK_GBS = 6650.0      # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
+
+
+def hbm_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        sm, mx, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            p = [x.strip() for x in r.split(",")]
+            if len(p) < 7:
+                continue
+            try:
+                sm.append(float(p[0])); mx = max(mx, float(p[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, p[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def load_workload(n_ranks: int):
+    from r4w_b200.config import load_config
+    cfg = load_config(os.path.join(ROOT, "configs", WORKLOAD), cli_elevation_mask_deg=5.0)   # the CLI's default mask
+    cfg.output.duration_s = SEGMENT_S * n_ranks
+    return cfg
+
+
+# ------------------------------------------------------------------------------------------------- CPU legs
+def cpu_synth(cfg, seconds: float, threads: int):
+    """oracle port of GnssScenario::generate_block, one thread per satellite (the reference's rayon `parallel` feature)."""
+    from oracle import oracle as O
+    c = cfg.copy()
+    c.output.duration_s = seconds
+    sc = O.OracleScenario(c, noise=True, threads=threads)
+    bs = sc.block_size()
+    t = time.perf_counter()
+    n = 0
+    while not sc.is_done():
+        n += sc.generate_block(bs).size
+    dt = time.perf_counter() - t
+    return n / dt / 1e6, n, dt
+
+
+def cpu_acq(x: np.ndarray, codes: np.ndarray, prns, n_snap: int, threads: int):
+    """oracle port of PcpsAcquisition::acquire; independent (snapshot, PRN) calls spread over host threads
+    (ctypes drops the GIL; the reference itself has no parallel acquisition)."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import oracle as O
+    acq = O.OraclePcps(CODE_LENGTH, 5e6).with_doppler_range(DOPPLER_MAX, DOPPLER_STEP)
+    x64 = np.ascontiguousarray(x[: n_snap * CODE_LENGTH], np.complex128)
+    jobs = [(s, c) for s in range(n_snap) for c in range(len(prns))]
+
+    def one(j):
+        s, c = j
+        r = acq.acquire(x64[s * CODE_LENGTH:(s + 1) * CODE_LENGTH], codes[c], prns[c])
+        return int(r.code_phase)
+
+    t = time.perf_counter()
+    with ThreadPoolExecutor(max_workers=threads) as ex:
+        list(ex.map(one, jobs))
+    dt = time.perf_counter() - t
+    cells = len(jobs) * acq.num_bins() * CODE_LENGTH
+    return cells / dt, cells, dt
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU algorithm (oracle port; the Rust crate cannot be built in this image)
+    on the host cores, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle as O
+    O.build()
+    cores = os.cpu_count() or 1
+    cfg = load_workload(max(1, args.gpus))
+    n_sats = len(cfg.satellites)
+    th_s = max(1, min(n_sats, cores))
+    prns = [s.prn for s in cfg.satellites]
+    codes = np.stack([O.e1c_replica(p, 5e6, CODE_LENGTH) for p in prns])
+    seconds = 0.1                                     # 0.5 Msamples per synthesis step
+    n_snap = max(1, min(2, cores // 8 + 1))
+    x = None
+    syn, acq = [], []
+    for it in range(args.warmup + args.steps):
+        v, n, dt = cpu_synth(cfg, seconds, th_s)
+        if x is None:
+            c = cfg.copy(); c.output.duration_s = n_snap * CODE_LENGTH / 5e6
+            x = O.to_cf32(O.OracleScenario(c, noise=True).generate_range(0, n_snap * CODE_LENGTH))
+        a, cells, adt = cpu_acq(x, codes, prns, n_snap, cores)
+        if it >= args.warmup:
+            syn.append((v, dt)); acq.append((a, adt))
+    v = float(np.mean([s[0] for s in syn])); a = float(np.mean([s[0] for s in acq]))
+    ms = float(np.mean([s[1] for s in syn])) * 1e3
+    sample = f"synthesis: {seconds} s of the scenario per step ({int(seconds*5e6)} samples), {th_s} threads (one per satellite); " \
+             f"acquisition: {n_snap} snapshot(s) x {len(prns)} PRNs x 41 bins per step, {cores} threads"
+    line = {
+        "impl": "reference", "metric": "gnss_iq_synth_msamples_per_s", "value": v, "unit": "Msamples/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{WORKLOAD}: 8 Galileo E1C PRNs, 5 MS/s, noise on; bounded sample per step", "sample": sample},
+        "cpu_baseline": {"value": v, "unit": "Msamples/s", "cores": th_s, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "acq": {"metric": "pcps_acq_cells_per_s", "value": a, "unit": "cells/s", "ms_per_step": float(np.mean([s[1] for s in acq])) * 1e3,
+                "cpu_baseline": {"value": a, "unit": "cells/s", "cores": cores, "kind": "port", "sample": sample},
+                "e2e": {"value": a, "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------- GPU arm
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    import r4w_b200 as R
+    from r4w_b200 import _lib
+    from r4w_b200.dist import all_gather_table, results_to_table, segment_for_rank
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    else:
+        torch.cuda.set_device(local)
+    R.init(local)
+    dev = torch.device("cuda", local)
+
+    cfg = load_workload(world)
+    prns = [s.prn for s in cfg.satellites]
+    codes = np.stack([R.e1c_replica(p, 5e6, CODE_LENGTH) for p in prns])
+    scen = R.GnssScenario(cfg, noise=True)
+    first, n = segment_for_rank(scen.total_samples(), CODE_LENGTH, rank, world)
+    n_snap_total = n // CODE_LENGTH
+    n_snap = n_snap_total if args.acq_snapshots <= 0 else min(args.acq_snapshots, n_snap_total)
+    acq = R.PcpsAcquisition(CODE_LENGTH, 5e6).with_doppler_range(DOPPLER_MAX, DOPPLER_STEP)
+    acq.set_profiling(True)
+    bins = acq.num_doppler_bins()
+    iq = torch.empty(n, dtype=torch.complex64, device=dev)       # 0.8 GB: larger than the 126 MB L2, no flush needed
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step(record):
+        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        e0.record()
+        scen.generate_device(first, n, iq)
+        e1.record()
+        pods = acq.acquire_batch_raw(iq, n_snap, CODE_LENGTH, CODE_LENGTH, codes, prns)
+        table = all_gather_table(results_to_table(pods, n_snap, len(prns)))
+        e2.record()
+        if record is not None:
+            record.append((e0, e1, e2, acq.last_profile(), acq.guard_count()))
+        return table
+
+    for _ in range(max(args.warmup, 0)):
+        step(None)
+    barrier()
+    launches0 = R.kernel_launches()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    rec = []
+    t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+    barrier()
+    t0.record()
+    table = None
+    for _ in range(args.steps):
+        table = step(rec)
+    t1.record()
+    barrier()
+    clk = clocks.stop() if rank == 0 else None
+    launches = R.kernel_launches() - launches0
+    ms_syn = float(np.mean([r[0].elapsed_time(r[1]) for r in rec]))
+    ms_acq = float(np.mean([r[1].elapsed_time(r[2]) for r in rec]))
+    ms_total = t0.elapsed_time(t1) / args.steps
+    prof = rec[-1][3]
+    guards = int(np.sum([r[4] for r in rec]))
+
+    # ---- e2e: the same step through the C-ABI with HOST buffers (pinned), copies inside the timed region
+    import ctypes as C
+    host = C.c_void_p()
+    _lib.check(_lib.lib().r4wb_host_alloc(C.byref(host), n * 8))
+    host_np = np.ctypeslib.as_array(C.cast(host, C.POINTER(C.c_float)), shape=(2 * n,)).view(np.complex64)
+    e2e_steps = max(1, min(args.steps, 3))
+    _lib.set_stream(torch.cuda.current_stream().cuda_stream)
+    scen.generate_range_into(first, n, host.value)              # warm-up (staging buffers, page faults)
+    acq.acquire_batch_raw(host_np, min(n_snap, 64), CODE_LENGTH, CODE_LENGTH, codes, prns)
+    barrier()
+    ts = time.perf_counter()
+    for _ in range(e2e_steps):
+        scen.generate_range_into(first, n, host.value)
+    torch.cuda.synchronize()
+    ms_syn_e2e = (time.perf_counter() - ts) * 1e3 / e2e_steps
+    ts = time.perf_counter()
+    for _ in range(e2e_steps):
+        pods = acq.acquire_batch_raw(host_np, n_snap, CODE_LENGTH, CODE_LENGTH, codes, prns)
+        tab2 = results_to_table(pods, n_snap, len(prns))
+    torch.cuda.synchronize()
+    ms_acq_e2e = (time.perf_counter() - ts) * 1e3 / e2e_steps
+
+    # ---- max over ranks
+    def rmax(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    ms_syn, ms_acq, ms_total, ms_syn_e2e, ms_acq_e2e = (rmax(v) for v in (ms_syn, ms_acq, ms_total, ms_syn_e2e, ms_acq_e2e))
+    inv_ms, inv_n = prof["inverse_fft_peak"]
+    fwd_ms, fwd_n = prof["forward_fft"]
+    inv_ms, fwd_ms = rmax(inv_ms), rmax(fwd_ms)
+
+    total_samples = n * world
+    cells_rank = n_snap * len(prns) * bins * CODE_LENGTH
+    cells = cells_rank * world
+    peak, peak_src = hbm_peak()
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import oracle as O
+        O.build()
+        cores = os.cpu_count() or 1
+        th_s = max(1, min(len(prns), cores))
+        v_s, n_s, dt_s = cpu_synth(cfg, 1.0, th_s)                    # 1 s of the scenario
+        ns_c = max(1, min(4, cores // 4))
+        v_a, c_a, dt_a = cpu_acq(host_np, codes, prns, ns_c, cores)
+        cpu = ({"value": v_s, "unit": "Msamples/s", "cores": th_s, "kind": "port",
+                "sample": f"1 s of {WORKLOAD} ({n_s} samples, {dt_s:.1f} s wall), oracle port, one thread per satellite"},
+               {"value": v_a, "unit": "cells/s", "cores": cores, "kind": "port",
+                "sample": f"{ns_c} snapshot(s) x {len(prns)} PRNs x {bins} bins ({c_a} cells, {dt_a:.1f} s wall), oracle port, {cores} threads"})
+    _lib.check(_lib.lib().r4wb_host_free(host))
+
+    if rank == 0:
+        synth_gbs = n * 8 / (ms_syn * 1e-3) / 1e9
+        acq_tflops = cells_rank * FLOP_PER_CELL / ((inv_ms + fwd_ms) * 1e-3) / 1e12 if inv_ms + fwd_ms > 0 else None
+        line = {
+            "metric": "gnss_iq_synth_msamples_per_s", "value": total_samples / (ms_syn * 1e-3) / 1e6, "unit": "Msamples/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_syn, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{WORKLOAD} x {world} GPU(s): {SEGMENT_S:.0f} s segment per GPU (time-sharded), 8 Galileo E1C PRNs, "
+                                   f"5 MS/s, noise on, cf32 into HBM; then PCPS over {n_snap} snapshots/GPU x 8 PRNs x {bins} Doppler bins x "
+                                   f"{CODE_LENGTH} lags", "samples_per_gpu": n, "snapshots_per_gpu": n_snap, "prns": prns,
+                       "l2": "per-step output 0.8 GB and spectra working set exceed the 126 MB L2 (no explicit flush)",
+                       "step": "synth then acquire; ms_per_step/value cover the synthesis half, acq.* the acquisition half, ms_step_total both"},
+            "ms_step_total": ms_total,
+            "roofline": {"bound": "hbm", "kernel": "k_synth", "achieved": synth_gbs, "peak": peak, "unit": "GB/s", "frac": synth_gbs / peak,
+                         "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": n * 8,
+                         "note": "8 B per output sample (one cf32 store); CUDA events on the launching stream"},
+            "e2e": {"value": total_samples / (ms_syn_e2e * 1e-3) / 1e6, "unit": "Msamples/s", "h2d_bytes_per_step": 0,
+                    "d2h_bytes_per_step": n * 8, "api": "r4wb_scenario_generate(..., R4WB_MEM_HOST, CF32) into pinned host memory"},
+            "acq": {"metric": "pcps_acq_cells_per_s", "value": cells / (ms_acq * 1e-3), "unit": "cells/s", "ms_per_step": ms_acq,
+                    "cells_per_step": cells, "f64_guard_reruns": guards,
+                    "kernel_ms": {k: v[0] for k, v in prof.items()}, "kernel_launches": {k: v[1] for k, v in prof.items()},
+                    "roofline": {"bound": "fp32", "kernel": "k_inv_peak (+k_fwd)", "achieved": acq_tflops, "peak": FP32_PEAK_TFLOPS,
+                                 "unit": "TFLOP/s", "frac": (acq_tflops / FP32_PEAK_TFLOPS) if acq_tflops else None, "traffic": None,
+                                 "peak_source": "nominal FP32 FMA peak (148 SM x 128 lanes x 2 x 1.965 GHz)",
+                                 "note": f"{FLOP_PER_CELL} reference-equivalent flop per cell / summed CUDA-event time of the forward and inverse FFT kernels"},
+                    "e2e": {"value": cells / (ms_acq_e2e * 1e-3), "unit": "cells/s", "h2d_bytes_per_step": n_snap * CODE_LENGTH * 8,
+                            "d2h_bytes_per_step": n_snap * len(prns) * 32,
+                            "api": "r4wb_pcps_acquire_batch(..., R4WB_MEM_HOST) from pinned host memory"},
+                    "first_snapshot": [[int(table[0, c, 2]), float(table[0, c, 3])] for c in range(len(prns))]},
+            "gpu_launches": int(launches),
+            "clocks": clk,
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = cpu[0]
+            line["acq"]["cpu_baseline"] = cpu[1]
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--acq-snapshots", type=int, default=0, help="snapshots per GPU per step (0 = the whole segment)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

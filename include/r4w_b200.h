@@ -229,6 +229,11 @@ r4wb_error r4wb_pcps_acquire_grid(r4wb_pcps* h, const void* input, r4wb_fmt fmt,
                                   const int8_t* code, uint64_t code_len, double* power_out, uint64_t cap);
 /* statistics of the last batch: rows run through the f64 near-tie guard */
 uint64_t r4wb_pcps_guard_count(const r4wb_pcps* h);
+/* Optional device-side timing of the last acquire_batch (measurement aid, no reference counterpart): when
+ * enabled, CUDA events bracket every kernel launch on the launching stream.  ms[4] / launches[4] are the summed
+ * durations and launch counts of {code spectra, forward FFT, inverse FFT + peak, pair reduce}. */
+r4wb_error r4wb_pcps_set_profiling(r4wb_pcps* h, int enabled);
+r4wb_error r4wb_pcps_last_profile(const r4wb_pcps* h, double* ms, uint64_t* launches);
 
 #ifdef __cplusplus
 }

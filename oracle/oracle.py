@@ -195,9 +195,12 @@ class OracleScenario:
             lib().orc_scenario_set_threads(h, threads)
 
     def __del__(self):
-        if getattr(self, "_h", None):
-            lib().orc_scenario_free(self._h)
-            self._h = None
+        try:
+            if getattr(self, "_h", None):
+                lib().orc_scenario_free(self._h)
+                self._h = None
+        except Exception:      # interpreter teardown
+            pass
 
     def total_samples(self) -> int: return int(lib().orc_scenario_total_samples(self._h))
     def block_size(self) -> int: return int(lib().orc_scenario_block_size(self._h))

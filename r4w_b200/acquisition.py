@@ -108,6 +108,16 @@ class PcpsAcquisition:
         """(snapshot, code) pairs of the last batch that were re-run in f64 (near-tie / near-threshold guard)."""
         return int(_lib.lib().r4wb_pcps_guard_count(self._h))
 
+    def set_profiling(self, enabled: bool = True):
+        _lib.check(_lib.lib().r4wb_pcps_set_profiling(self._h, int(bool(enabled))))
+
+    def last_profile(self):
+        """{kernel kind: (summed CUDA-event ms, launches)} of the last acquire_batch (profiling must be enabled)."""
+        ms = np.zeros(4, np.float64)
+        n = np.zeros(4, np.uint64)
+        _lib.check(_lib.lib().r4wb_pcps_last_profile(self._h, ms.ctypes.data_as(C.c_void_p), n.ctypes.data_as(C.c_void_p)))
+        return {k: (float(ms[i]), int(n[i])) for i, k in enumerate(("code_spectra", "forward_fft", "inverse_fft_peak", "pair_reduce"))}
+
     # ---- searches
     def acquire(self, input_, code, prn: int) -> AcquisitionResult:
         x, fmt = _as_samples(input_)

@@ -127,6 +127,8 @@ public:
     uint64_t fft_size() const { return fft_size_; }
     uint32_t num_bins() const;
     uint64_t guard_count() const { return guard_count_; }
+    void set_profiling(bool on) { profiling_ = on; }
+    void last_profile(double* ms4, uint64_t* launches4) const;
 
     void acquire_batch(const void* input, r4wb_fmt fmt, r4wb_mem where, uint64_t n_snapshots, uint64_t stride,
                        uint64_t n_input, const int8_t* codes, uint64_t code_len, const uint8_t* prns, uint32_t n_codes,
@@ -147,6 +149,18 @@ private:
     uint64_t coherent_ = 1;
     uint64_t guard_count_ = 0;
     int logn_ = 0;
+
+    // optional per-launch CUDA-event timing (kind 0..3 = code spectra, forward, inverse+peak, pair reduce)
+    struct Timed { cudaEvent_t a, b; int kind; };
+    void prof_begin(int kind);
+    void prof_end();
+    void prof_collect();
+    bool profiling_ = false;
+    std::vector<Timed> timed_;
+    std::vector<cudaEvent_t> event_pool_;
+    size_t event_next_ = 0;
+    double prof_ms_[4] = {0, 0, 0, 0};
+    uint64_t prof_n_[4] = {0, 0, 0, 0};
 
     AcqWork<float> w32_;
     AcqWork<double> w64_;

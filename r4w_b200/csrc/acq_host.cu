@@ -38,7 +38,47 @@ Pcps::Pcps(uint64_t code_length, double sample_rate) : code_length_(code_length)
     while ((1ull << logn_) < f) ++logn_;
 }
 
-Pcps::~Pcps() {}
+Pcps::~Pcps()
+{
+    for (cudaEvent_t e : event_pool_) cudaEventDestroy(e);
+}
+
+void Pcps::prof_begin(int kind)
+{
+    if (!profiling_) return;
+    while (event_pool_.size() < event_next_ + 2) {
+        cudaEvent_t e;
+        R4WB_CUDA(cudaEventCreate(&e));
+        event_pool_.push_back(e);
+    }
+    Timed t{event_pool_[event_next_], event_pool_[event_next_ + 1], kind};
+    event_next_ += 2;
+    R4WB_CUDA(cudaEventRecord(t.a, current_stream()));
+    timed_.push_back(t);
+}
+
+void Pcps::prof_end()
+{
+    if (!profiling_) return;
+    R4WB_CUDA(cudaEventRecord(timed_.back().b, current_stream()));
+}
+
+void Pcps::prof_collect()   // after the stream has been synchronised
+{
+    for (const Timed& t : timed_) {
+        float ms = 0.0f;
+        R4WB_CUDA(cudaEventElapsedTime(&ms, t.a, t.b));
+        prof_ms_[t.kind] += (double)ms;
+        prof_n_[t.kind] += 1;
+    }
+    timed_.clear();
+    event_next_ = 0;
+}
+
+void Pcps::last_profile(double* ms4, uint64_t* launches4) const
+{
+    for (int k = 0; k < 4; ++k) { ms4[k] = prof_ms_[k]; launches4[k] = prof_n_[k]; }
+}
 
 void Pcps::set_doppler_range(double max_hz, double step_hz)
 {
@@ -79,7 +119,10 @@ void Pcps::run(AcqWork<T>& w, const void* d_input, r4wb_fmt fmt, uint64_t s0, ui
     }
     const uint32_t take = (uint32_t)std::min<uint64_t>(n_input, g.L);               // input.iter().take(samples_per_code)
     const uint32_t code_take = (uint32_t)std::min<uint64_t>(code_len, g.N);         // code_fft.resize(fft_size)
-    launch_fwd_codes<T>(g, nc, d_codes + (size_t)c0 * code_len, code_len, code_take, w.tw.p, w.c.reserve((size_t)nc * g.N), st);
+    w.c.reserve((size_t)nc * g.N);
+    prof_begin(0);
+    launch_fwd_codes<T>(g, nc, d_codes + (size_t)c0 * code_len, code_len, code_take, w.tw.p, w.c.p, st);
+    prof_end();
 
     const size_t row_bytes = (size_t)g.N * sizeof(cx<T>);
     uint64_t chunk = std::max<uint64_t>(1, kSpectraChunkBytes / (row_bytes * std::max(1u, g.D)));
@@ -91,9 +134,15 @@ void Pcps::run(AcqWork<T>& w, const void* d_input, r4wb_fmt fmt, uint64_t s0, ui
     for (uint64_t s = 0; s < ns; s += chunk) {
         const uint32_t cs = (uint32_t)std::min<uint64_t>(chunk, ns - s);
         const unsigned char* in = static_cast<const unsigned char*>(d_input) + (s0 + s) * stride * bps;
+        prof_begin(1);
         launch_fwd_input<T>(g, cs * g.D, in, fmt == R4WB_FMT_CF64 ? 1u : 0u, stride, take, w.tw.p, w.x.p, st);
+        prof_end();
+        prof_begin(2);
         launch_inv_peak<T>(g, cs * g.D, w.x.p, w.c.p, w.tw.p, d_rowpeaks_.p, d_grid, st);
+        prof_end();
+        prof_begin(3);
         launch_pair_reduce(g, cs, d_rowpeaks_.p, d_out + s * nc, st);
+        prof_end();
     }
 }
 
@@ -147,10 +196,12 @@ void Pcps::acquire_batch(const void* input, r4wb_fmt fmt, r4wb_mem where, uint64
     const size_t pairs = (size_t)S * P;
     d_pairpeaks_.reserve(pairs + 1);
 
+    for (int k = 0; k < 4; ++k) { prof_ms_[k] = 0.0; prof_n_[k] = 0; }
     run<float>(w32_, d_input, fmt, 0, S, stride, n_input, d_codes_.p, code_len, 0, P, d_pairpeaks_.p, nullptr);
     std::vector<PairPeak> pk(pairs);
     R4WB_CUDA(cudaMemcpyAsync(pk.data(), d_pairpeaks_.p, pairs * sizeof(PairPeak), cudaMemcpyDeviceToHost, st));
     R4WB_CUDA(cudaStreamSynchronize(st));
+    prof_collect();
 
     guard_count_ = 0;
     for (size_t i = 0; i < pairs; ++i) {
@@ -166,6 +217,7 @@ void Pcps::acquire_batch(const void* input, r4wb_fmt fmt, r4wb_mem where, uint64
             PairPeak g;
             R4WB_CUDA(cudaMemcpyAsync(&g, d_g, sizeof g, cudaMemcpyDeviceToHost, st));
             R4WB_CUDA(cudaStreamSynchronize(st));
+            prof_collect();
             finish(g, prn, out[i]);
             ++guard_count_;
         }
@@ -189,6 +241,7 @@ void Pcps::acquire_grid(const void* input, r4wb_fmt fmt, uint64_t n_input, const
     run<double>(w64_, d_in_.p, fmt, 0, 1, 0, n_input, d_codes_.p, code_len, 0, 1, d_pairpeaks_.p, d_grid_.p);
     R4WB_CUDA(cudaMemcpyAsync(power_out, d_grid_.p, cells * sizeof(double), cudaMemcpyDeviceToHost, st));
     R4WB_CUDA(cudaStreamSynchronize(st));
+    prof_collect();
 }
 
 }  // namespace r4wb

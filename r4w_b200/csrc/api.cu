@@ -232,6 +232,20 @@ uint64_t r4wb_pcps_fft_size(const r4wb_pcps* h) { return h ? h->impl.fft_size() 
 uint32_t r4wb_pcps_num_doppler_bins(const r4wb_pcps* h) { return h ? h->impl.num_bins() : 0; }
 uint64_t r4wb_pcps_guard_count(const r4wb_pcps* h) { return h ? h->impl.guard_count() : 0; }
 
+r4wb_error r4wb_pcps_set_profiling(r4wb_pcps* h, int enabled)
+{
+    if (!h) { t_error = "handle is NULL"; return R4WB_ERR_NULL_POINTER; }
+    h->impl.set_profiling(enabled != 0);
+    return R4WB_OK;
+}
+
+r4wb_error r4wb_pcps_last_profile(const r4wb_pcps* h, double* ms, uint64_t* launches)
+{
+    if (!h || !ms || !launches) { t_error = "NULL argument"; return R4WB_ERR_NULL_POINTER; }
+    h->impl.last_profile(ms, launches);
+    return R4WB_OK;
+}
+
 r4wb_error r4wb_pcps_acquire(r4wb_pcps* h, const void* input, r4wb_fmt fmt, uint64_t n_input, const int8_t* code,
                              uint64_t code_len, uint8_t prn, r4wb_acq_result* out)
 {

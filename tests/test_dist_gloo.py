@@ -1,0 +1,59 @@
+"""N>1 plumbing on CPU: world_size-2 gloo group, the all-gather of the ragged peak table and the rank segments."""
+import os
+import socket
+
+import numpy as np
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    import torch.distributed as dist
+    from r4w_b200.dist import all_gather_table, segment_for_rank
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        total = 7 * 20000 + 123                       # ragged: 7 snapshots over 2 ranks + a tail
+        first, n = segment_for_rank(total, 20000, rank, world)
+        s0, ns = first // 20000, n // 20000
+        # fake peak table whose content encodes the global snapshot index, so order after the gather is checkable
+        local = np.zeros((ns, 3, 6))
+        for s in range(ns):
+            local[s, :, 0] = [3, 25, 8]
+            local[s, :, 2] = (s0 + s) * 100 + np.arange(3)
+        full = all_gather_table(local)
+        q.put((rank, first, n, full))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_all_gather_peak_table_world2():
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    out = sorted([q.get(timeout=120) for _ in range(world)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (r0, f0, n0, t0), (r1, f1, n1, t1) = out
+    assert f0 == 0 and f0 + n0 == f1 and f1 + n1 == 7 * 20000 + 123
+    assert n0 == 4 * 20000 and n1 == 3 * 20000 + 123
+    assert t0.shape == (7, 3, 6) and np.array_equal(t0, t1)
+    assert np.array_equal(t0[:, 0, 2], np.arange(7) * 100.0) and np.array_equal(t0[:, 2, 2], np.arange(7) * 100.0 + 2)
+
+
+def test_all_gather_single_process_is_identity():
+    from r4w_b200.dist import all_gather_table
+    a = np.arange(24, dtype=np.float64).reshape(2, 2, 6)
+    assert np.array_equal(all_gather_table(a), a)

@@ -1,0 +1,210 @@
+"""Parity of the CUDA PCPS acquisition path (through the C-ABI) with the oracle: the detected (code phase,
+Doppler bin) indices are the bit-exact contract.  Run on the B200 box: pytest -m gpu."""
+import numpy as np
+import pytest
+
+from tests.conftest import config_path
+
+pytestmark = pytest.mark.gpu
+ALL8 = [3, 25, 8, 2, 5, 16, 13, 15]
+
+
+def _cfg(name):
+    from r4w_b200.config import load_config
+    return load_config(config_path(name), cli_elevation_mask_deg=5.0)
+
+
+def _same(r, o, metric_rtol=2e-4):
+    assert (r.code_phase, r.doppler_hz, bool(r.detected)) == (o.code_phase, o.doppler_hz, bool(o.detected)), (r, o.code_phase, o.doppler_hz)
+    assert r.peak_metric == pytest.approx(o.peak_metric, rel=metric_rtol)
+    assert (r.cn0_estimate is None) == (not o.has_cn0)
+    if o.has_cn0:
+        assert r.cn0_estimate == pytest.approx(o.cn0_estimate, abs=1e-3)
+
+
+def test_reference_kats(gpu, oracle):
+    """test_acquisition_no_noise / _wrong_prn / _grid (acquisition.rs:294-377) through the CUDA path"""
+    code = oracle.gps_ca_code(1)
+    i = np.arange(1023)
+    sig = code[(i + 1023 - 100) % 1023] * np.exp(2j * np.pi * 1000.0 * (i / 1023.0))
+    acq = gpu.PcpsAcquisition(1023, 1023.0).with_doppler_range(5000.0, 500.0).with_threshold(2.0)
+    assert acq.fft_size() == 1024 and acq.num_doppler_bins() == 21
+    r = acq.acquire(sig, code, 1)
+    assert r.detected and int(r.code_phase) == 100 and abs(r.doppler_hz - 1000.0) <= 500.0
+    _same(r, oracle.OraclePcps(1023, 1023.0).with_doppler_range(5000.0, 500.0).with_threshold(2.0).acquire(sig, code, 1))
+    c7 = oracle.gps_ca_code(7)
+    r = gpu.PcpsAcquisition(1023, 1023.0).with_threshold(2.5).acquire(code.astype(np.complex128), c7, 7)
+    assert (not r.detected) or r.peak_metric < 10.0
+    _same(r, oracle.OraclePcps(1023, 1023.0).with_threshold(2.5).acquire(code.astype(np.complex128), c7, 7))
+    g = gpu.PcpsAcquisition(1023, 1023.0).with_doppler_range(2000.0, 500.0).acquire_grid(code.astype(np.complex128), code)
+    dop, ph, pw = g.find_peak()
+    assert abs(dop) <= 500.0 and (ph <= 1.0 or abs(ph - 1023.0) <= 1.0)
+    og, olin = oracle.OraclePcps(1023, 1023.0).with_doppler_range(2000.0, 500.0).acquire_grid(code.astype(np.complex128), code)
+    assert g.power.shape == og.shape == (9, 1023) and np.abs(g.power - og).max() / og.max() < 1e-11
+    assert int(np.argmax(g.power)) == olin
+
+
+def test_scenario_kat_gps_2046(gpu, oracle):
+    """the shape of test_acquisition_on_scenario (scenario.rs:793-855): 2046 samples/code at 2.046 MHz, N = 2048"""
+    rng = np.random.default_rng(7)
+    code = np.repeat(oracle.gps_ca_code(5), 2)
+    i = np.arange(2046)
+    sig = np.roll(code, 321) * np.exp(2j * np.pi * 1750.0 * i / 2.046e6) + 0.7 * (rng.standard_normal(2046) + 1j * rng.standard_normal(2046))
+    a = gpu.PcpsAcquisition(2046, 2.046e6).with_threshold(1.5)
+    o = oracle.OraclePcps(2046, 2.046e6).with_threshold(1.5)
+    assert a.fft_size() == 2048
+    r = a.acquire(sig, code, 5)
+    _same(r, o.acquire(sig, code, 5))
+    assert int(r.code_phase) == 2046 - 321
+
+
+@pytest.mark.parametrize("name", ["e1c_8prn_20s_clean", "e1c_prn3_20s_withdoppler", "e1c_60s_all_prns", "e1c_8prn_60s_cn34_orbital"])
+def test_e1c_indices_match_oracle_all_prns(gpu, oracle, name):
+    """every PRN 1-50 (present, absent, and the wrap-around-lag cases) on oracle-generated noisy input: (lag, bin) identical"""
+    cfg = _cfg(name)
+    cfg.output.duration_s = 0.008
+    x = oracle.to_cf32(oracle.OracleScenario(cfg, noise=True, threads=8).generate_range(0, 40000))
+    prns = list(range(1, 51))
+    codes = np.stack([gpu.e1c_replica(p, 5e6, 20000) for p in prns])
+    acq = gpu.PcpsAcquisition(20000, 5e6).with_doppler_range(5000.0, 250.0)
+    assert acq.fft_size() == 32768 and acq.num_doppler_bins() == 41
+    res = acq.acquire_batch(x, 2, 20000, 20000, codes, prns)
+    oacq = oracle.OraclePcps(20000, 5e6).with_doppler_range(5000.0, 250.0)
+    from concurrent.futures import ThreadPoolExecutor
+    x64 = x.astype(np.complex128)
+    jobs = [(s, c) for s in range(2) for c in range(50)]
+    with ThreadPoolExecutor(8) as ex:
+        want = list(ex.map(lambda j: oacq.acquire(x64[j[0] * 20000:(j[0] + 1) * 20000], codes[j[1]], prns[j[1]]), jobs))
+    for (s, c), o in zip(jobs, want):
+        _same(res[s][c], o)
+        assert res[s][c].prn == prns[c]
+
+
+def test_clean_anchor_values(gpu, oracle):
+    """SURVEY.md §8c anchors through synth + acquire on the GPU end to end (noise off)"""
+    cfg = _cfg("e1c_8prn_20s_clean")
+    x = gpu.GnssScenario(cfg, noise=False).generate_range(0, 20000)
+    acq = gpu.PcpsAcquisition(20000, 5e6).with_doppler_range(5000.0, 250.0)
+    want = {3: (5625, 18), 25: (12965, 22), 8: (6074, 26), 2: (15397, 32), 13: (16269, 15), 15: (3532, 9),
+            5: (4040, 32), 16: (227, 38), 1: (731, 20)}
+    for prn, (lag, dbin) in want.items():
+        r = acq.acquire(x, gpu.e1c_replica(prn, 5e6, 20000), prn)
+        assert (int(r.code_phase), int(round((r.doppler_hz + 5000.0) / 250.0))) == (lag, dbin), prn
+
+
+def test_default_doppler_grid_and_cf64_input(gpu, oracle):
+    """reference defaults (+-5 kHz / 500 Hz = 21 bins, threshold 2.5) and Complex64 input as the Rust API passes it"""
+    cfg = _cfg("e1c_8prn_20s_clean")
+    x = oracle.OracleScenario(cfg, noise=True).generate_range(0, 20000)          # f64
+    a, o = gpu.PcpsAcquisition(20000, 5e6), oracle.OraclePcps(20000, 5e6)
+    assert a.num_doppler_bins() == 21
+    for prn in (3, 15, 7):
+        rep = gpu.e1c_replica(prn, 5e6, 20000)
+        _same(a.acquire(x, rep, prn), o.acquire(x, rep, prn))
+
+
+def test_edge_cases(gpu, oracle):
+    rng = np.random.default_rng(3)
+    a, o = gpu.PcpsAcquisition(20000, 5e6), oracle.OraclePcps(20000, 5e6)
+    rep = gpu.e1c_replica(3, 5e6, 20000)
+    # short input: `take(code_length)` just correlates fewer samples (acquisition.rs:134)
+    x = (rng.standard_normal(12345) + 1j * rng.standard_normal(12345)).astype(np.complex64)
+    _same(a.acquire(x, rep, 3), o.acquire(x.astype(np.complex128), rep, 3))
+    # long input: only the first code_length samples are read
+    x = (rng.standard_normal(30000) + 1j * rng.standard_normal(30000)).astype(np.complex64)
+    _same(a.acquire(x, rep, 3), o.acquire(x.astype(np.complex128), rep, 3))
+    # replica shorter / longer than the FFT size (zero-padded / truncated by resize, acquisition.rs:112)
+    _same(a.acquire(x, rep[:7777], 3), o.acquire(x.astype(np.complex128), rep[:7777], 3))
+    long_rep = np.concatenate([rep, rep])
+    _same(a.acquire(x, long_rep, 3), o.acquire(x.astype(np.complex128), long_rep, 3))
+    # all-zero input: nothing exceeds best_peak = 0 -> phase 0, doppler 0.0, metric 0, not detected
+    z = a.acquire(np.zeros(20000, np.complex64), rep, 3)
+    zo = o.acquire(np.zeros(20000, np.complex128), rep, 3)
+    assert (z.code_phase, z.doppler_hz, z.peak_metric, z.detected) == (zo.code_phase, zo.doppler_hz, zo.peak_metric, bool(zo.detected)) == (0.0, 0.0, 0.0, False)
+    # tiny transforms (fft_size 1, 2, 4, 8, 16, 32)
+    for L in (1, 2, 3, 5, 13, 31):
+        code = rng.choice(np.array([-1, 1], np.int8), L)
+        sig = rng.standard_normal(L) + 1j * rng.standard_normal(L)
+        _same(gpu.PcpsAcquisition(L, 1000.0).with_doppler_range(100.0, 50.0).acquire(sig, code, 9),
+              oracle.OraclePcps(L, 1000.0).with_doppler_range(100.0, 50.0).acquire(sig, code, 9))
+    with pytest.raises(gpu.R4wB200Error):
+        gpu.PcpsAcquisition(20000, 5e6).with_doppler_range(5000.0, 0.0)
+
+
+def test_exact_ties_take_lowest_index(gpu):
+    """equal maxima in every Doppler row: the reference's ascending strict-`>` scan keeps the first (acquisition.rs:159)"""
+    L = 8
+    x = np.zeros(L, np.complex128); x[0] = 1.0
+    r = gpu.PcpsAcquisition(L, 8.0).with_doppler_range(2.0, 1.0).acquire(x, np.ones(L, np.int8), 1)
+    assert (r.code_phase, r.doppler_hz) == (0.0, -2.0)
+
+
+def test_near_tie_guard_runs_f64(gpu, oracle):
+    """two cells 3e-6 apart (below f32 resolution of the pipeline): the f64 re-run must decide as the oracle does"""
+    L = 1023
+    code = oracle.gps_ca_code(3)
+    i = np.arange(L)
+    a1, a2 = 1.0, 1.0 - 1.5e-6
+    sig = a1 * np.roll(code, 200).astype(np.float64) + a2 * np.roll(code, 700).astype(np.float64)
+    acq = gpu.PcpsAcquisition(L, 1.023e6).with_doppler_range(0.0, 500.0)
+    r = acq.acquire(sig.astype(np.complex128), code, 3)
+    o = oracle.OraclePcps(L, 1.023e6).with_doppler_range(0.0, 500.0).acquire(sig.astype(np.complex128), code, 3)
+    assert acq.guard_count() == 1
+    assert (r.code_phase, r.doppler_hz) == (o.code_phase, o.doppler_hz)
+    assert r.peak_metric == pytest.approx(o.peak_metric, rel=1e-9)
+
+
+def test_batch_layouts_and_device_input(gpu, oracle):
+    """snapshot stride != n_input, device-resident input, results in [snapshot][code] order"""
+    import torch
+    cfg = _cfg("e1c_8prn_20s_clean")
+    n = 5 * 20000
+    d = torch.empty(n, dtype=torch.complex64, device="cuda")
+    gpu.GnssScenario(cfg, noise=True).generate_device(0, n, d)
+    host = d.cpu().numpy()
+    codes = np.stack([gpu.e1c_replica(p, 5e6, 20000) for p in ALL8])
+    acq = gpu.PcpsAcquisition(20000, 5e6).with_doppler_range(5000.0, 250.0)
+    dev_res = acq.acquire_batch(d, 5, 20000, 20000, codes, ALL8)
+    host_res = acq.acquire_batch(host, 5, 20000, 20000, codes, ALL8)
+    strided = acq.acquire_batch(host, 3, 40000, 20000, codes, ALL8)
+    for s in range(5):
+        for c in range(8):
+            assert dev_res[s][c] == host_res[s][c]
+            single = acq.acquire(host[s * 20000:(s + 1) * 20000], codes[c], ALL8[c])
+            assert single == host_res[s][c]
+    for k, s in enumerate((0, 2, 4)):
+        assert strided[k] == host_res[s]
+    # present PRNs land on the same Doppler bin in consecutive snapshots (static scenario)
+    for c, prn in enumerate(ALL8):
+        if prn in (3, 25, 8, 15):
+            assert len({host_res[s][c].doppler_hz for s in range(5)}) == 1
+    with pytest.raises(ValueError):
+        acq.acquire_batch(host, 6, 20000, 20000, codes, ALL8)
+
+
+def test_batch_vs_oracle_on_gpu_generated_scenario(gpu, oracle):
+    """synth -> acquire pipeline on the GPU vs the oracle acquiring the SAME GPU-generated samples"""
+    cfg = _cfg("e1c_60s_all_prns")
+    x = gpu.GnssScenario(cfg, noise=True).generate_range(150_000_000, 3 * 20000)
+    codes = np.stack([gpu.e1c_replica(p, 5e6, 20000) for p in ALL8])
+    acq = gpu.PcpsAcquisition(20000, 5e6).with_doppler_range(5000.0, 250.0)
+    res = acq.acquire_batch(x, 3, 20000, 20000, codes, ALL8)
+    oacq = oracle.OraclePcps(20000, 5e6).with_doppler_range(5000.0, 250.0)
+    x64 = x.astype(np.complex128)
+    for s in range(3):
+        for c, prn in enumerate(ALL8):
+            _same(res[s][c], oacq.acquire(x64[s * 20000:(s + 1) * 20000], codes[c], prn))
+
+
+def test_golden_acquisition_cases(gpu):
+    """committed oracle results for PRN 1-50 on a committed noisy snapshot (tests/golden/acq_cases.npz)"""
+    import os
+    from tests.conftest import GOLDEN_DIR
+    a = np.load(os.path.join(GOLDEN_DIR, "acq_cases.npz"))
+    x, rows = a["x"], a["results"]
+    prns = [int(p) for p in rows[:, 0]]
+    codes = np.stack([gpu.e1c_replica(p, 5e6, 20000) for p in prns])
+    res = gpu.PcpsAcquisition(20000, 5e6).with_doppler_range(5000.0, 250.0).acquire_batch(x, 1, 20000, 20000, codes, prns)[0]
+    for r, (prn, lag, dop, metric, det) in zip(res, rows):
+        assert (r.prn, r.code_phase, r.doppler_hz, r.detected) == (int(prn), lag, dop, bool(det))
+        assert r.peak_metric == pytest.approx(metric, rel=2e-4)
