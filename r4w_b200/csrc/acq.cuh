@@ -89,18 +89,13 @@ struct CodeLoad {
     R4WB_HD cx<T> operator()(uint32_t n) const { return cx<T>{n < take ? (T)code[n] : (T)0, (T)0}; }
 };
 
-// spectrum product fused into the inverse-FFT load (gnss/acquisition.rs:146-148); 1/N of ifft_inplace
-// (core/fft_utils.rs:104-107) folded in
+// spectrum product fused into the inverse-FFT load (gnss/acquisition.rs:146-148).  The 1/N of ifft_inplace
+// (core/fft_utils.rs:104-107) is folded into the stored code spectrum: c = conj(FFT(code)) / N.
 template <typename T>
 struct ProductLoad {
     const cx<T>* x;      // forward spectrum of the wiped-off snapshot
-    const cx<T>* c;      // conj(code spectrum)
-    T inv_n;
-    R4WB_HD cx<T> operator()(uint32_t n) const
-    {
-        const cx<T> v = x[n] * c[n];
-        return cx<T>{v.re * inv_n, v.im * inv_n};
-    }
+    const cx<T>* c;      // conj(code spectrum) / N
+    R4WB_HD cx<T> operator()(uint32_t n) const { return x[n] * c[n]; }
 };
 
 struct AcqGeom {

@@ -36,7 +36,7 @@ __device__ __forceinline__ void transform_item(cx<T>* s, const Load& load, const
     constexpr uint32_t NT = FftThreads<T>::value;
     const uint32_t M = 1u << g.logM;
 #pragma unroll 4
-    for (uint32_t k = threadIdx.x; k < M; k += NT) s[fft_pad(k)] = fft_fold_point<SIGN, T>(load, k, g.logM, g.logF, r, g.logN, W);
+    for (uint32_t k = threadIdx.x; k < M; k += NT) st_cx(s + fft_pad(k), fft_fold_point<SIGN, T>(load, k, g.logM, g.logF, r, g.logN, W));
     __syncthreads();
     const int np = fft_num_passes(g.logM);
     for (int p = 0; p < np; ++p) {
@@ -73,8 +73,8 @@ k_fwd(AcqGeom g, const void* __restrict__ input, uint32_t in64, uint64_t stride,
     }
     cx<T>* o = out + (size_t)row * g.N;
     for (uint32_t m = threadIdx.x; m < M; m += NT) {
-        cx<T> v = s[fft_pad(nat_to_pos(m, g.logM))];
-        if (MODE == 1) v = cconj(v);
+        cx<T> v = ld_cx(s + fft_pad(nat_to_pos(m, g.logM)));
+        if (MODE == 1) { const T inv_n = (T)1 / (T)g.N; v = cx<T>{v.re * inv_n, -v.im * inv_n}; }   // conj, and ifft's 1/N
         o[(m << g.logF) + r] = v;
     }
 }
@@ -90,6 +90,57 @@ __device__ __forceinline__ PeakAcc<V> peak_shfl_xor(const PeakAcc<V>& a, int off
     return o;
 }
 
+// Fold of the spectrum product for F = 2, f32 (the E1C shape, N = 32768): z[k] = (Y[k] +- Y[k+M]) * w^{kr} / N with
+// Y = X * C.  Each thread owns element PAIRS so every global load is 16 bytes, and all loads of U iterations are
+// issued before the first use (the generic fold stores to shared memory between loads, which the compiler must
+// keep ordered against the un-restricted global pointers — that serialised every L2 round trip).
+__device__ __forceinline__ void fold_product_f2(cx<float>* s, const cx<float>* __restrict__ X, const cx<float>* __restrict__ C,
+                                                const cx<float>* __restrict__ W, int logM, uint32_t r)
+{
+    constexpr uint32_t NT = FftThreads<float>::value;
+    constexpr int U = 4;
+    const uint32_t M = 1u << logM;
+    const float4* X4 = reinterpret_cast<const float4*>(X);
+    const float4* C4 = reinterpret_cast<const float4*>(C);
+    const float4* W4 = reinterpret_cast<const float4*>(W);
+    const uint32_t half = M >> 1;                      // float4 index of element M
+    for (uint32_t i0 = threadIdx.x; i0 < half; i0 += U * NT) {
+        float4 x0[U], x1[U], c0[U], c1[U], w[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint32_t i = i0 + (uint32_t)u * NT;
+            if (i < half) {
+                x0[u] = __ldg(X4 + i); x1[u] = __ldg(X4 + i + half);
+                c0[u] = __ldg(C4 + i); c1[u] = __ldg(C4 + i + half);
+                if (r) w[u] = __ldg(W4 + i);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint32_t i = i0 + (uint32_t)u * NT;
+            if (i >= half) break;
+            // two complex products per operand pair
+            const float a0r = x0[u].x * c0[u].x - x0[u].y * c0[u].y, a0i = x0[u].x * c0[u].y + x0[u].y * c0[u].x;
+            const float a1r = x0[u].z * c0[u].z - x0[u].w * c0[u].w, a1i = x0[u].z * c0[u].w + x0[u].w * c0[u].z;
+            const float b0r = x1[u].x * c1[u].x - x1[u].y * c1[u].y, b0i = x1[u].x * c1[u].y + x1[u].y * c1[u].x;
+            const float b1r = x1[u].z * c1[u].z - x1[u].w * c1[u].w, b1i = x1[u].z * c1[u].w + x1[u].w * c1[u].z;
+            cx<float> z0, z1;
+            if (r == 0) {
+                z0 = cx<float>{a0r + b0r, a0i + b0i};
+                z1 = cx<float>{a1r + b1r, a1i + b1i};
+            } else {                                   // (Y[k] - Y[k+M]) * conj(W[k])
+                const float d0r = a0r - b0r, d0i = a0i - b0i;
+                const float d1r = a1r - b1r, d1i = a1i - b1i;
+                z0 = cx<float>{d0r * w[u].x + d0i * w[u].y, d0i * w[u].x - d0r * w[u].y};
+                z1 = cx<float>{d1r * w[u].z + d1i * w[u].w, d1i * w[u].z - d1r * w[u].w};
+            }
+            const uint32_t p = fft_pad(2u * i);        // 2i and 2i+1 share a pad group
+            st_cx(s + p, z0);
+            st_cx(s + p + 1, z1);
+        }
+    }
+}
+
 // blockIdx.x = ((row * P) + code) * F + r, row = snapshot * D + d
 template <typename T>
 __global__ void __launch_bounds__(FftThreads<T>::value)
@@ -100,23 +151,39 @@ k_inv_peak(AcqGeom g, const cx<T>* __restrict__ X, const cx<T>* __restrict__ C, 
     cx<T>* s = reinterpret_cast<cx<T>*>(smem_raw);
     constexpr uint32_t NT = FftThreads<T>::value;
     __shared__ PeakAcc<T> s_red[NT / 32];
+    __shared__ uint32_t s_hi[64];
     const uint32_t F = 1u << g.logF, M = 1u << g.logM;
     const uint32_t r = blockIdx.x & (F - 1u);
     const uint32_t rc = blockIdx.x >> g.logF;
     const uint32_t row = rc / g.P, code = rc - row * g.P;
 
+    // digit reversal is a bit permutation: pos_to_nat(tid | i * NT) = pos_to_nat(tid) | pos_to_nat(i * NT)
+    if (threadIdx.x < 64 && threadIdx.x * NT < M) s_hi[threadIdx.x] = pos_to_nat(threadIdx.x * NT, g.logM);
+
     ProductLoad<T> ld;
     ld.x = X + (size_t)row * g.N;
     ld.c = C + (size_t)code * g.N;
-    ld.inv_n = (T)1 / (T)g.N;
-    transform_item<+1, T>(s, ld, g, r, W);
+    if (sizeof(T) == 4 && g.logF == 1 && g.logM >= 2) {
+        fold_product_f2(reinterpret_cast<cx<float>*>(s), reinterpret_cast<const cx<float>*>(ld.x), reinterpret_cast<const cx<float>*>(ld.c),
+                        reinterpret_cast<const cx<float>*>(W), g.logM, r);
+        __syncthreads();
+        const int np = fft_num_passes(g.logM);
+        for (int p = 0; p < np; ++p) {
+            fft_pass<+1, T>(s, g.logM, g.logN, W, p, threadIdx.x, NT);
+            __syncthreads();
+        }
+    } else {
+        transform_item<+1, T>(s, ld, g, r, W);
+    }
 
     PeakAcc<T> acc;
     peak_init(acc);
-    for (uint32_t p = threadIdx.x; p < M; p += NT) {
-        const uint32_t n = (pos_to_nat(p, g.logM) << g.logF) + r;      // lag
+    const uint32_t lo = threadIdx.x < M ? pos_to_nat(threadIdx.x, g.logM) : 0u;
+    for (uint32_t p = threadIdx.x, i = 0; p < M; p += NT, ++i) {
+        const uint32_t m = M > NT ? (lo | s_hi[i]) : lo;
+        const uint32_t n = (m << g.logF) + r;                              // lag
         if (n < g.L) {
-            const cx<T> v = s[fft_pad(p)];
+            const cx<T> v = ld_cx(s + fft_pad(p));
             const T mag = v.re * v.re + v.im * v.im;
             peak_push(acc, mag, n);
             if (grid) grid[(size_t)(row % g.D) * g.L + n] = (double)mag;

@@ -25,6 +25,43 @@ template <typename T> R4WB_HD cx<T> operator-(cx<T> a, cx<T> b) { return {a.re -
 template <typename T> R4WB_HD cx<T> operator*(cx<T> a, cx<T> b) { return {a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re}; }
 template <typename T> R4WB_HD cx<T> cconj(cx<T> a) { return {a.re, -a.im}; }
 
+// one 8-byte (cf32) / 16-byte (cf64) access per complex element (the plain struct copy is split into two scalar
+// accesses by the compiler)
+R4WB_HD cx<float> ld_cx(const cx<float>* p)
+{
+#ifdef __CUDA_ARCH__
+    const float2 v = *reinterpret_cast<const float2*>(p);
+    return cx<float>{v.x, v.y};
+#else
+    return *p;
+#endif
+}
+R4WB_HD cx<double> ld_cx(const cx<double>* p)
+{
+#ifdef __CUDA_ARCH__
+    const double2 v = *reinterpret_cast<const double2*>(p);
+    return cx<double>{v.x, v.y};
+#else
+    return *p;
+#endif
+}
+R4WB_HD void st_cx(cx<float>* p, cx<float> v)
+{
+#ifdef __CUDA_ARCH__
+    *reinterpret_cast<float2*>(p) = make_float2(v.re, v.im);
+#else
+    *p = v;
+#endif
+}
+R4WB_HD void st_cx(cx<double>* p, cx<double> v)
+{
+#ifdef __CUDA_ARCH__
+    *reinterpret_cast<double2*>(p) = make_double2(v.re, v.im);
+#else
+    *p = v;
+#endif
+}
+
 // shared-memory position of logical element p: one pad element per 16 keeps every pass's half-warp
 // accesses on distinct 8-byte banks (strides 2^k collide otherwise)
 R4WB_HD uint32_t fft_pad(uint32_t p) { return p + (p >> 4); }
@@ -114,11 +151,11 @@ R4WB_HD void fft_butterfly(cx<T>* s, uint32_t b, int logL, int logN, const cx<T>
     const uint32_t base = (g << logL) + q;
     cx<T> a[R];
 #pragma unroll
-    for (int j = 0; j < R; ++j) a[j] = s[fft_pad(base + (uint32_t)j * st)];
+    for (int j = 0; j < R; ++j) a[j] = ld_cx(s + fft_pad(base + (uint32_t)j * st));
     dft_bitrev<R, SIGN, T>(a);
     if (logst == 0) {           // last pass: all twiddles are 1
 #pragma unroll
-        for (int i = 0; i < R; ++i) s[fft_pad(base + (uint32_t)i * st)] = a[bitrev_r<R>(i)];
+        for (int i = 0; i < R; ++i) st_cx(s + fft_pad(base + (uint32_t)i * st), a[bitrev_r<R>(i)]);
         return;
     }
     // w[i] = w_L^{i q}; built as a product tree (depth <= 4) so rounding does not pile up
@@ -140,9 +177,9 @@ R4WB_HD void fft_butterfly(cx<T>* s, uint32_t b, int logL, int logN, const cx<T>
             for (int i = 1; i < 8; ++i) w[(8 + i) % R] = w[8 % R] * w[i];
         }
     }
-    s[fft_pad(base)] = a[0];
+    st_cx(s + fft_pad(base), a[0]);
 #pragma unroll
-    for (int i = 1; i < R; ++i) s[fft_pad(base + (uint32_t)i * st)] = a[bitrev_r<R>(i)] * w[i];
+    for (int i = 1; i < R; ++i) st_cx(s + fft_pad(base + (uint32_t)i * st), a[bitrev_r<R>(i)] * w[i]);
 }
 
 // All butterflies of pass `pass_idx` that thread `tid` of `nthreads` owns.  Returns false once the

@@ -17,6 +17,10 @@ constexpr int kFracBits = 46;         // fixed-point fraction of the half-chip p
 constexpr int kTBits = 24;            // fraction bits of "oversamples since boundary" (8 integer bits: up to 256 oversamples)
 constexpr int kMaxSats = 64;
 constexpr int kMaxSegments = 512;
+constexpr int kYStride = 81;          // boundary-age classes per sign pattern (odd: spreads patterns over banks)
+constexpr int kPerBits = 2 * kCodeLen;   // half-chips of one primary-code period
+constexpr int kPerWords = 260;        // 8184 sign bits + 64 wrap-around bits, padded to a multiple of 4 words
+constexpr int kSynthThreads = 256;
 
 // One piece of the reference's sequential f64 `phase += phase_inc` (gnss/scenario.rs:518-527) for a
 // constant-Doppler satellite: from visible-sample count i0 on, phase = x0 + (m - i0) * step EXACTLY
@@ -57,6 +61,7 @@ struct ScenConst {
     uint64_t lattice_den;           // D: half-chip fractions of a block lie on offset + k/D (0 = dense)
     uint32_t kmul;                  // round(S * 2^24), S = oversamples per half-chip
     uint32_t cj[8];                 // round(j * S * 2^24)
+    uint32_t dsum0;                 // (cj[1] >> 24) + (cj[2] >> 24) + (cj[3] >> 24)
     float noise_std;
     uint64_t seed;
 };
@@ -85,9 +90,10 @@ struct BlockHdr { uint64_t first; uint32_t n; uint32_t pad; };
 struct SynthArgs {
     const BlockSat* tab;       // [n_tab_blocks][n_sats]
     const BlockHdr* hdr;       // [n_tab_blocks]
-    const uint32_t* codebits;  // [n_sats][128] packed primary code, bit=1 -> chip -1
+    const uint32_t* perbits;   // [n_sats][kPerWords] half-chip signs of one primary-code period (code x BOC(1,1)), bit=1 -> -1
     const float* taps;         // [64] h[k] (f32), [63] = 0
     const float* etab;         // [64] E[d] = sum_{k<=d} h[k]  (E[62] = E[63] = 1)
+    const float* ytab;         // [32][kYStride] collapsed-FIR outputs per (sign pattern, boundary-age class)
     void* out;                 // cf32 or cf64, out[0] <-> sample out_first
     double* power_sum;         // optional accumulator of |s|^2
     uint64_t out_first, out_n; // only samples in [out_first, out_first + out_n) are written
@@ -100,6 +106,7 @@ struct SynthArgs {
     uint64_t delta46;
     uint32_t kmul;
     uint32_t cj[8];
+    uint32_t dsum0;            // floor(S) + floor(2S) + floor(3S): offset of the boundary-age class index
     double spc;
     float noise_std;
     uint64_t seed;
@@ -115,9 +122,11 @@ struct ScenarioModel {
     std::vector<r4wb_sat_cfg> cfg_sats;
     r4wb_scenario_cfg cfg{};
     std::vector<PhaseSegment> segments;
-    std::vector<uint32_t> codebits;     // [n_sats][128]
+    std::vector<uint32_t> codebits;     // [n_sats][128] packed primary code (bit=1 -> chip -1)
+    std::vector<uint32_t> perbits;      // [n_sats][kPerWords]
     float taps_f[64];
     float etab_f[64];
+    std::vector<float> ytab;            // [32][kYStride]
     int tile_k = 10;                    // samples per tile = 256 threads * 2 * tile_k
     uint32_t nw64 = 0;
     bool any_dynamic = false, any_var_visibility = false;
@@ -177,8 +186,8 @@ private:
     // device state
     DevBuf<SatConst> d_sat_;
     DevBuf<PhaseSegment> d_segments_;
-    DevBuf<uint32_t> d_codebits_;
-    DevBuf<float> d_taps_, d_etab_;
+    DevBuf<uint32_t> d_perbits_;
+    DevBuf<float> d_taps_, d_etab_, d_ytab_;
     DevBuf<BlockSat> d_tab_, d_seq_tab_;
     DevBuf<BlockHdr> d_hdr_, d_seq_hdr_;
     DevBuf<double> d_power_;

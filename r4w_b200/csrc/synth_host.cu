@@ -21,7 +21,8 @@ Scenario::Scenario(const r4wb_scenario_cfg& cfg) : md_(cfg)
     const auto& sats = md_.sats;
     R4WB_CUDA(cudaMemcpyAsync(d_sat_.reserve(std::max<size_t>(1, sats.size())), sats.data(), sats.size() * sizeof(SatConst), cudaMemcpyHostToDevice, st));
     R4WB_CUDA(cudaMemcpyAsync(d_segments_.reserve(md_.segments.size()), md_.segments.data(), md_.segments.size() * sizeof(PhaseSegment), cudaMemcpyHostToDevice, st));
-    R4WB_CUDA(cudaMemcpyAsync(d_codebits_.reserve(md_.codebits.size()), md_.codebits.data(), md_.codebits.size() * 4, cudaMemcpyHostToDevice, st));
+    R4WB_CUDA(cudaMemcpyAsync(d_perbits_.reserve(md_.perbits.size()), md_.perbits.data(), md_.perbits.size() * 4, cudaMemcpyHostToDevice, st));
+    R4WB_CUDA(cudaMemcpyAsync(d_ytab_.reserve(md_.ytab.size()), md_.ytab.data(), md_.ytab.size() * 4, cudaMemcpyHostToDevice, st));
     R4WB_CUDA(cudaMemcpyAsync(d_taps_.reserve(64), md_.taps_f, sizeof md_.taps_f, cudaMemcpyHostToDevice, st));
     R4WB_CUDA(cudaMemcpyAsync(d_etab_.reserve(64), md_.etab_f, sizeof md_.etab_f, cudaMemcpyHostToDevice, st));
     d_power_.reserve(1);
@@ -71,7 +72,7 @@ void Scenario::launch_synth(const BlockSat* tab, const BlockHdr* hdr, uint32_t t
 {
     const ScenConst& sc = md_.sc;
     SynthArgs a{};
-    a.tab = tab; a.hdr = hdr; a.codebits = d_codebits_.p; a.taps = d_taps_.p; a.etab = d_etab_.p;
+    a.tab = tab; a.hdr = hdr; a.perbits = d_perbits_.p; a.taps = d_taps_.p; a.etab = d_etab_.p; a.ytab = d_ytab_.p;
     a.out = d_out; a.power_sum = d_power_.p;
     a.out_first = out_first; a.out_n = out_n;
     a.tb_begin = tb_begin; a.tb_count = tb_count;
@@ -79,7 +80,7 @@ void Scenario::launch_synth(const BlockSat* tab, const BlockHdr* hdr, uint32_t t
     a.tiles_per_block = (uint32_t)((max_block_n + tile - 1) / tile);
     a.n_sats = sc.n_sats; a.nw64 = md_.nw64; a.flags = sc.flags;
     a.out_aligned16 = ((uintptr_t)d_out & 15u) == 0 ? 1u : 0u;
-    a.delta46 = sc.delta46; a.kmul = sc.kmul;
+    a.delta46 = sc.delta46; a.kmul = sc.kmul; a.dsum0 = sc.dsum0;
     for (int j = 0; j < 8; ++j) a.cj[j] = sc.cj[j];
     a.spc = sc.spc; a.noise_std = sc.noise_std; a.seed = sc.seed;
 

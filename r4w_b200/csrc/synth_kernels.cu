@@ -80,35 +80,51 @@ __global__ void __launch_bounds__(1024) k_phase_scan(const SatConst* __restrict_
 // ----------------------------------------------------------------------------------------------
 // synthesis kernel: persistent CTAs, one tile (<= 256*2*K consecutive samples of one 1 ms block) at a time.
 // Thread t owns the sample pairs (2t, 2t+1) + 512 k of the tile, so every store is a 16-byte float4 and a
-// warp writes 512 contiguous bytes.
-constexpr int kThreads = 256;
+// warp writes 512 contiguous bytes.  Per satellite and pair: one 64-bit code-NCO step, two boundary-age classes,
+// one shared-memory window load for both 5-sign patterns, two table look-ups, and a packed (FFMA2) phasor recurrence.
+constexpr int kThreads = kSynthThreads;
+
+struct SynthSmem {
+    float* ytab; float* taps; float* etab; uint32_t* per; TileSat* tsat; uint2* t64; uint32_t* w32; float* yfix;
+};
+
+__device__ __forceinline__ SynthSmem carve_smem(unsigned char* raw, uint32_t n_sats, uint32_t nw64)
+{
+    SynthSmem m;
+    m.ytab = reinterpret_cast<float*>(raw);                                   // [32][kYStride]
+    m.taps = m.ytab + 32 * kYStride;                                          // [64]
+    m.etab = m.taps + 64;                                                     // [64]
+    size_t off = ((size_t)(32 * kYStride + 128) * 4 + 15) & ~(size_t)15;
+    m.per = reinterpret_cast<uint32_t*>(raw + off);                           // [n_sats][kPerWords]
+    off += (size_t)n_sats * kPerWords * 4;
+    m.tsat = reinterpret_cast<TileSat*>(raw + off);                           // [n_sats]
+    off += (size_t)n_sats * sizeof(TileSat);
+    m.t64 = reinterpret_cast<uint2*>(raw + off);                              // [n_sats][nw64]
+    off += (size_t)n_sats * nw64 * 8;
+    m.w32 = reinterpret_cast<uint32_t*>(raw + off);                           // [n_sats][nw64 + 1]
+    off += (size_t)n_sats * (nw64 + 1) * 4;
+    m.yfix = reinterpret_cast<float*>(raw + off);                             // [n_sats][8]
+    return m;
+}
 
 template <int K, bool CF64>
 __global__ void __launch_bounds__(kThreads) k_synth(SynthArgs a)
 {
     constexpr int TILE = kThreads * 2 * K;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float* erep = reinterpret_cast<float*>(smem_raw);                          // [63][32]
-    float4* coef = reinterpret_cast<float4*>(erep + 63 * 32);                  // [32][8]
-    float* taps = reinterpret_cast<float*>(coef + 32 * 8);                     // [64]
-    uint32_t* codes = reinterpret_cast<uint32_t*>(taps + 64);                  // [n_sats][128]
-    TileSat* tsat = reinterpret_cast<TileSat*>(codes + a.n_sats * 128);        // [n_sats]
-    uint2* t64 = reinterpret_cast<uint2*>(tsat + a.n_sats);                    // [n_sats][nw64]
-    uint32_t* w32 = reinterpret_cast<uint32_t*>(t64 + a.n_sats * a.nw64);      // [n_sats][nw64+1]
-    float* yfix = reinterpret_cast<float*>(w32 + a.n_sats * (a.nw64 + 1));     // [n_sats][8]
+    const SynthSmem sm = carve_smem(smem_raw, a.n_sats, a.nw64);
     __shared__ float s_pow[kThreads / 32];
 
     const uint32_t tid = threadIdx.x, lane = tid & 31u;
+    const SynthK KK = make_synth_k(a.delta46, a.kmul, a.cj, a.dsum0, a.spc);
 
     // kernel-lifetime tables
-    for (uint32_t k = tid; k < 63 * 32; k += kThreads) erep[k] = a.etab[k >> 5];
-    for (uint32_t k = tid; k < 32 * 8; k += kThreads) coef[k] = coef_entry(k >> 3);
-    for (uint32_t k = tid; k < 64; k += kThreads) taps[k] = a.taps[k];
-    for (uint32_t k = tid; k < a.n_sats * 128; k += kThreads) codes[k] = a.codebits[k];
+    for (uint32_t k = tid; k < 32 * kYStride; k += kThreads) sm.ytab[k] = a.ytab[k];
+    for (uint32_t k = tid; k < 64; k += kThreads) { sm.taps[k] = a.taps[k]; sm.etab[k] = a.etab[k]; }
+    for (uint32_t k = tid; k < a.n_sats * kPerWords; k += kThreads) sm.per[k] = a.perbits[k];
 
     float pow_acc = 0.0f;
     const uint32_t n_tiles = a.tb_count * a.tiles_per_block;
-    const uint64_t d8 = a.delta46 * (uint64_t)kOversample;
 
     for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const uint32_t tb = a.tb_begin + tile / a.tiles_per_block;
@@ -121,61 +137,40 @@ __global__ void __launch_bounds__(kThreads) k_synth(SynthArgs a)
         if (hd.first + i_end <= a.out_first || hd.first + i_begin >= a.out_first + a.out_n) continue;
         const BlockSat* row = a.tab + (size_t)tb * a.n_sats;
 
-        __syncthreads();   // previous tile's readers are done
-        if (tid < a.n_sats) tsat[tid] = tile_sat(row[tid], i_begin, d8);
+        __syncthreads();   // previous tile's readers are done (and the kernel-lifetime tables are in place)
+        if (tid < a.n_sats) sm.tsat[tid] = tile_sat(row[tid], a.tab, i_begin, KK.d8);
         __syncthreads();
         // half-chip sign words: bit n of word w <-> half-chip hb + 32 w + n
         for (uint32_t k = tid; k < a.n_sats * (a.nw64 + 1); k += kThreads) {
             const uint32_t s = k / (a.nw64 + 1), w = k - s * (a.nw64 + 1);
-            w32[k] = sign_word(codes + s * 128, tsat[s].hb, w);
+            sm.w32[k] = sign_word(sm.per + s * kPerWords, sm.tsat[s].hb, w);
         }
-        __syncthreads();
-        for (uint32_t k = tid; k < a.n_sats * a.nw64; k += kThreads) {
-            const uint32_t s = k / a.nw64, w = k - s * a.nw64;
-            t64[k] = make_uint2(w32[s * (a.nw64 + 1) + w], w32[s * (a.nw64 + 1) + w + 1]);
-        }
-        // first 8 samples of a block: their window reaches into the previous block
+        // first 8 samples of a block whose delay differs from its predecessor's
         if (chunk == 0) {
             for (uint32_t k = tid; k < a.n_sats * 8; k += kThreads) {
                 const uint32_t s = k >> 3, i = k & 7u;
                 float y = 0.0f;
-                if ((row[s].flags & 1u) && i < hd.n) y = fir_direct(row[s], a.tab, codes + s * 128, taps, (int)i, a.delta46, a.spc);
-                yfix[k] = y;
+                if ((sm.tsat[s].flags & 9u) == 9u && i < hd.n)
+                    y = fir_block_start(row[s], a.tab, sm.per + s * kPerWords, sm.taps, sm.etab, (int)i, KK);
+                sm.yfix[k] = y;
             }
         }
         __syncthreads();
+        for (uint32_t k = tid; k < a.n_sats * a.nw64; k += kThreads) {
+            const uint32_t s = k / a.nw64, w = k - s * a.nw64;
+            sm.t64[k] = make_uint2(sm.w32[s * (a.nw64 + 1) + w], sm.w32[s * (a.nw64 + 1) + w + 1]);
+        }
+        __syncthreads();
 
-        float2 acc[K][2];
+        float2 ar[K], ai[K];      // (re_a, re_b), (im_a, im_b) of pair k
 #pragma unroll
-        for (int k = 0; k < K; ++k) acc[k][0] = acc[k][1] = make_float2(0.0f, 0.0f);
+        for (int k = 0; k < K; ++k) ar[k] = ai[k] = make_float2(0.0f, 0.0f);
 
         for (uint32_t s = 0; s < a.n_sats; ++s) {
-            const TileSat ts = tsat[s];
+            const TileSat ts = sm.tsat[s];
             if (!(ts.flags & 1u)) continue;
-            const uint2* tw = t64 + s * a.nw64;
-            const uint32_t ia0 = i_begin + 2 * tid;                          // sample index within the block
-            uint64_t ua = ts.u0 + (uint64_t)(2 * tid) * d8;
-            // phase of sample i: phi + (i+1) f + i(i+1)/2 df, advanced by 512 samples per k
-            uint64_t pha = carrier_phase(ts, ia0);
-            uint64_t gb = (uint64_t)ts.f + (uint64_t)ts.df * (uint64_t)(ia0 + 1);       // increment applied at sample i+1
-            uint64_t step = (uint64_t)(2 * kThreads) * (uint64_t)ts.f +
-                            (uint64_t)ts.df * ((uint64_t)(2 * kThreads) * ia0 + (uint64_t)(2 * kThreads) * (2 * kThreads + 1) / 2);
-            const uint64_t step2 = (uint64_t)ts.df * (uint64_t)(2 * kThreads) * (uint64_t)(2 * kThreads);
-            const uint64_t g512 = (uint64_t)ts.df * (uint64_t)(2 * kThreads);
-#pragma unroll
-            for (int k = 0; k < K; ++k) {
-                const uint32_t ia = ia0 + 2 * kThreads * k;
-                bool amb_a = false, amb_b = false;
-                float ya = fir_fast(ua, ts, tw, erep, coef, a.kmul, a.cj, lane, amb_a);
-                float yb = fir_fast(ua + d8, ts, tw, erep, coef, a.kmul, a.cj, lane, amb_b);
-                if (amb_a && ia < i_end) ya = fir_direct(row[s], a.tab, codes + s * 128, taps, (int)ia, a.delta46, a.spc);
-                if (amb_b && ia + 1 < i_end) yb = fir_direct(row[s], a.tab, codes + s * 128, taps, (int)ia + 1, a.delta46, a.spc);
-                if (k == 0 && chunk == 0 && tid < 4) { ya = yfix[s * 8 + 2 * tid]; yb = yfix[s * 8 + 2 * tid + 1]; }
-                rotate_acc(ya * ts.amp, pha, acc[k][0].x, acc[k][0].y);
-                rotate_acc(yb * ts.amp, pha + gb, acc[k][1].x, acc[k][1].y);
-                ua += d8 * (uint64_t)(2 * kThreads);
-                pha += step; step += step2; gb += g512;
-            }
+            const SlowCtx slow{row + s, a.tab, sm.per + s * kPerWords, sm.taps};
+            sat_accumulate<K>(ts, KK, sm.t64 + s * a.nw64, sm.ytab, sm.yfix + s * 8, slow, tid, i_begin, i_end, ar, ai, nullptr);
         }
 
         // noise, power, store
@@ -185,7 +180,7 @@ __global__ void __launch_bounds__(kThreads) k_synth(SynthArgs a)
             if (ia >= i_end) continue;
             const uint64_t m = hd.first + ia;                    // global sample index
             const bool has_b = ia + 1 < i_end;
-            float2 va = acc[k][0], vb = acc[k][1];
+            float2 va = make_float2(ar[k].x, ai[k].x), vb = make_float2(ar[k].y, ai[k].y);
             if (!(a.flags & R4WB_FLAG_NOISE_OFF)) {
                 float2 ga, gb2;
                 if ((m & 1ull) == 0) {      // one Philox draw covers both samples of the pair

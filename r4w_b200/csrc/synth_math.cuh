@@ -210,10 +210,10 @@ R4WB_HD void fill_block_sat(const ScenConst& sc, const SatConst& st, const Phase
     // ambiguity band: the reference's cf = fl(phase0 + fl(g/spc)) is within ulp(cf) chips of the real value
     const double cf_max = phase0 + (double)(G + (uint64_t)kOversample * n) / sc.spc + 2.0;
     const double ulp = scalbn(1.0, ilogb(cf_max) - 52);
-    const double eps_hc = 4.0 * ulp + 1.4901161193847656e-08 /* 2^-26 */;
+    const double eps_hc = 4.0 * ulp + 2.9802322387695312e-08 /* 2^-25: fixed-point error of the fast path */;
     double e46 = ceil(eps_hc * 70368744177664.0 /* 2^46 */);
     if (e46 > 2147483648.0) e46 = 2147483648.0;
-    double et = ceil(eps_hc * (sc.spc * 0.5) * 16777216.0 /* 2^24 */) + 2.0;
+    double et = ceil(eps_hc * (sc.spc * 0.5) * 16777216.0 /* 2^24 */) + 8.0;
     if (et > 4194304.0) et = 4194304.0;
     uint32_t flags = visible ? 1u : 0u;
     {
@@ -261,48 +261,150 @@ R4WB_HD uint64_t block_advance(const BlockSat& b)
 }
 
 // ----------------------------------------------------------------------------------------------
+// packed pairs: a float2 holds the same quantity for the two adjacent samples (a, b) a thread owns; on sm_100a
+// one FFMA2 / FMUL2 / FADD2 processes both
+R4WB_HD float2 pk_fma(float2 a, float2 b, float2 c)
+{
+#ifdef __CUDA_ARCH__
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d)
+        : "l"(reinterpret_cast<unsigned long long&>(a)), "l"(reinterpret_cast<unsigned long long&>(b)), "l"(reinterpret_cast<unsigned long long&>(c)));
+    return reinterpret_cast<float2&>(d);
+#else
+    return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y));
+#endif
+}
+R4WB_HD float2 pk_mul(float2 a, float2 b)
+{
+#ifdef __CUDA_ARCH__
+    unsigned long long d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(reinterpret_cast<unsigned long long&>(a)), "l"(reinterpret_cast<unsigned long long&>(b)));
+    return reinterpret_cast<float2&>(d);
+#else
+    return make_float2(a.x * b.x, a.y * b.y);
+#endif
+}
+R4WB_HD float2 pk_add(float2 a, float2 b)
+{
+#ifdef __CUDA_ARCH__
+    unsigned long long d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(reinterpret_cast<unsigned long long&>(a)), "l"(reinterpret_cast<unsigned long long&>(b)));
+    return reinterpret_cast<float2&>(d);
+#else
+    return make_float2(a.x + b.x, a.y + b.y);
+#endif
+}
+// low 32 bits of ((hi:lo) >> min(sh, 32))
+R4WB_HD uint32_t funnel_rc(uint32_t lo, uint32_t hi, uint32_t sh)
+{
+#ifdef __CUDA_ARCH__
+    return __funnelshift_rc(lo, hi, sh);
+#else
+    return (uint32_t)(((((uint64_t)hi) << 32) | (uint64_t)lo) >> (sh < 32u ? sh : 32u));
+#endif
+}
+R4WB_HD void accurate_sincos_cycles(uint64_t ph, float* s, float* c)
+{
+    // phase in cycles (0.64 fixed) -> sin/cos with full f32 accuracy (used once per tile and satellite)
+    const float x = (float)(int32_t)(ph >> 32) * 4.656612873077393e-10f;   // * 2^-31 -> half-cycles in [-1, 1)
+#ifdef __CUDA_ARCH__
+    sincospif(x, s, c);
+#else
+    *s = (float)sin(3.141592653589793 * (double)x);
+    *c = (float)cos(3.141592653589793 * (double)x);
+#endif
+}
+
+// ----------------------------------------------------------------------------------------------
 // per-tile, per-satellite state
 struct TileSat {
-    uint64_t u0;        // half-chip position at the newest oversample of the tile's first sample
+    uint64_t u0;        // half-chip position (18.46) at the newest oversample of the tile's first sample
     uint64_t phi;
     long long f, df;
     uint32_t hb;        // half-chip index of bit 0 of the sign table
     float amp;
-    uint32_t flags;
+    uint32_t flags;     // bit0 visible, bit1 ambiguity checks needed, bit2 per-sample sincos (large Doppler rate),
+                        // bit3 first 8 samples of the block come from yfix, bit4 Doppler varies inside the block
     uint32_t eps_t;
+    float wr, wi;       // e^{j phase advance over 2*kSynthThreads samples}, at the tile's first sample
+    float th1, th2;     // radians: growth of that advance per sample index, and per step of 2*kSynthThreads samples
 };
 
-R4WB_HD TileSat tile_sat(const BlockSat& b, uint32_t i_begin, uint64_t d8)
+// constants of one launch, derived from SynthArgs once per thread
+struct SynthK {
+    uint64_t delta46, d8;       // half-chips per oversample / per output sample, 2^-46 units
+    uint64_t step32;            // half-chips per 2*kSynthThreads samples, 32.32 fixed
+    uint32_t d8_32;             // half-chips per output sample, 0.32 fixed (< 1)
+    uint32_t kmul, c1, c2, c3, dsum0;
+    double spc;
+};
+
+R4WB_HD SynthK make_synth_k(uint64_t delta46, uint32_t kmul, const uint32_t* cj, uint32_t dsum0, double spc)
+{
+    SynthK k;
+    k.delta46 = delta46;
+    k.d8 = delta46 * (uint64_t)kOversample;
+    k.step32 = (k.d8 * (uint64_t)(2 * kSynthThreads)) >> (kFracBits - 32);
+    k.d8_32 = (uint32_t)(k.d8 >> (kFracBits - 32));
+    k.kmul = kmul; k.c1 = cj[1]; k.c2 = cj[2]; k.c3 = cj[3]; k.dsum0 = dsum0;
+    k.spc = spc;
+    return k;
+}
+
+R4WB_HD bool continues_prev(const BlockSat& cur, const BlockSat* __restrict__ tab);
+
+R4WB_HD TileSat tile_sat(const BlockSat& b, const BlockSat* __restrict__ tab, uint32_t i_begin, uint64_t d8)
 {
     TileSat t;
     t.u0 = b.U + (uint64_t)i_begin * d8;
     const uint32_t h0 = (uint32_t)(t.u0 >> kFracBits);
     t.hb = h0 - (uint32_t)(kJ + 2);            // may go "negative": all uses are modulo differences
-    t.phi = b.phi; t.f = b.f; t.df = b.df; t.amp = b.amp; t.flags = b.flags; t.eps_t = b.eps_t;
+    t.phi = b.phi; t.f = b.f; t.df = b.df; t.amp = b.amp; t.eps_t = b.eps_t;
+    uint32_t fl = b.flags & 3u;
+    // rotation over one step of 2*kSynthThreads samples, starting at sample i: phase(i + n) - phase(i) with
+    // phase(i) = phi + (i+1) f + i(i+1)/2 df
+    const uint64_t n = (uint64_t)(2 * kSynthThreads);
+    const uint64_t step = n * (uint64_t)b.f + (uint64_t)b.df * (n * (uint64_t)i_begin + n * (n + 1) / 2);
+    accurate_sincos_cycles(step, &t.wi, &t.wr);
+    const float two_pi_cyc = 3.4061215800865545e-19f;      // 2 pi / 2^64
+    t.th1 = (float)((double)b.df * (double)n) * two_pi_cyc;
+    t.th2 = (float)((double)b.df * (double)(n * n)) * two_pi_cyc;
+    if (b.df != 0) {
+        fl |= 16u;
+        // the linearised step phasor is good to (th1 * tile)^2 / 2 and (th2 * K)^2 / 2: fall back to per-sample sincos beyond 1e-4
+        if (fabsf(t.th1) * 8192.0f > 1e-4f || fabsf(t.th2) * 16.0f > 1e-4f) fl |= 4u;
+    }
+    if (i_begin == 0 && !continues_prev(b, tab)) fl |= 8u;
+    t.flags = fl;
     return t;
 }
 
-R4WB_HD uint32_t code_bit(const uint32_t* __restrict__ code, uint32_t c) { return (code[c >> 5] >> (c & 31)) & 1u; }
+// sign bit (1 <=> -1) of half-chip hc in [0, 204600): primary code x BOC(1,1) from the period table, x secondary code
+R4WB_HD uint32_t halfchip_sign(const uint32_t* __restrict__ per, uint32_t hc)
+{
+    const uint32_t e = hc / (uint32_t)kPerBits, p = hc - e * (uint32_t)kPerBits;
+    return ((per[p >> 5] >> (p & 31u)) ^ (kSecBits >> e)) & 1u;
+}
+R4WB_HD uint32_t code_bit(const uint32_t* __restrict__ per, uint32_t c) { return (per[c >> 4] >> ((2u * c) & 31u)) & 1u; }
 
 // word w of the per-tile half-chip sign table: bit n <-> half-chip hb + 32 w + n (1 <=> -1)
-R4WB_HD uint32_t sign_word(const uint32_t* __restrict__ code, uint32_t hb, uint32_t w)
+R4WB_HD uint32_t sign_word(const uint32_t* __restrict__ per, uint32_t hb, uint32_t w)
 {
     int64_t hh = (int64_t)(int32_t)hb + 32 * (int64_t)w;
     hh %= (int64_t)kHalfChipsPerSec;
     if (hh < 0) hh += kHalfChipsPerSec;
-    uint32_t h = (uint32_t)hh, chip = h >> 1, e = chip / kCodeLen, c = chip - e * kCodeLen, word = 0;
-#pragma unroll 4
-    for (int n = 0; n < 32; ++n) {
-        word |= (code_bit(code, c) ^ (h & 1u) ^ ((kSecBits >> e) & 1u)) << n;
-        if (h & 1u) { if (++c == (uint32_t)kCodeLen) { c = 0; if (++e == (uint32_t)kSecLen) e = 0; } }
-        if (++h == kHalfChipsPerSec) { h = 0; }
-    }
-    return word;
+    const uint32_t h = (uint32_t)hh, e = h / (uint32_t)kPerBits, p = h - e * (uint32_t)kPerBits;
+    const uint32_t bits = funnel_r(per[p >> 5], per[(p >> 5) + 1], p);       // the table repeats its first 64 bits at the end
+    const uint32_t e1 = e + 1 == (uint32_t)kSecLen ? 0u : e + 1;
+    const uint32_t se = 0u - ((kSecBits >> e) & 1u), se1 = 0u - ((kSecBits >> e1) & 1u);
+    const uint32_t nlow = (uint32_t)kPerBits - p;                             // bits of this word inside epoch e
+    const uint32_t lowmask = nlow >= 32u ? 0xffffffffu : ((1u << nlow) - 1u);
+    return bits ^ ((se & lowmask) | (se1 & ~lowmask));
 }
 
 // sign bit (1 <=> -1) of oversample q (>= 0, relative to the block start) of block entry bs;
 // evaluates the reference expression literally when q is within the rounding band of a boundary.
-R4WB_HD_NOINLINE uint32_t chip_sign_exact(const BlockSat& bs, long long q, const uint32_t* __restrict__ code, double spc)
+R4WB_HD_NOINLINE uint32_t chip_sign_exact(const BlockSat& bs, long long q, const uint32_t* __restrict__ per, double spc)
 {
     const double g = (double)(bs.G + (uint64_t)q);
     const double cf = add_rn(bs.phase0, div_rn(g, spc));                       // satellite_emitter.rs:268
@@ -313,25 +415,22 @@ R4WB_HD_NOINLINE uint32_t chip_sign_exact(const BlockSat& bs, long long q, const
     const double eq = div_rn(cf, (double)kCodeLen);
     const uint64_t ep = (uint64_t)bs.e0 + (eq > 0.0 ? (uint64_t)eq : 0ull);      // :278
     const uint32_t boc = fmod(mul_rn(cp, 2.0), 2.0) < 1.0 ? 0u : 1u;             // :303-305
-    return code_bit(code, c) ^ boc ^ ((kSecBits >> (uint32_t)(ep % kSecLen)) & 1u);
+    return code_bit(per, c) ^ boc ^ ((kSecBits >> (uint32_t)(ep % kSecLen)) & 1u);
 }
 
-R4WB_HD uint32_t chip_sign(const BlockSat& bs, long long q, const uint32_t* __restrict__ code, uint64_t delta46, double spc)
+R4WB_HD uint32_t chip_sign(const BlockSat& bs, long long q, const uint32_t* __restrict__ per, uint64_t delta46, double spc)
 {
     const uint64_t u = bs.U + (uint64_t)q * delta46;
     const uint64_t fr = u & kFracMask;
-    if (fr < bs.eps46 || fr > kFracMask - bs.eps46) return chip_sign_exact(bs, q, code, spc);
+    if (fr < bs.eps46 || fr > kFracMask - bs.eps46) return chip_sign_exact(bs, q, per, spc);
     uint32_t h = (uint32_t)(u >> kFracBits);
     if (h >= kHalfChipsPerSec) h -= kHalfChipsPerSec;
-    const uint32_t chip = h >> 1;
-    const uint32_t e = chip / kCodeLen, c = chip - e * kCodeLen;
-    return code_bit(code, c) ^ (h & 1u) ^ ((kSecBits >> e) & 1u);
+    return halfchip_sign(per, h);
 }
 
-// direct 63-tap evaluation of output sample i of block entry `cur` (history from `prev`): the reference's
-// own loop (fir.rs:392-409 over satellite_emitter.rs:264-330), used for the first 8 samples of a block and
-// for samples whose window touches an ambiguous boundary.
-R4WB_HD_NOINLINE float fir_direct(const BlockSat& cur, const BlockSat* __restrict__ tab, const uint32_t* __restrict__ code,
+// direct 63-tap evaluation of output sample i of block entry `cur` (history from `prev`): the reference's own loop
+// (fir.rs:392-409 over satellite_emitter.rs:264-330), used for samples whose window touches an ambiguous boundary.
+R4WB_HD_NOINLINE float fir_direct(const BlockSat& cur, const BlockSat* __restrict__ tab, const uint32_t* __restrict__ per,
                                   const float* __restrict__ taps, int i, uint64_t delta46, double spc)
 {
     float acc = 0.0f;
@@ -340,60 +439,71 @@ R4WB_HD_NOINLINE float fir_direct(const BlockSat& cur, const BlockSat* __restric
         long long q = g - k;
         uint32_t sgn;
         if (q >= 0) {
-            sgn = chip_sign(cur, q, code, delta46, spc);
+            sgn = chip_sign(cur, q, per, delta46, spc);
         } else {
             if (cur.prev < 0) continue;                      // zero-initialised delay line
             const BlockSat& pb = tab[cur.prev];
             q += (long long)kOversample * pb.n;
             if (q < 0) continue;                             // history older than one block: not modelled
-            sgn = chip_sign(pb, q, code, delta46, spc);
+            sgn = chip_sign(pb, q, per, delta46, spc);
         }
         acc += sgn ? -taps[k] : taps[k];
     }
     return acc;
 }
 
-// collapsed FIR: four table look-ups + one 5-bit sign pattern.
-//   u     half-chip position (18.46) of the newest oversample of the output sample
-//   t64   [nw64] per-tile sign table as overlapping 64-bit windows (word k = bits 32k .. 32k+63)
-//   erep  [63][32] E[d] replicated over the 32 banks, coef [32][8] (s_j - s_{j+1}) per sign pattern
-R4WB_HD float fir_fast(uint64_t u, const TileSat& ts, const uint2* __restrict__ t64, const float* __restrict__ erep,
-                       const float4* __restrict__ coef, uint32_t kmul, const uint32_t* cj, uint32_t lane, bool& ambiguous)
+// true when block `cur` continues its predecessor's code sequence exactly (same delay, adjacent in time): the
+// collapsed FIR may then look back across the block boundary through the sign table
+R4WB_HD bool continues_prev(const BlockSat& cur, const BlockSat* __restrict__ tab)
 {
-    const uint32_t h = (uint32_t)(u >> kFracBits);
-    const uint32_t f32 = (uint32_t)(u >> (kFracBits - 32));
-    const uint32_t t0 = umulhi32(f32, kmul);            // oversamples since the newest boundary, 2^-24 units
-    const uint32_t t1 = t0 + cj[1], t2 = t0 + cj[2], t3 = t0 + cj[3];
-    const uint32_t d0 = t0 >> kTBits, d1 = t1 >> kTBits, d2 = t2 >> kTBits;
-    uint32_t d3 = t3 >> kTBits;
-    if (d3 > 62u) d3 = 62u;
-    if (ts.flags & 2u) {
-        const uint32_t m = (1u << kTBits) - 1u, e = ts.eps_t;
-        ambiguous = ((t0 + e) & m) < 2 * e || ((t1 + e) & m) < 2 * e || ((t2 + e) & m) < 2 * e || ((t3 + e) & m) < 2 * e;
-    }
-    const float e0 = erep[(d0 < 62u ? d0 : 62u) * 32 + lane], e1 = erep[(d1 < 62u ? d1 : 62u) * 32 + lane];
-    const float e2 = erep[(d2 < 62u ? d2 : 62u) * 32 + lane], e3 = erep[d3 * 32 + lane];
-    const uint32_t idx = h - ts.hb - (uint32_t)kJ;       // bit of half-chip h-J
-    const uint2 w = t64[idx >> 5];
-    const uint32_t pat = funnel_r(w.x, w.y, idx) & 31u;  // bit m <-> half-chip h-J+m
-    const float4 c = coef[pat * 8 + (lane & 7)];
-    const uint32_t so_bits = 0x3f800000u | (pat << 31);
-#ifdef __CUDA_ARCH__
-    const float s_old = __int_as_float((int)so_bits);
-#else
-    float s_old;
-    { union { uint32_t u; float f; } cv; cv.u = so_bits; s_old = cv.f; }
-#endif
-    return fmaf(c.x, e0, fmaf(c.y, e1, fmaf(c.z, e2, fmaf(c.w, e3, s_old))));
+    if (cur.prev < 0) return false;
+    const BlockSat& pb = tab[cur.prev];
+    return (pb.flags & 1u) && pb.phase0 == cur.phase0 && pb.e0 == cur.e0 && pb.G + (uint64_t)kOversample * pb.n == cur.G;
 }
 
-// coefficient table entry for sign pattern `pat` (bit m <-> half-chip h-J+m  =>  s_j (age index j) is bit J-j)
-R4WB_HD float4 coef_entry(uint32_t pat)
+// boundary ages d_j = floor(t0 + j S) of the half-chip boundaries inside the window (t0 = oversamples since the newest one)
+R4WB_HD void boundary_ages(uint32_t frac32, const SynthK& K, uint32_t d[4])
 {
+    const uint32_t t0 = umulhi32(frac32, K.kmul);
+    d[0] = t0 >> kTBits; d[1] = (t0 + K.c1) >> kTBits; d[2] = (t0 + K.c2) >> kTBits; d[3] = (t0 + K.c3) >> kTBits;
+}
+
+// Collapsed FIR restricted to taps k <= g of the window whose newest oversample sits at half-chip position u of the
+// code sequence: s_4 E[g] + sum_j (s_j - s_{j+1}) E[min(d_j, g)]   (g = 62 gives the whole window)
+R4WB_HD float fir_collapsed_upto(uint64_t u, uint32_t g, const uint32_t* __restrict__ per, const float* __restrict__ etab, const SynthK& K)
+{
+    uint32_t h = (uint32_t)(u >> kFracBits);
+    uint32_t d[4];
+    boundary_ages((uint32_t)(u >> (kFracBits - 32)), K, d);
     float s[kJ + 1];
 #pragma unroll
-    for (int j = 0; j <= kJ; ++j) s[j] = ((pat >> (kJ - j)) & 1u) ? -1.0f : 1.0f;
-    return make_float4(s[0] - s[1], s[1] - s[2], s[2] - s[3], s[3] - s[4]);
+    for (int j = 0; j <= kJ; ++j) {
+        const uint32_t hc = (h + kHalfChipsPerSec - (uint32_t)j) % kHalfChipsPerSec;
+        s[j] = halfchip_sign(per, hc) ? -1.0f : 1.0f;
+    }
+    float y = s[kJ] * etab[g];
+#pragma unroll
+    for (int j = 0; j < kJ; ++j) y = fmaf(s[j] - s[j + 1], etab[d[j] < g ? d[j] : g], y);
+    return y;
+}
+
+// Output sample i (< 8) of a block whose code delay differs from its predecessor's: taps reaching oversamples >= 0 see
+// the block's own sequence, older taps the tail of the previous visible block (the FIR delay line persists across
+// blocks, core/filters/fir.rs:392-409 + gnss/scenario.rs:486-489).  Both parts in collapsed form; the literal 63-tap
+// loop only when either block has a boundary inside the f64 rounding band.
+R4WB_HD float fir_block_start(const BlockSat& cur, const BlockSat* __restrict__ tab, const uint32_t* __restrict__ per,
+                              const float* __restrict__ taps, const float* __restrict__ etab, int i, const SynthK& K)
+{
+    const bool has_prev = cur.prev >= 0;
+    if ((cur.flags & 2u) || (has_prev && (tab[cur.prev].flags & 2u))) return fir_direct(cur, tab, per, taps, i, K.delta46, K.spc);
+    const uint32_t g = (uint32_t)(kOversample * i);
+    float y = fir_collapsed_upto(cur.U + (uint64_t)g * K.delta46, g, per, etab, K);
+    if (has_prev) {
+        const BlockSat& pb = tab[cur.prev];
+        const uint64_t up = pb.U + ((uint64_t)kOversample * pb.n + g) * K.delta46;   // the old sequence, continued
+        y += fir_collapsed_upto(up, kTaps - 1, per, etab, K) - fir_collapsed_upto(up, g, per, etab, K);
+    }
+    return y;
 }
 
 // carrier phase (cycles 0.64) of sample i of a block: phi + (i+1) f + i(i+1)/2 df   (scenario.rs:519-524)
@@ -402,12 +512,106 @@ R4WB_HD uint64_t carrier_phase(const TileSat& ts, uint32_t i)
     return ts.phi + (uint64_t)(i + 1) * (uint64_t)ts.f + ((uint64_t)i * (i + 1) / 2) * (uint64_t)ts.df;
 }
 
-R4WB_HD void rotate_acc(float y, uint64_t ph, float& re, float& im)
+R4WB_HD void phasor(uint64_t ph, float* s, float* c)
 {
-    float s, c;
-    fast_sincos((float)(int32_t)(ph >> 32) * 1.4629180792671596e-09f /* 2 pi / 2^32 */, &s, &c);
-    re = fmaf(y, c, re);
-    im = fmaf(y, s, im);
+    fast_sincos((float)(int32_t)(ph >> 32) * 1.4629180792671596e-09f /* 2 pi / 2^32 */, s, c);
+}
+
+// what the slow paths of sat_accumulate need
+struct SlowCtx {
+    const BlockSat* cur;           // this block's entry for the satellite
+    const BlockSat* tab;           // whole table (history links)
+    const uint32_t* per;           // the satellite's period table
+    const float* taps;
+};
+
+// One satellite's contribution to the NK sample pairs thread `tid` owns in a tile: pair k = samples
+// (i_begin + 2 tid + 2 kSynthThreads k, +1).  ar[k] / ai[k] accumulate (re_a, re_b) / (im_a, im_b).
+//   t64   [nw64] per-tile sign table as overlapping 64-bit windows (word k = bits 32k .. 32k+63)
+//   ytab  [32][kYStride] collapsed-FIR outputs per (sign pattern, boundary-age class)
+//   yfix  first 8 outputs of the block when its window reaches into a block with another delay (flags bit3)
+template <int NK>
+R4WB_HD void sat_accumulate(const TileSat& ts, const SynthK& K, const uint2* __restrict__ t64, const float* __restrict__ ytab,
+                            const float* __restrict__ yfix, const SlowCtx& slow, uint32_t tid, uint32_t i_begin, uint32_t i_end,
+                            float2 (&ar)[NK], float2 (&ai)[NK], uint64_t* n_ambiguous)
+{
+    const uint32_t ia0 = i_begin + 2u * tid;
+    // code position of sample a, 32.32 fixed relative to bit 0 of the pattern field: hi = h - hb - J, lo = fraction
+    const uint64_t ua = ts.u0 + (uint64_t)(2u * tid) * K.d8;
+    uint64_t pos = (ua - ((uint64_t)(ts.hb + (uint32_t)kJ) << kFracBits)) >> (kFracBits - 32);
+
+    // carrier: exact 64-bit start phases, then a phasor recurrence over the strided pairs
+    const uint64_t pha = carrier_phase(ts, ia0);
+    const uint64_t gb = (uint64_t)ts.f + (uint64_t)ts.df * (uint64_t)(ia0 + 1);      // increment applied at sample ia0 + 1
+    float sa, ca, sb, cb;
+    phasor(pha, &sa, &ca);
+    phasor(pha + gb, &sb, &cb);
+    float2 zr = make_float2(ca * ts.amp, cb * ts.amp), zi = make_float2(sa * ts.amp, sb * ts.amp);
+    const bool dyn = (ts.flags & 16u) != 0u, exact_rot = (ts.flags & 4u) != 0u, check = (ts.flags & 2u) != 0u;
+    float wr = ts.wr, wi = ts.wi, dr = 0.0f, di = 0.0f;
+    if (dyn) {
+        const float dl = ts.th1 * (float)(2u * tid);
+        wr = fmaf(-dl, ts.wi, ts.wr);
+        wi = fmaf(dl, ts.wr, ts.wi);
+        dr = -ts.th2 * wi;
+        di = ts.th2 * wr;
+    }
+    float2 w_r = make_float2(wr, wr), w_i = make_float2(wi, wi), w_ni = make_float2(-wi, -wi);
+    const float2 d_r = make_float2(dr, dr), d_i = make_float2(di, di), d_ni = make_float2(-di, -di);
+    // exact-rotation mode state
+    uint64_t ph_k = pha, gb_k = gb;
+    uint64_t step = (uint64_t)(2 * kSynthThreads) * (uint64_t)ts.f +
+                    (uint64_t)ts.df * ((uint64_t)(2 * kSynthThreads) * ia0 + (uint64_t)(2 * kSynthThreads) * (2 * kSynthThreads + 1) / 2);
+    const uint64_t step2 = (uint64_t)ts.df * (uint64_t)(2 * kSynthThreads) * (uint64_t)(2 * kSynthThreads);
+    const uint64_t g_n = (uint64_t)ts.df * (uint64_t)(2 * kSynthThreads);
+
+#pragma unroll
+    for (int k = 0; k < NK; ++k) {
+        const uint32_t hi = (uint32_t)(pos >> 32), lo = (uint32_t)pos;
+        const uint32_t lob = lo + K.d8_32, hib = hi + (lob < lo ? 1u : 0u);
+        // boundary-age classes
+        const uint32_t ta0 = umulhi32(lo, K.kmul), ta1 = ta0 + K.c1, ta2 = ta0 + K.c2, ta3 = ta0 + K.c3;
+        const uint32_t tb0 = umulhi32(lob, K.kmul), tb1 = tb0 + K.c1, tb2 = tb0 + K.c2, tb3 = tb0 + K.c3;
+        const uint32_t cls_a = (ta0 >> kTBits) + (ta1 >> kTBits) + (ta2 >> kTBits) + (ta3 >> kTBits) - K.dsum0;
+        const uint32_t cls_b = (tb0 >> kTBits) + (tb1 >> kTBits) + (tb2 >> kTBits) + (tb3 >> kTBits) - K.dsum0;
+        // 5-sign patterns out of one 64-bit window
+        const uint2 w = t64[hi >> 5];
+        const uint32_t pa = funnel_r(w.x, w.y, hi) & 31u;
+        const uint32_t pb = funnel_rc(w.x, w.y, (hi & 31u) + (hib - hi)) & 31u;
+        float2 y = make_float2(ytab[pa * (uint32_t)kYStride + cls_a], ytab[pb * (uint32_t)kYStride + cls_b]);
+        if (check) {
+            const uint32_t m = (1u << kTBits) - 1u, e = ts.eps_t;
+            const bool amb_a = ((ta0 + e) & m) < 2 * e || ((ta1 + e) & m) < 2 * e || ((ta2 + e) & m) < 2 * e || ((ta3 + e) & m) < 2 * e;
+            const bool amb_b = ((tb0 + e) & m) < 2 * e || ((tb1 + e) & m) < 2 * e || ((tb2 + e) & m) < 2 * e || ((tb3 + e) & m) < 2 * e;
+            const uint32_t ia = ia0 + 2u * (uint32_t)kSynthThreads * (uint32_t)k;
+            if (amb_a && ia < i_end) {
+                y.x = fir_direct(*slow.cur, slow.tab, slow.per, slow.taps, (int)ia, K.delta46, K.spc);
+                if (n_ambiguous) ++*n_ambiguous;
+            }
+            if (amb_b && ia + 1 < i_end) {
+                y.y = fir_direct(*slow.cur, slow.tab, slow.per, slow.taps, (int)ia + 1, K.delta46, K.spc);
+                if (n_ambiguous) ++*n_ambiguous;
+            }
+        }
+        if (k == 0 && (ts.flags & 8u) && tid < 4u) y = make_float2(yfix[2u * tid], yfix[2u * tid + 1u]);
+        if (exact_rot) {
+            float s0, c0, s1, c1;
+            phasor(ph_k, &s0, &c0);
+            phasor(ph_k + gb_k, &s1, &c1);
+            zr = make_float2(c0 * ts.amp, c1 * ts.amp);
+            zi = make_float2(s0 * ts.amp, s1 * ts.amp);
+            ph_k += step; step += step2; gb_k += g_n;
+        }
+        ar[k] = pk_fma(y, zr, ar[k]);
+        ai[k] = pk_fma(y, zi, ai[k]);
+        if (!exact_rot && k + 1 < NK) {
+            const float2 nr = pk_fma(zr, w_r, pk_mul(zi, w_ni));
+            const float2 ni = pk_fma(zr, w_i, pk_mul(zi, w_r));
+            zr = nr; zi = ni;
+            if (dyn) { w_r = pk_add(w_r, d_r); w_i = pk_add(w_i, d_i); w_ni = pk_add(w_ni, d_ni); }
+        }
+        pos += K.step32;
+    }
 }
 
 // ----------------------------------------------------------------------------------------------

@@ -146,6 +146,7 @@ ScenarioModel::ScenarioModel(const r4wb_scenario_cfg& c_in) : cfg(c_in)
     const RxState rx0 = rx_at(rx, 0.0);
     sats.resize(cfg.n_sats);
     codebits.assign((size_t)std::max(1u, cfg.n_sats) * 128, 0u);
+    perbits.assign((size_t)std::max(1u, cfg.n_sats) * kPerWords, 0u);
     for (uint32_t k = 0; k < cfg.n_sats; ++k) {
         const r4wb_sat_cfg& c = cfg_sats[k];
         if (c.signal != R4WB_SIG_GALILEO_E1C)
@@ -191,17 +192,52 @@ ScenarioModel::ScenarioModel(const r4wb_scenario_cfg& c_in) : cfg(c_in)
         s.seg_count = (int32_t)segments.size() - s.seg_begin;
         for (uint32_t i = 0; i < (uint32_t)kCodeLen; ++i)
             codebits[(size_t)k * 128 + (i >> 5)] |= e1_sign_bit(1, c.prn, i) << (i & 31);
+        // half-chip signs of one primary-code period (code x BOC(1,1): second half of every chip inverted), followed by a
+        // copy of its first 64 bits so a 32-bit window may start anywhere in the period
+        uint32_t* per = perbits.data() + (size_t)k * kPerWords;
+        for (uint32_t n = 0; n < (uint32_t)kPerBits + 64u; ++n) {
+            const uint32_t hc = n % (uint32_t)kPerBits;
+            per[n >> 5] |= (e1_sign_bit(1, c.prn, hc >> 1) ^ (hc & 1u)) << (n & 31);
+        }
     }
     if (segments.empty()) segments.push_back(PhaseSegment{0, 0.0, 0.0});
 
     // filter: FirFilter::lowpass(lpf_cutoff or fs/2, 8 fs, 63)  (scenario.rs:209-217)
     double h[kTaps];
     design_lowpass(oc.lpf_cutoff_hz > 0.0 ? oc.lpf_cutoff_hz : oc.sample_rate / 2.0, os_rate, h);
-    double run = 0.0;
+    double etab[64], run = 0.0;
     for (int d = 0; d < 64; ++d) {
         taps_f[d] = 0.0f;
         if (d < kTaps) { taps_f[d] = (float)h[d]; run += h[d]; }
-        etab_f[d] = d >= kTaps - 1 ? 1.0f : (float)run;      // window fully covered -> sum h = 1
+        etab[d] = d >= kTaps - 1 ? 1.0 : run;                // E[d] = sum_{k<=d} h[k]; window fully covered -> 1
+        etab_f[d] = (float)etab[d];
+    }
+    // Collapsed-FIR table.  With t0 = oversamples since the newest half-chip boundary (2^-24 fixed point), the
+    // boundary ages are d_j = (t0 + cj[j]) >> 24; every time one of them steps, d_0+d_1+d_2+d_3 steps by one, so
+    // that sum (minus its minimum) names the age class.  Entry = s_4 + sum_j (s_j - s_{j+1}) E[min(d_j, 62)],
+    // evaluated in f64 and rounded once.
+    sc.dsum0 = (sc.cj[1] >> kTBits) + (sc.cj[2] >> kTBits) + (sc.cj[3] >> kTBits);
+    ytab.assign((size_t)32 * kYStride, 0.0f);
+    {
+        std::vector<uint64_t> starts{0};
+        const uint64_t one = 1ull << kTBits;
+        for (int j = 0; j < 4; ++j)
+            for (uint64_t n = 1; n * one < (uint64_t)sc.kmul + sc.cj[j] + one; ++n)
+                if (n * one >= sc.cj[j] && n * one - sc.cj[j] < sc.kmul) starts.push_back(n * one - sc.cj[j]);
+        std::sort(starts.begin(), starts.end());
+        for (uint64_t t0 : starts) {
+            uint32_t d[4], dsum = 0;
+            for (int j = 0; j < 4; ++j) { d[j] = (uint32_t)((t0 + sc.cj[j]) >> kTBits); dsum += d[j]; }
+            dsum -= d[0] * 0 + sc.dsum0;
+            if (dsum >= (uint32_t)kYStride) fail(R4WB_ERR_NOT_SUPPORTED, "FIR age class %u out of range", dsum);
+            for (uint32_t pat = 0; pat < 32; ++pat) {
+                double sgn[kJ + 1];
+                for (int j = 0; j <= kJ; ++j) sgn[j] = ((pat >> (kJ - j)) & 1u) ? -1.0 : 1.0;
+                double y = sgn[kJ];
+                for (int j = 0; j < kJ; ++j) y += (sgn[j] - sgn[j + 1]) * etab[d[j] < 62u ? d[j] : 62u];
+                ytab[(size_t)pat * kYStride + dsum] = (float)y;
+            }
+        }
     }
 
     tile_k = 10;
@@ -282,8 +318,8 @@ void SeqState::advance(const ScenarioModel& md, const std::vector<BlockSat>& tab
 
 size_t synth_smem_bytes(uint32_t n_sats, uint32_t nw64)
 {
-    size_t b = 63 * 32 * 4 + 32 * 8 * 16 + 64 * 4;
-    b += (size_t)n_sats * 128 * 4;
+    size_t b = ((size_t)(32 * kYStride + 128) * 4 + 15) & ~(size_t)15;   // ytab, taps, etab
+    b += (size_t)n_sats * kPerWords * 4;
     b += (size_t)n_sats * sizeof(TileSat);
     b += (size_t)n_sats * nw64 * 8;
     b += (size_t)n_sats * (nw64 + 1) * 4;
@@ -291,6 +327,6 @@ size_t synth_smem_bytes(uint32_t n_sats, uint32_t nw64)
     return (b + 15) & ~(size_t)15;
 }
 
-int synth_tile_samples(int K) { return 256 * 2 * K; }
+int synth_tile_samples(int K) { return kSynthThreads * 2 * K; }
 
 }  // namespace r4wb

@@ -76,7 +76,11 @@ int pcps_t(uint64_t code_length, double fs, double dmax, double dstep, const voi
     CodeLoad<T> cl{code, (uint32_t)std::min<uint64_t>(code_len, g.N)};
     for (uint32_t r = 0; r < F; ++r) {
         transform_item<-1, T>(s, cl, g, r, W.data(), NT);
-        for (uint32_t m = 0; m < M; ++m) C[(m << g.logF) + r] = cconj(s[fft_pad(nat_to_pos(m, g.logM))]);
+        for (uint32_t m = 0; m < M; ++m) {
+            const cx<T> v = s[fft_pad(nat_to_pos(m, g.logM))];
+            const T inv_n = (T)1 / (T)g.N;
+            C[(m << g.logF) + r] = cx<T>{v.re * inv_n, -v.im * inv_n};
+        }
     }
     PeakAcc<double> pair;
     peak_init(pair);
@@ -88,7 +92,7 @@ int pcps_t(uint64_t code_length, double fs, double dmax, double dstep, const voi
             transform_item<-1, T>(s, wl, g, r, W.data(), NT);
             for (uint32_t m = 0; m < M; ++m) X[(m << g.logF) + r] = s[fft_pad(nat_to_pos(m, g.logM))];
         }
-        ProductLoad<T> pl{X.data(), C.data(), (T)1 / (T)g.N};
+        ProductLoad<T> pl{X.data(), C.data()};
         for (uint32_t r = 0; r < F; ++r) {
             transform_item<+1, T>(s, pl, g, r, W.data(), NT);
             // per-thread accumulators merged in the kernel's order: lanes by xor butterflies, then warps

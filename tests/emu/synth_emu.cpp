@@ -65,19 +65,16 @@ struct Emu {
     }
 
     // k_synth, thread loops flattened.  only_sat >= 0 renders that satellite alone.
-    void render(const BlockSat* tb_tab, const BlockHdr* tb_hdr, uint32_t tb_begin, uint32_t tb_count, uint64_t out_first,
-                uint64_t out_n, float* out, uint64_t max_block_n, int only_sat, uint64_t* n_ambiguous)
+    template <int K>
+    void render_t(const BlockSat* tb_tab, const BlockHdr* tb_hdr, uint32_t tb_begin, uint32_t tb_count, uint64_t out_first,
+                  uint64_t out_n, float* out, uint64_t max_block_n, int only_sat, uint64_t* n_ambiguous)
     {
         const ScenConst& sc = md.sc;
         const uint32_t ns = sc.n_sats, nw64 = md.nw64;
-        const int K = md.tile_k, kThreads = 256;
+        constexpr int kThreads = kSynthThreads;
         const uint32_t TILE = (uint32_t)synth_tile_samples(K);
         const uint32_t tiles_per_block = (uint32_t)((max_block_n + TILE - 1) / TILE);
-        std::vector<float> erep(63 * 32);
-        std::vector<float4> coef(32 * 8);
-        for (uint32_t k = 0; k < 63 * 32; ++k) erep[k] = md.etab_f[k >> 5];
-        for (uint32_t k = 0; k < 32 * 8; ++k) coef[k] = coef_entry(k >> 3);
-        const uint64_t d8 = sc.delta46 * (uint64_t)kOversample;
+        const SynthK KK = make_synth_k(sc.delta46, sc.kmul, sc.cj, sc.dsum0, sc.spc);
         std::vector<TileSat> tsat(std::max(1u, ns));
         std::vector<uint32_t> w32((size_t)std::max(1u, ns) * (nw64 + 1));
         std::vector<uint2> t64((size_t)std::max(1u, ns) * nw64);
@@ -92,53 +89,42 @@ struct Emu {
             const uint32_t i_end = std::min(hd.n, i_begin + TILE);
             if (hd.first + i_end <= out_first || hd.first + i_begin >= out_first + out_n) continue;
             const BlockSat* row = tb_tab + (size_t)tb * ns;
-            for (uint32_t s = 0; s < ns; ++s) tsat[s] = tile_sat(row[s], i_begin, d8);
+            for (uint32_t s = 0; s < ns; ++s) tsat[s] = tile_sat(row[s], tb_tab, i_begin, KK.d8);
             for (uint32_t k = 0; k < ns * (nw64 + 1); ++k) {
                 const uint32_t s = k / (nw64 + 1), w = k - s * (nw64 + 1);
-                w32[k] = sign_word(md.codebits.data() + s * 128, tsat[s].hb, w);
-            }
-            for (uint32_t k = 0; k < ns * nw64; ++k) {
-                const uint32_t s = k / nw64, w = k - s * nw64;
-                t64[k] = make_uint2(w32[s * (nw64 + 1) + w], w32[s * (nw64 + 1) + w + 1]);
+                w32[k] = sign_word(md.perbits.data() + s * kPerWords, tsat[s].hb, w);
             }
             if (chunk == 0)
                 for (uint32_t k = 0; k < ns * 8; ++k) {
                     const uint32_t s = k >> 3, i = k & 7u;
                     float y = 0.0f;
-                    if ((row[s].flags & 1u) && i < hd.n)
-                        y = fir_direct(row[s], tb_tab, md.codebits.data() + s * 128, md.taps_f, (int)i, sc.delta46, sc.spc);
+                    if ((tsat[s].flags & 9u) == 9u && i < hd.n)
+                        y = fir_block_start(row[s], tb_tab, md.perbits.data() + s * kPerWords, md.taps_f, md.etab_f, (int)i, KK);
                     yfix[k] = y;
                 }
+            for (uint32_t k = 0; k < ns * nw64; ++k) {
+                const uint32_t s = k / nw64, w = k - s * nw64;
+                t64[k] = make_uint2(w32[s * (nw64 + 1) + w], w32[s * (nw64 + 1) + w + 1]);
+            }
             for (uint32_t tid = 0; tid < (uint32_t)kThreads; ++tid) {
-                const uint32_t lane = tid & 31u;
+                float2 ar[K], ai[K];
+                for (int k = 0; k < K; ++k) ar[k] = ai[k] = make_float2(0.0f, 0.0f);
+                for (uint32_t s = 0; s < ns; ++s) {
+                    if (only_sat >= 0 && (int)s != only_sat) continue;
+                    const TileSat ts = tsat[s];
+                    if (!(ts.flags & 1u)) continue;
+                    const SlowCtx slow{row + s, tb_tab, md.perbits.data() + s * kPerWords, md.taps_f};
+                    sat_accumulate<K>(ts, KK, t64.data() + s * nw64, md.ytab.data(), yfix.data() + s * 8, slow, tid, i_begin, i_end, ar, ai,
+                                      n_ambiguous);
+                }
                 for (int k = 0; k < K; ++k) {
                     const uint32_t ia = i_begin + 2 * tid + 2 * kThreads * k;
-                    if (ia >= i_end) continue;
-                    float2 v[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
-                    for (uint32_t s = 0; s < ns; ++s) {
-                        if (only_sat >= 0 && (int)s != only_sat) continue;
-                        const TileSat ts = tsat[s];
-                        if (!(ts.flags & 1u)) continue;
-                        for (uint32_t j = 0; j < 2; ++j) {
-                            const uint32_t i = ia + j;
-                            if (i >= i_end) continue;
-                            const uint64_t u = ts.u0 + (uint64_t)(i - i_begin) * d8;
-                            bool amb = false;
-                            float y = fir_fast(u, ts, t64.data() + s * nw64, erep.data(), coef.data(), sc.kmul, sc.cj, lane, amb);
-                            if (amb) {
-                                y = fir_direct(row[s], tb_tab, md.codebits.data() + s * 128, md.taps_f, (int)i, sc.delta46, sc.spc);
-                                if (n_ambiguous) ++*n_ambiguous;
-                            }
-                            if (chunk == 0 && i < 8) y = yfix[s * 8 + i];
-                            rotate_acc(y * ts.amp, carrier_phase(ts, i), v[j].x, v[j].y);
-                        }
-                    }
                     for (uint32_t j = 0; j < 2; ++j) {
                         const uint32_t i = ia + j;
                         if (i >= i_end) continue;
                         const uint64_t m = hd.first + i;
                         if (m < out_first || m >= out_first + out_n) continue;
-                        float2 val = v[j];
+                        float2 val = j == 0 ? make_float2(ar[k].x, ai[k].x) : make_float2(ar[k].y, ai[k].y);
                         if (noise && only_sat < 0) {
                             const float2 g = noise_of_sample(m, sc.seed);
                             val.x = fmaf(g.x, sc.noise_std, val.x);
@@ -150,6 +136,13 @@ struct Emu {
                 }
             }
         }
+    }
+
+    void render(const BlockSat* tb_tab, const BlockHdr* tb_hdr, uint32_t tb_begin, uint32_t tb_count, uint64_t out_first,
+                uint64_t out_n, float* out, uint64_t max_block_n, int only_sat, uint64_t* n_ambiguous)
+    {
+        if (md.tile_k == 5) render_t<5>(tb_tab, tb_hdr, tb_begin, tb_count, out_first, out_n, out, max_block_n, only_sat, n_ambiguous);
+        else render_t<10>(tb_tab, tb_hdr, tb_begin, tb_count, out_first, out_n, out, max_block_n, only_sat, n_ambiguous);
     }
 };
 

@@ -55,7 +55,7 @@ def test_scenario_kat_gps_2046(gpu, oracle):
     assert a.fft_size() == 2048
     r = a.acquire(sig, code, 5)
     _same(r, o.acquire(sig, code, 5))
-    assert int(r.code_phase) == 2046 - 321
+    assert int(r.code_phase) == 321 and r.doppler_hz == 1500.0      # corr[k] = sum x[n+k] c[n] peaks at the roll amount
 
 
 @pytest.mark.parametrize("name", ["e1c_8prn_20s_clean", "e1c_prn3_20s_withdoppler", "e1c_60s_all_prns", "e1c_8prn_60s_cn34_orbital"])
@@ -140,18 +140,21 @@ def test_exact_ties_take_lowest_index(gpu):
 
 
 def test_near_tie_guard_runs_f64(gpu, oracle):
-    """two cells 3e-6 apart (below f32 resolution of the pipeline): the f64 re-run must decide as the oracle does"""
-    L = 1023
+    """a Doppler 1 mHz off the midpoint of two bins: the two candidate cells differ by 2.4e-6 relative, the size of the f32
+    pipeline's own error, so the f64 re-run must decide — and must decide as the oracle does"""
+    L, fs = 1023, 1.023e6
     code = oracle.gps_ca_code(3)
     i = np.arange(L)
-    a1, a2 = 1.0, 1.0 - 1.5e-6
-    sig = a1 * np.roll(code, 200).astype(np.float64) + a2 * np.roll(code, 700).astype(np.float64)
-    acq = gpu.PcpsAcquisition(L, 1.023e6).with_doppler_range(0.0, 500.0)
-    r = acq.acquire(sig.astype(np.complex128), code, 3)
-    o = oracle.OraclePcps(L, 1.023e6).with_doppler_range(0.0, 500.0).acquire(sig.astype(np.complex128), code, 3)
+    sig = (np.roll(code, 200) * np.exp(2j * np.pi * 250.001 * i / fs)).astype(np.complex128)
+    acq = gpu.PcpsAcquisition(L, fs).with_doppler_range(500.0, 500.0)
+    r = acq.acquire(sig, code, 3)
+    o = oracle.OraclePcps(L, fs).with_doppler_range(500.0, 500.0).acquire(sig, code, 3)
     assert acq.guard_count() == 1
-    assert (r.code_phase, r.doppler_hz) == (o.code_phase, o.doppler_hz)
+    assert (r.code_phase, r.doppler_hz) == (o.code_phase, o.doppler_hz) == (200.0, 500.0)
     assert r.peak_metric == pytest.approx(o.peak_metric, rel=1e-9)
+    # a clear winner does not take the guard
+    acq.acquire((np.roll(code, 200) * np.exp(2j * np.pi * 480.0 * i / fs)).astype(np.complex128), code, 3)
+    assert acq.guard_count() == 0
 
 
 def test_batch_layouts_and_device_input(gpu, oracle):
