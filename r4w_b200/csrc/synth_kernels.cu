@@ -108,7 +108,7 @@ __device__ __forceinline__ SynthSmem carve_smem(unsigned char* raw, uint32_t n_s
 }
 
 template <int K, bool CF64>
-__global__ void __launch_bounds__(kThreads) k_synth(SynthArgs a)
+__global__ void __launch_bounds__(kThreads, K <= 5 ? 3 : 2) k_synth(SynthArgs a)
 {
     constexpr int TILE = kThreads * 2 * K;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -117,6 +117,7 @@ __global__ void __launch_bounds__(kThreads) k_synth(SynthArgs a)
 
     const uint32_t tid = threadIdx.x, lane = tid & 31u;
     const SynthK KK = make_synth_k(a.delta46, a.kmul, a.cj, a.dsum0, a.spc);
+    const PhiloxKeys PK = philox_keys(a.seed);
 
     // kernel-lifetime tables
     for (uint32_t k = tid; k < 32 * kYStride; k += kThreads) sm.ytab[k] = a.ytab[k];
@@ -173,7 +174,38 @@ __global__ void __launch_bounds__(kThreads) k_synth(SynthArgs a)
             sat_accumulate<K>(ts, KK, sm.t64 + s * a.nw64, sm.ytab, sm.yfix + s * 8, slow, tid, i_begin, i_end, ar, ai, nullptr);
         }
 
-        // noise, power, store
+        // noise, power, store.  A tile that lies inside the requested range and starts on a 16-byte boundary of the
+        // output (the usual case) stores float4 pairs without per-sample range checks.
+        const bool noise_on = !(a.flags & R4WB_FLAG_NOISE_OFF);
+        const uint64_t m0 = hd.first + i_begin;
+        const bool tile_plain = !CF64 && a.out_aligned16 && m0 >= a.out_first && hd.first + i_end <= a.out_first + a.out_n &&
+                                (((m0 - a.out_first) | (uint64_t)i_end) & 1ull) == 0;
+        if (tile_plain) {
+            float4* out = reinterpret_cast<float4*>(reinterpret_cast<float2*>(a.out) + (m0 - a.out_first)) + tid;
+            const uint64_t ctr0 = (m0 >> 1) + tid;               // m0 is even when out_first is; odd handled below
+            const bool m_even = (m0 & 1ull) == 0;
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                if (i_begin + 2 * tid + 2 * kThreads * k >= i_end) continue;
+                float4 v = make_float4(ar[k].x, ai[k].x, ar[k].y, ai[k].y);
+                if (noise_on) {
+                    float2 ga, gb2;
+                    const uint64_t ctr = ctr0 + (uint64_t)(kThreads * k);
+                    if (m_even) {
+                        noise_of_counter(ctr, PK, ga, gb2);
+                    } else {
+                        float2 t0, t1;
+                        noise_of_counter(ctr, PK, t0, ga);
+                        noise_of_counter(ctr + 1, PK, gb2, t1);
+                    }
+                    v.x = fmaf(ga.x, a.noise_std, v.x); v.y = fmaf(ga.y, a.noise_std, v.y);
+                    v.z = fmaf(gb2.x, a.noise_std, v.z); v.w = fmaf(gb2.y, a.noise_std, v.w);
+                }
+                pow_acc += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+                out[kThreads * k] = v;
+            }
+            continue;
+        }
 #pragma unroll
         for (int k = 0; k < K; ++k) {
             const uint32_t ia = i_begin + 2 * tid + 2 * kThreads * k;
@@ -181,16 +213,14 @@ __global__ void __launch_bounds__(kThreads) k_synth(SynthArgs a)
             const uint64_t m = hd.first + ia;                    // global sample index
             const bool has_b = ia + 1 < i_end;
             float2 va = make_float2(ar[k].x, ai[k].x), vb = make_float2(ar[k].y, ai[k].y);
-            if (!(a.flags & R4WB_FLAG_NOISE_OFF)) {
+            if (noise_on) {
                 float2 ga, gb2;
                 if ((m & 1ull) == 0) {      // one Philox draw covers both samples of the pair
-                    uint32_t r0, r1, r2, r3;
-                    const uint64_t ctr = m >> 1;
-                    philox4x32_10((uint32_t)ctr, (uint32_t)(ctr >> 32), 0u, 0u, (uint32_t)a.seed, (uint32_t)(a.seed >> 32), r0, r1, r2, r3);
-                    ga = gauss_pair(r0, r1); gb2 = gauss_pair(r2, r3);
+                    noise_of_counter(m >> 1, PK, ga, gb2);
                 } else {
-                    ga = noise_of_sample(m, a.seed);
-                    gb2 = noise_of_sample(m + 1, a.seed);
+                    float2 t0, t1;
+                    noise_of_counter(m >> 1, PK, t0, ga);
+                    noise_of_counter((m >> 1) + 1, PK, gb2, t1);
                 }
                 va.x = fmaf(ga.x, a.noise_std, va.x); va.y = fmaf(ga.y, a.noise_std, va.y);
                 vb.x = fmaf(gb2.x, a.noise_std, vb.x); vb.y = fmaf(gb2.y, a.noise_std, vb.y);

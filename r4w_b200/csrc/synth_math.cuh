@@ -530,8 +530,10 @@ struct SlowCtx {
 //   t64   [nw64] per-tile sign table as overlapping 64-bit windows (word k = bits 32k .. 32k+63)
 //   ytab  [32][kYStride] collapsed-FIR outputs per (sign pattern, boundary-age class)
 //   yfix  first 8 outputs of the block when its window reaches into a block with another delay (flags bit3)
-template <int NK>
-R4WB_HD void sat_accumulate(const TileSat& ts, const SynthK& K, const uint2* __restrict__ t64, const float* __restrict__ ytab,
+//   GENERAL = false: no ambiguity checks, phasor recurrence, DYN compile-time (the common case, straight-line code)
+//   GENERAL = true:  checks / per-sample sincos / varying Doppler selected at run time from ts.flags
+template <int NK, bool GENERAL, bool DYN>
+R4WB_HD void sat_accumulate_t(const TileSat& ts, const SynthK& K, const uint2* __restrict__ t64, const float* __restrict__ ytab,
                             const float* __restrict__ yfix, const SlowCtx& slow, uint32_t tid, uint32_t i_begin, uint32_t i_end,
                             float2 (&ar)[NK], float2 (&ai)[NK], uint64_t* n_ambiguous)
 {
@@ -547,7 +549,8 @@ R4WB_HD void sat_accumulate(const TileSat& ts, const SynthK& K, const uint2* __r
     phasor(pha, &sa, &ca);
     phasor(pha + gb, &sb, &cb);
     float2 zr = make_float2(ca * ts.amp, cb * ts.amp), zi = make_float2(sa * ts.amp, sb * ts.amp);
-    const bool dyn = (ts.flags & 16u) != 0u, exact_rot = (ts.flags & 4u) != 0u, check = (ts.flags & 2u) != 0u;
+    const bool dyn = GENERAL ? (ts.flags & 16u) != 0u : DYN;
+    const bool exact_rot = GENERAL && (ts.flags & 4u) != 0u, check = GENERAL && (ts.flags & 2u) != 0u;
     float wr = ts.wr, wi = ts.wi, dr = 0.0f, di = 0.0f;
     if (dyn) {
         const float dl = ts.th1 * (float)(2u * tid);
@@ -575,7 +578,7 @@ R4WB_HD void sat_accumulate(const TileSat& ts, const SynthK& K, const uint2* __r
         const uint32_t cls_a = (ta0 >> kTBits) + (ta1 >> kTBits) + (ta2 >> kTBits) + (ta3 >> kTBits) - K.dsum0;
         const uint32_t cls_b = (tb0 >> kTBits) + (tb1 >> kTBits) + (tb2 >> kTBits) + (tb3 >> kTBits) - K.dsum0;
         // 5-sign patterns out of one 64-bit window
-        const uint2 w = t64[hi >> 5];
+        const uint2 w = *reinterpret_cast<const uint2*>(reinterpret_cast<const unsigned char*>(t64) + ((hi >> 2) & 0x3ffffff8u));
         const uint32_t pa = funnel_r(w.x, w.y, hi) & 31u;
         const uint32_t pb = funnel_rc(w.x, w.y, (hi & 31u) + (hib - hi)) & 31u;
         float2 y = make_float2(ytab[pa * (uint32_t)kYStride + cls_a], ytab[pb * (uint32_t)kYStride + cls_b]);
@@ -614,39 +617,110 @@ R4WB_HD void sat_accumulate(const TileSat& ts, const SynthK& K, const uint2* __r
     }
 }
 
+template <int NK>
+R4WB_HD void sat_accumulate(const TileSat& ts, const SynthK& K, const uint2* __restrict__ t64, const float* __restrict__ ytab,
+                            const float* __restrict__ yfix, const SlowCtx& slow, uint32_t tid, uint32_t i_begin, uint32_t i_end,
+                            float2 (&ar)[NK], float2 (&ai)[NK], uint64_t* n_ambiguous)
+{
+    if (ts.flags & 6u) sat_accumulate_t<NK, true, false>(ts, K, t64, ytab, yfix, slow, tid, i_begin, i_end, ar, ai, n_ambiguous);
+    else if (ts.flags & 16u) sat_accumulate_t<NK, false, true>(ts, K, t64, ytab, yfix, slow, tid, i_begin, i_end, ar, ai, n_ambiguous);
+    else sat_accumulate_t<NK, false, false>(ts, K, t64, ytab, yfix, slow, tid, i_begin, i_end, ar, ai, n_ambiguous);
+}
+
 // ----------------------------------------------------------------------------------------------
 // noise: Philox4x32-10 keyed by the scenario seed, counter = global sample index / 2 (one draw -> two samples)
-R4WB_HD void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
+struct PhiloxKeys { uint32_t k0[10], k1[10]; };
+
+R4WB_HD PhiloxKeys philox_keys(uint64_t seed)
+{
+    PhiloxKeys K;
+    uint32_t a = (uint32_t)seed, b = (uint32_t)(seed >> 32);
+#pragma unroll
+    for (int r = 0; r < 10; ++r) { K.k0[r] = a; K.k1[r] = b; a += 0x9E3779B9u; b += 0xBB67AE85u; }
+    return K;
+}
+
+R4WB_HD void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const PhiloxKeys& K,
                            uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3)
 {
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
         const uint32_t hi0 = umulhi32(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
         const uint32_t hi1 = umulhi32(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
-        c0 = hi1 ^ c1 ^ k0; c1 = lo1; c2 = hi0 ^ c3 ^ k1; c3 = lo0;
-        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+        c0 = hi1 ^ c1 ^ K.k0[r]; c1 = lo1; c2 = hi0 ^ c3 ^ K.k1[r]; c3 = lo0;
     }
     r0 = c0; r1 = c1; r2 = c2; r3 = c3;
 }
 
-// Box-Muller on two 32-bit words: u1 = ((a>>8)+1) 2^-24 in (0,1], angle = 2 pi ((b>>8) 2^-24 - 1/2)
+// uint32 -> float, rounded toward zero (never reaches 2^32)
+R4WB_HD float u32_to_float_rz(uint32_t a)
+{
+#ifdef __CUDA_ARCH__
+    return __uint2float_rz(a);
+#else
+    if (a >> 24) {
+        int top = 31;
+        while (!((a >> top) & 1u)) --top;
+        const int sh = top - 23;
+        a = (a >> sh) << sh;
+    }
+    return (float)a;
+#endif
+}
+R4WB_HD float approx_lg2(float x)
+{
+#ifdef __CUDA_ARCH__
+    float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r;
+#else
+    return log2f(x);
+#endif
+}
+R4WB_HD float approx_sqrt(float x)
+{
+#ifdef __CUDA_ARCH__
+    float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r;
+#else
+    return sqrtf(x);
+#endif
+}
+R4WB_HD void approx_sincos(float x, float* s, float* c)
+{
+#ifdef __CUDA_ARCH__
+    asm("sin.approx.ftz.f32 %0, %1;" : "=f"(*s) : "f"(x));
+    asm("cos.approx.ftz.f32 %0, %1;" : "=f"(*c) : "f"(x));
+#else
+    *s = sinf(x);
+    *c = cosf(x);
+#endif
+}
+
+// Box-Muller on two 32-bit words: u1 = (a + 256) 2^-32 in [2^-24, 1], angle = 2 pi (b 2^-32 - 1/2)
 R4WB_HD float2 gauss_pair(uint32_t a, uint32_t b)
 {
-    const float u1 = (float)((a >> 8) + 1u) * 5.9604644775390625e-08f;
-    const float ang = ((float)(b >> 8) * 5.9604644775390625e-08f - 0.5f) * 6.283185307179586f;
-    const float r = sqrtf(-1.3862943611198906f * fast_log2(u1));
+    const float u1 = fmaf(u32_to_float_rz(a), 2.3283064365386963e-10f, 5.9604644775390625e-08f);
+    const float ang = fmaf(u32_to_float_rz(b), 1.4629180792671596e-09f /* 2 pi 2^-32 */, -3.14159265358979f);
+    const float r = approx_sqrt(-1.3862943611198906f * approx_lg2(u1));
     float sn, cs;
-    fast_sincos(ang, &sn, &cs);
+    approx_sincos(ang, &sn, &cs);
     return make_float2(r * cs, r * sn);
+}
+
+// unit-variance noise pairs (re, im) of the two samples 2c and 2c+1 sharing Philox counter c
+R4WB_HD void noise_of_counter(uint64_t ctr, const PhiloxKeys& K, float2& g0, float2& g1)
+{
+    uint32_t r0, r1, r2, r3;
+    philox4x32_10((uint32_t)ctr, (uint32_t)(ctr >> 32), 0u, 0u, K, r0, r1, r2, r3);
+    g0 = gauss_pair(r0, r1);
+    g1 = gauss_pair(r2, r3);
 }
 
 // the (re, im) unit-variance noise pair of global sample m
 R4WB_HD float2 noise_of_sample(uint64_t m, uint64_t seed)
 {
-    uint32_t r0, r1, r2, r3;
-    const uint64_t ctr = m >> 1;
-    philox4x32_10((uint32_t)ctr, (uint32_t)(ctr >> 32), 0u, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), r0, r1, r2, r3);
-    return (m & 1ull) ? gauss_pair(r2, r3) : gauss_pair(r0, r1);
+    const PhiloxKeys K = philox_keys(seed);
+    float2 g0, g1;
+    noise_of_counter(m >> 1, K, g0, g1);
+    return (m & 1ull) ? g1 : g0;
 }
 
 // test hook: a BlockSat entry as 12 doubles

@@ -3,6 +3,7 @@
 // No CUDA runtime calls in this file.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "synth_math.cuh"
@@ -241,6 +242,7 @@ ScenarioModel::ScenarioModel(const r4wb_scenario_cfg& c_in) : cfg(c_in)
     }
 
     tile_k = 10;
+    if (const char* e = std::getenv("R4WB_SYNTH_TILE_K")) { if (std::atoi(e) == 5) tile_k = 5; }   // tuning hook
     {
         const double span = std::ceil((double)synth_tile_samples(tile_k) * kOversample * (2.0 / sc.spc)) + 2.0;
         nw64 = (uint32_t)std::ceil((span + 8.0) / 32.0) + 1u;

@@ -177,10 +177,12 @@ def test_batch_layouts_and_device_input(gpu, oracle):
             assert single == host_res[s][c]
     for k, s in enumerate((0, 2, 4)):
         assert strided[k] == host_res[s]
-    # present PRNs land on the same Doppler bin in consecutive snapshots (static scenario)
+    # present PRNs stay within one Doppler bin of each other in consecutive snapshots (static scenario; a Doppler between
+    # two bins may land on either with noise)
     for c, prn in enumerate(ALL8):
         if prn in (3, 25, 8, 15):
-            assert len({host_res[s][c].doppler_hz for s in range(5)}) == 1
+            dops = [host_res[s][c].doppler_hz for s in range(5)]
+            assert max(dops) - min(dops) <= 250.0
     with pytest.raises(ValueError):
         acq.acquire_batch(host, 6, 20000, 20000, codes, ALL8)
 
