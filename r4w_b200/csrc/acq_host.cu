@@ -2,6 +2,7 @@
 // through the FFT kernels, re-runs near-ties in f64, and finishes the AcquisitionResult in f64 on the host.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "acq.cuh"
@@ -20,6 +21,22 @@ template <typename T>
 void launch_inv_peak(const AcqGeom& g, uint32_t rows, const cx<T>* X, const cx<T>* C, const cx<T>* W, RowPeak* peaks, double* grid,
                      cudaStream_t st);
 void launch_pair_reduce(const AcqGeom& g, uint32_t n_snap, const RowPeak* peaks, PairPeak* out, cudaStream_t st);
+// register-resident f32 fast path for fft_size 32768 (acq_rf_kernels.cu)
+bool rf_supported(const AcqGeom& g);
+void launch_rf_fwd_input(const AcqGeom& g, uint32_t rows, const void* input, uint32_t in64, uint64_t stride, uint32_t take,
+                         const cx<float>* W, cx<float>* out, cudaStream_t st);
+void launch_rf_fwd_codes(const AcqGeom& g, uint32_t n_codes, const int8_t* codes, uint64_t code_len, uint32_t take, const cx<float>* W,
+                         cx<float>* out, cudaStream_t st);
+void launch_rf_inv_peak(const AcqGeom& g, uint32_t rows, const cx<float>* X, const cx<float>* C, const cx<float>* W, RowPeak* peaks,
+                        cudaStream_t st);
+
+// tuning / A-B hook: R4WB_ACQ_ENGINE=smem forces the in-shared-memory engine for every size
+static bool rf_enabled()
+{
+    static int v = -1;
+    if (v < 0) { const char* e = std::getenv("R4WB_ACQ_ENGINE"); v = (e && std::strcmp(e, "smem") == 0) ? 0 : 1; }
+    return v == 1;
+}
 
 // f32 results whose two best cells are closer than this (relative) are re-run in f64 so the reported
 // (lag, Doppler bin) is the one an f64 evaluation (the reference's arithmetic) picks
@@ -119,9 +136,18 @@ void Pcps::run(AcqWork<T>& w, const void* d_input, r4wb_fmt fmt, uint64_t s0, ui
     }
     const uint32_t take = (uint32_t)std::min<uint64_t>(n_input, g.L);               // input.iter().take(samples_per_code)
     const uint32_t code_take = (uint32_t)std::min<uint64_t>(code_len, g.N);         // code_fft.resize(fft_size)
+    // f32, fft_size 32768, no surface dump: the register-resident engine (one CTA per row / per (row, code))
+    const bool fast = sizeof(T) == 4 && d_grid == nullptr && rf_enabled() && rf_supported(g);
+    AcqGeom gr = g;                                                                 // geometry of the RowPeak table
+    if (fast) gr.logF = 0;
+    const uint32_t Fr = 1u << gr.logF;
     w.c.reserve((size_t)nc * g.N);
     prof_begin(0);
-    launch_fwd_codes<T>(g, nc, d_codes + (size_t)c0 * code_len, code_len, code_take, w.tw.p, w.c.p, st);
+    if (fast)
+        launch_rf_fwd_codes(g, nc, d_codes + (size_t)c0 * code_len, code_len, code_take, reinterpret_cast<const cx<float>*>(w.tw.p),
+                            reinterpret_cast<cx<float>*>(w.c.p), st);
+    else
+        launch_fwd_codes<T>(g, nc, d_codes + (size_t)c0 * code_len, code_len, code_take, w.tw.p, w.c.p, st);
     prof_end();
 
     const size_t row_bytes = (size_t)g.N * sizeof(cx<T>);
@@ -129,19 +155,27 @@ void Pcps::run(AcqWork<T>& w, const void* d_input, r4wb_fmt fmt, uint64_t s0, ui
     chunk = std::min<uint64_t>(chunk, std::max<uint64_t>(1, 0x3fffffffull / ((uint64_t)std::max(1u, g.D) * nc * F)));
     chunk = std::min(chunk, ns);
     w.x.reserve((size_t)chunk * g.D * g.N);
-    d_rowpeaks_.reserve((size_t)chunk * g.D * nc * F);
+    d_rowpeaks_.reserve((size_t)chunk * g.D * nc * Fr);
     const size_t bps = fmt == R4WB_FMT_CF64 ? 16 : 8;
     for (uint64_t s = 0; s < ns; s += chunk) {
         const uint32_t cs = (uint32_t)std::min<uint64_t>(chunk, ns - s);
         const unsigned char* in = static_cast<const unsigned char*>(d_input) + (s0 + s) * stride * bps;
         prof_begin(1);
-        launch_fwd_input<T>(g, cs * g.D, in, fmt == R4WB_FMT_CF64 ? 1u : 0u, stride, take, w.tw.p, w.x.p, st);
+        if (fast)
+            launch_rf_fwd_input(g, cs * g.D, in, fmt == R4WB_FMT_CF64 ? 1u : 0u, stride, take, reinterpret_cast<const cx<float>*>(w.tw.p),
+                                reinterpret_cast<cx<float>*>(w.x.p), st);
+        else
+            launch_fwd_input<T>(g, cs * g.D, in, fmt == R4WB_FMT_CF64 ? 1u : 0u, stride, take, w.tw.p, w.x.p, st);
         prof_end();
         prof_begin(2);
-        launch_inv_peak<T>(g, cs * g.D, w.x.p, w.c.p, w.tw.p, d_rowpeaks_.p, d_grid, st);
+        if (fast)
+            launch_rf_inv_peak(g, cs * g.D, reinterpret_cast<const cx<float>*>(w.x.p), reinterpret_cast<const cx<float>*>(w.c.p),
+                               reinterpret_cast<const cx<float>*>(w.tw.p), d_rowpeaks_.p, st);
+        else
+            launch_inv_peak<T>(g, cs * g.D, w.x.p, w.c.p, w.tw.p, d_rowpeaks_.p, d_grid, st);
         prof_end();
         prof_begin(3);
-        launch_pair_reduce(g, cs, d_rowpeaks_.p, d_out + s * nc, st);
+        launch_pair_reduce(gr, cs, d_rowpeaks_.p, d_out + s * nc, st);
         prof_end();
     }
 }
