@@ -38,6 +38,16 @@ FP32_PEAK_TFLOPS = 74.4        # 148 SM x 128 lanes x 2 x 1.965 GHz (nominal; ME
 HBM_FALLBACK_GBS = 6650.0      # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
 
 
+def ncu_traffic(kernel: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed ncu capture of this
+    bench command (profiles/ncu_traffic.json, written by tools/ncu_summary.py --traffic); None when not captured."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            return json.load(f).get(kernel)
+    except Exception:
+        return None
+
+
 def hbm_peak():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -299,11 +309,11 @@ def run_b200(args):
         O.build()
         cores = os.cpu_count() or 1
         th_s = max(1, min(len(prns), cores))
-        v_s, n_s, dt_s = cpu_synth(cfg, 1.0, th_s)                    # 1 s of the scenario
-        ns_c = max(1, min(4, cores // 4))
+        v_s, n_s, dt_s = cpu_synth(cfg, 3.0, th_s)                    # 3 s of the scenario: ~10-15 s of host work
+        ns_c = max(1, min(n_snap, 8 * cores))                         # ~10 s of host work on all cores
         v_a, c_a, dt_a = cpu_acq(host_np, codes, prns, ns_c, cores)
         cpu = ({"value": v_s, "unit": "Msamples/s", "cores": th_s, "kind": "port",
-                "sample": f"1 s of {WORKLOAD} ({n_s} samples, {dt_s:.1f} s wall), oracle port, one thread per satellite"},
+                "sample": f"3 s of {WORKLOAD} ({n_s} samples, {dt_s:.1f} s wall), oracle port, one thread per satellite"},
                {"value": v_a, "unit": "cells/s", "cores": cores, "kind": "port",
                 "sample": f"{ns_c} snapshot(s) x {len(prns)} PRNs x {bins} bins ({c_a} cells, {dt_a:.1f} s wall), oracle port, {cores} threads"})
     _lib.check(_lib.lib().r4wb_host_free(host))
@@ -322,15 +332,15 @@ def run_b200(args):
                        "step": "synth then acquire; ms_per_step/value cover the synthesis half, acq.* the acquisition half, ms_step_total both"},
             "ms_step_total": ms_total,
             "roofline": {"bound": "hbm", "kernel": "k_synth", "achieved": synth_gbs, "peak": peak, "unit": "GB/s", "frac": synth_gbs / peak,
-                         "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": n * 8,
+                         "traffic": ncu_traffic("k_synth"), "peak_source": peak_src, "algorithmic_bytes_per_launch": n * 8,
                          "note": "8 B per output sample (one cf32 store); CUDA events on the launching stream"},
             "e2e": {"value": total_samples / (ms_syn_e2e * 1e-3) / 1e6, "unit": "Msamples/s", "h2d_bytes_per_step": 0,
                     "d2h_bytes_per_step": n * 8, "api": "r4wb_scenario_generate(..., R4WB_MEM_HOST, CF32) into pinned host memory"},
             "acq": {"metric": "pcps_acq_cells_per_s", "value": cells / (ms_acq * 1e-3), "unit": "cells/s", "ms_per_step": ms_acq,
                     "cells_per_step": cells, "f64_guard_reruns": guards,
                     "kernel_ms": {k: v[0] for k, v in prof.items()}, "kernel_launches": {k: v[1] for k, v in prof.items()},
-                    "roofline": {"bound": "fp32", "kernel": "k_inv_peak (+k_fwd)", "achieved": acq_tflops, "peak": FP32_PEAK_TFLOPS,
-                                 "unit": "TFLOP/s", "frac": (acq_tflops / FP32_PEAK_TFLOPS) if acq_tflops else None, "traffic": None,
+                    "roofline": {"bound": "fp32", "kernel": "k_rf_inv_peak (+k_rf_fwd)", "achieved": acq_tflops, "peak": FP32_PEAK_TFLOPS,
+                                 "unit": "TFLOP/s", "frac": (acq_tflops / FP32_PEAK_TFLOPS) if acq_tflops else None, "traffic": ncu_traffic("k_rf_inv_peak"),
                                  "peak_source": "nominal FP32 FMA peak (148 SM x 128 lanes x 2 x 1.965 GHz)",
                                  "note": f"{FLOP_PER_CELL} reference-equivalent flop per cell / summed CUDA-event time of the forward and inverse FFT kernels"},
                     "e2e": {"value": cells / (ms_acq_e2e * 1e-3), "unit": "cells/s", "h2d_bytes_per_step": n_snap * CODE_LENGTH * 8,
