@@ -62,6 +62,7 @@ struct ScenConst {
     uint32_t kmul;                  // round(S * 2^24), S = oversamples per half-chip
     uint32_t cj[8];                 // round(j * S * 2^24)
     uint32_t dsum0;                 // (cj[1] >> 24) + (cj[2] >> 24) + (cj[3] >> 24)
+    uint32_t lut_den;               // D when the boundary-age class can be read from a D-entry table (0: compute it)
     float noise_std;
     uint64_t seed;
 };
@@ -87,13 +88,36 @@ static_assert(sizeof(BlockSat) == 80, "BlockSat layout");
 
 struct BlockHdr { uint64_t first; uint32_t n; uint32_t pad; };
 
+// per-tile, per-satellite state (built by k_tile_params, read by k_synth)
+struct TileSat {
+    uint64_t u0;        // half-chip position (18.46) at the newest oversample of the tile's first sample
+    uint64_t phi;
+    long long f, df;
+    uint32_t hb;        // half-chip index of bit 0 of the sign table
+    float amp;
+    uint32_t flags;     // bit0 visible, bit1 ambiguity checks needed, bit2 per-sample sincos (large Doppler rate),
+                        // bit3 first 8 samples of the block come from yfix, bit4 Doppler varies inside the block
+    uint32_t eps_t;
+    float wr, wi;       // e^{j phase advance over 2*kSynthThreads samples}, at the tile's first sample
+    float th1, th2;     // radians: growth of that advance per sample index, and per step of 2*kSynthThreads samples
+};
+// one record per (table block, chunk, satellite): 96 bytes = 6 x 16
+struct TileRec {
+    TileSat ts;
+    float yfix[8];      // first 8 FIR outputs of the block when its delay differs from its predecessor's (chunk 0, flags bit3)
+};
+static_assert(sizeof(TileSat) == 64 && sizeof(TileRec) == 96, "TileRec layout");
+
 struct SynthArgs {
     const BlockSat* tab;       // [n_tab_blocks][n_sats]
     const BlockHdr* hdr;       // [n_tab_blocks]
+    const TileRec* tiles;      // [n_tab_blocks][tiles_per_block][n_sats]
     const uint32_t* perbits;   // [n_sats][kPerWords] half-chip signs of one primary-code period (code x BOC(1,1)), bit=1 -> -1
     const float* taps;         // [64] h[k] (f32), [63] = 0
     const float* etab;         // [64] E[d] = sum_{k<=d} h[k]  (E[62] = E[63] = 1)
     const float* ytab;         // [32][kYStride] collapsed-FIR outputs per (sign pattern, boundary-age class)
+    const uint8_t* clslut;     // [lut_den, padded to 16] boundary-age class of half-chip fraction bin q (swizzled, see cls_lut_index)
+    uint32_t lut_den;
     void* out;                 // cf32 or cf64, out[0] <-> sample out_first
     double* power_sum;         // optional accumulator of |s|^2
     uint64_t out_first, out_n; // only samples in [out_first, out_first + out_n) are written
@@ -127,6 +151,7 @@ struct ScenarioModel {
     float taps_f[64];
     float etab_f[64];
     std::vector<float> ytab;            // [32][kYStride]
+    std::vector<uint8_t> clslut;        // [lut_den padded to 16]
     int tile_k = 10;                    // samples per tile = 256 threads * 2 * tile_k
     uint32_t nw64 = 0;
     bool any_dynamic = false, any_var_visibility = false;
@@ -149,7 +174,7 @@ struct SeqState {
     void advance(const ScenarioModel& md, const std::vector<BlockSat>& tab, uint32_t n);
 };
 
-size_t synth_smem_bytes(uint32_t n_sats, uint32_t nw64);
+size_t synth_smem_bytes(uint32_t n_sats, uint32_t nw64, uint32_t lut_den);
 int synth_tile_samples(int K);
 
 class Scenario {
@@ -174,8 +199,10 @@ public:
     void debug_block(uint64_t block, uint32_t sat, double* out12);
 
 private:
-    void launch_synth(const BlockSat* tab, const BlockHdr* hdr, uint32_t tb_begin, uint32_t tb_count,
+    void launch_synth(const BlockSat* tab, const BlockHdr* hdr, const TileRec* tiles, uint32_t tb_begin, uint32_t tb_count,
                       uint64_t out_first, uint64_t out_n, void* d_out, r4wb_fmt fmt, uint64_t max_block_n);
+    SynthArgs base_args(const BlockSat* tab, const BlockHdr* hdr, uint64_t max_block_n) const;
+    void build_tiles(const SynthArgs& a, uint32_t tb_begin, uint32_t tb_count, TileRec* out);
     void build_canonical_table(uint64_t blk_begin, uint64_t blk_end);   // fills d_tab_/d_hdr_ for [blk_begin, blk_end)
     void render_to(uint64_t first, uint64_t n, void* dst, r4wb_mem where, r4wb_fmt fmt);
 
@@ -188,8 +215,11 @@ private:
     DevBuf<PhaseSegment> d_segments_;
     DevBuf<uint32_t> d_perbits_;
     DevBuf<float> d_taps_, d_etab_, d_ytab_;
+    DevBuf<uint8_t> d_clslut_;
     DevBuf<BlockSat> d_tab_, d_seq_tab_;
     DevBuf<BlockHdr> d_hdr_, d_seq_hdr_;
+    DevBuf<TileRec> d_tiles_, d_seq_tiles_;
+    uint32_t tiles_per_block_cached_ = 0;   // d_tiles_ holds records for this tiling of the canonical table (0: none)
     DevBuf<double> d_power_;
     DevBuf<unsigned char> d_stage_;
     uint64_t tab_blk0_ = 0, tab_blk1_ = 0;   // canonical block range currently held by d_tab_

@@ -13,6 +13,7 @@ void launch_synth_kernel(const SynthArgs& a, int K, bool cf64, int grid, cudaStr
 int synth_max_blocks_per_sm(int K, bool cf64, size_t smem);
 void launch_block_params(const ScenConst&, const SatConst*, const PhaseSegment*, uint64_t, uint32_t, BlockSat*, BlockHdr*, cudaStream_t);
 void launch_phase_scan(const SatConst*, uint32_t, uint32_t, BlockSat*, cudaStream_t);
+void launch_tile_params(const SynthArgs& a, uint32_t tb_begin, uint32_t tb_count, uint32_t tile_samples, TileRec* out, cudaStream_t st);
 
 Scenario::Scenario(const r4wb_scenario_cfg& cfg) : md_(cfg)
 {
@@ -25,6 +26,7 @@ Scenario::Scenario(const r4wb_scenario_cfg& cfg) : md_(cfg)
     R4WB_CUDA(cudaMemcpyAsync(d_ytab_.reserve(md_.ytab.size()), md_.ytab.data(), md_.ytab.size() * 4, cudaMemcpyHostToDevice, st));
     R4WB_CUDA(cudaMemcpyAsync(d_taps_.reserve(64), md_.taps_f, sizeof md_.taps_f, cudaMemcpyHostToDevice, st));
     R4WB_CUDA(cudaMemcpyAsync(d_etab_.reserve(64), md_.etab_f, sizeof md_.etab_f, cudaMemcpyHostToDevice, st));
+    R4WB_CUDA(cudaMemcpyAsync(d_clslut_.reserve(md_.clslut.size()), md_.clslut.data(), md_.clslut.size(), cudaMemcpyHostToDevice, st));
     d_power_.reserve(1);
     R4WB_CUDA(cudaMemsetAsync(d_power_.p, 0, sizeof(double), st));
     R4WB_CUDA(cudaStreamSynchronize(st));
@@ -65,24 +67,43 @@ void Scenario::build_canonical_table(uint64_t blk_begin, uint64_t blk_end)
     tab_blk0_ = blk_begin;
     tab_blk1_ = blk_end;
     tab_valid_ = true;
+    // per-tile records for the canonical tiling (block size B)
+    {
+        SynthArgs a = base_args(d_tab_.p, d_hdr_.p, sc.B);
+        d_tiles_.reserve(std::max<size_t>(1, (size_t)nblk * a.tiles_per_block * sc.n_sats));
+        build_tiles(a, 0, (uint32_t)nblk, d_tiles_.p);
+    }
 }
 
-void Scenario::launch_synth(const BlockSat* tab, const BlockHdr* hdr, uint32_t tb_begin, uint32_t tb_count,
-                            uint64_t out_first, uint64_t out_n, void* d_out, r4wb_fmt fmt, uint64_t max_block_n)
+SynthArgs Scenario::base_args(const BlockSat* tab, const BlockHdr* hdr, uint64_t max_block_n) const
 {
     const ScenConst& sc = md_.sc;
     SynthArgs a{};
-    a.tab = tab; a.hdr = hdr; a.perbits = d_perbits_.p; a.taps = d_taps_.p; a.etab = d_etab_.p; a.ytab = d_ytab_.p;
-    a.out = d_out; a.power_sum = d_power_.p;
-    a.out_first = out_first; a.out_n = out_n;
-    a.tb_begin = tb_begin; a.tb_count = tb_count;
+    a.tab = tab; a.hdr = hdr; a.perbits = d_perbits_.p; a.taps = d_taps_.p; a.etab = d_etab_.p; a.ytab = d_ytab_.p; a.clslut = d_clslut_.p; a.lut_den = sc.lut_den;
     const uint32_t tile = (uint32_t)synth_tile_samples(md_.tile_k);
     a.tiles_per_block = (uint32_t)((max_block_n + tile - 1) / tile);
     a.n_sats = sc.n_sats; a.nw64 = md_.nw64; a.flags = sc.flags;
-    a.out_aligned16 = ((uintptr_t)d_out & 15u) == 0 ? 1u : 0u;
     a.delta46 = sc.delta46; a.kmul = sc.kmul; a.dsum0 = sc.dsum0;
     for (int j = 0; j < 8; ++j) a.cj[j] = sc.cj[j];
     a.spc = sc.spc; a.noise_std = sc.noise_std; a.seed = sc.seed;
+    return a;
+}
+
+// per-tile records of table blocks [tb_begin, tb_begin + tb_count) (k_tile_params)
+void Scenario::build_tiles(const SynthArgs& a, uint32_t tb_begin, uint32_t tb_count, TileRec* out)
+{
+    launch_tile_params(a, tb_begin, tb_count, (uint32_t)synth_tile_samples(md_.tile_k), out, current_stream());
+}
+
+void Scenario::launch_synth(const BlockSat* tab, const BlockHdr* hdr, const TileRec* tiles, uint32_t tb_begin, uint32_t tb_count,
+                            uint64_t out_first, uint64_t out_n, void* d_out, r4wb_fmt fmt, uint64_t max_block_n)
+{
+    SynthArgs a = base_args(tab, hdr, max_block_n);
+    a.tiles = tiles;
+    a.out = d_out; a.power_sum = d_power_.p;
+    a.out_first = out_first; a.out_n = out_n;
+    a.tb_begin = tb_begin; a.tb_count = tb_count;
+    a.out_aligned16 = ((uintptr_t)d_out & 15u) == 0 ? 1u : 0u;
 
     static int sm_count = 0;
     if (!sm_count) {
@@ -91,7 +112,7 @@ void Scenario::launch_synth(const BlockSat* tab, const BlockHdr* hdr, uint32_t t
         R4WB_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
     }
     const bool cf64 = fmt == R4WB_FMT_CF64;
-    const size_t smem = synth_smem_bytes(a.n_sats, a.nw64);
+    const size_t smem = synth_smem_bytes(a.n_sats, a.nw64, a.lut_den);
     const int per_sm = std::max(1, synth_max_blocks_per_sm(md_.tile_k, cf64, smem));
     const uint64_t n_tiles = (uint64_t)tb_count * a.tiles_per_block;
     const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>(n_tiles, (uint64_t)sm_count * per_sm));
@@ -110,7 +131,7 @@ void Scenario::render_to(uint64_t first, uint64_t n, void* dst, r4wb_mem where, 
     const uint64_t tb0 = tab_blk0_;
 
     if (where == R4WB_MEM_DEVICE) {
-        launch_synth(d_tab_.p, d_hdr_.p, (uint32_t)(b0 - tb0), (uint32_t)(b1 - b0 + 1), first, n, dst, fmt, sc.B);
+        launch_synth(d_tab_.p, d_hdr_.p, d_tiles_.p, (uint32_t)(b0 - tb0), (uint32_t)(b1 - b0 + 1), first, n, dst, fmt, sc.B);
         return;
     }
     // host destination: render chunk by chunk into a device staging buffer and copy out
@@ -119,7 +140,7 @@ void Scenario::render_to(uint64_t first, uint64_t n, void* dst, r4wb_mem where, 
     for (uint64_t cb = b0; cb <= b1; cb += chunk_blocks) {
         const uint64_t ce = std::min(b1 + 1, cb + chunk_blocks);
         const uint64_t f = std::max(first, cb * sc.B), l = std::min(first + n, ce * sc.B);
-        launch_synth(d_tab_.p, d_hdr_.p, (uint32_t)(cb - tb0), (uint32_t)(ce - cb), f, l - f, stage, fmt, sc.B);
+        launch_synth(d_tab_.p, d_hdr_.p, d_tiles_.p, (uint32_t)(cb - tb0), (uint32_t)(ce - cb), f, l - f, stage, fmt, sc.B);
         R4WB_CUDA(cudaMemcpyAsync((unsigned char*)dst + (f - first) * bps, stage, (l - f) * bps, cudaMemcpyDeviceToHost, st));
         R4WB_CUDA(cudaStreamSynchronize(st));
     }
@@ -152,7 +173,12 @@ uint64_t Scenario::generate_block(uint64_t n_req, void* dst, r4wb_mem where, r4w
     R4WB_CUDA(cudaMemsetAsync(d_power_.p, 0, sizeof(double), st));
     const size_t bps = fmt == R4WB_FMT_CF64 ? 16 : 8;
     void* d_out = where == R4WB_MEM_DEVICE ? dst : (void*)d_stage_.reserve((size_t)n * bps);
-    launch_synth(d_seq_tab_.p, d_seq_hdr_.p, 1, 1, current_, n, d_out, fmt, n);
+    {
+        SynthArgs a = base_args(d_seq_tab_.p, d_seq_hdr_.p, n);
+        d_seq_tiles_.reserve(std::max<size_t>(1, (size_t)2 * a.tiles_per_block * sc.n_sats));
+        build_tiles(a, 1, 1, d_seq_tiles_.p);
+    }
+    launch_synth(d_seq_tab_.p, d_seq_hdr_.p, d_seq_tiles_.p, 1, 1, current_, n, d_out, fmt, n);
     if (where != R4WB_MEM_DEVICE) R4WB_CUDA(cudaMemcpyAsync(dst, d_out, (size_t)n * bps, cudaMemcpyDeviceToHost, st));
     R4WB_CUDA(cudaStreamSynchronize(st));   // `tab`/`hdr` are stack/heap temporaries
     seq_.advance(md_, tab, (uint32_t)n);

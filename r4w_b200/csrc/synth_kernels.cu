@@ -77,6 +77,40 @@ __global__ void __launch_bounds__(1024) k_phase_scan(const SatConst* __restrict_
     }
 }
 
+// Per (table block, chunk, satellite): everything k_synth needs about the tile that costs latency to derive (f64 phasor
+// of the rotation step, link to the previous block, the collapsed block-start fix-up), so the synthesis kernel's per-tile
+// prologue is one coalesced 96-byte read per satellite.
+__global__ void k_tile_params(SynthArgs a, uint32_t tb_begin, uint32_t tb_count, uint32_t tile_samples, TileRec* __restrict__ out)
+{
+    const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t total = (uint64_t)tb_count * a.tiles_per_block * a.n_sats;
+    if (idx >= total) return;
+    const uint32_t s = (uint32_t)(idx % a.n_sats);
+    const uint32_t tile = (uint32_t)(idx / a.n_sats);
+    const uint32_t tb = tb_begin + tile / a.tiles_per_block, chunk = tile % a.tiles_per_block;
+    const SynthK KK = make_synth_k(a.delta46, a.kmul, a.cj, a.dsum0, a.spc, a.lut_den);
+    const BlockSat* row = a.tab + (size_t)tb * a.n_sats;
+    const BlockHdr hd = a.hdr[tb];
+    TileRec r;
+    r.ts = tile_sat(row[s], a.tab, chunk * tile_samples, KK.d8);
+#pragma unroll 1
+    for (int i = 0; i < 8; ++i) {
+        float y = 0.0f;
+        if (chunk == 0 && (r.ts.flags & 9u) == 9u && (uint32_t)i < hd.n)
+            y = fir_block_start(row[s], a.tab, a.perbits + (size_t)s * kPerWords, a.taps, a.etab, i, KK);
+        r.yfix[i] = y;
+    }
+    out[((size_t)tb * a.tiles_per_block + chunk) * a.n_sats + s] = r;
+}
+
+void launch_tile_params(const SynthArgs& a, uint32_t tb_begin, uint32_t tb_count, uint32_t tile_samples, TileRec* out, cudaStream_t st)
+{
+    const uint64_t total = (uint64_t)tb_count * a.tiles_per_block * a.n_sats;
+    if (total == 0) return;
+    k_tile_params<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(a, tb_begin, tb_count, tile_samples, out);
+    R4WB_LAUNCH_CHECK();
+}
+
 // ----------------------------------------------------------------------------------------------
 // synthesis kernel: persistent CTAs, one tile (<= 256*2*K consecutive samples of one 1 ms block) at a time.
 // Thread t owns the sample pairs (2t, 2t+1) + 512 k of the tile, so every store is a 16-byte float4 and a
@@ -85,7 +119,7 @@ __global__ void __launch_bounds__(1024) k_phase_scan(const SatConst* __restrict_
 constexpr int kThreads = kSynthThreads;
 
 struct SynthSmem {
-    float* ytab; float* taps; float* etab; uint32_t* per; TileSat* tsat; uint2* t64; uint32_t* w32; float* yfix;
+    float* ytab; float* taps; float* etab; uint32_t* per; TileRec* trec; uint2* t64; uint32_t* w32; uint8_t* clslut;
 };
 
 __device__ __forceinline__ SynthSmem carve_smem(unsigned char* raw, uint32_t n_sats, uint32_t nw64)
@@ -97,13 +131,14 @@ __device__ __forceinline__ SynthSmem carve_smem(unsigned char* raw, uint32_t n_s
     size_t off = ((size_t)(32 * kYStride + 128) * 4 + 15) & ~(size_t)15;
     m.per = reinterpret_cast<uint32_t*>(raw + off);                           // [n_sats][kPerWords]
     off += (size_t)n_sats * kPerWords * 4;
-    m.tsat = reinterpret_cast<TileSat*>(raw + off);                           // [n_sats]
-    off += (size_t)n_sats * sizeof(TileSat);
+    m.trec = reinterpret_cast<TileRec*>(raw + off);                           // [n_sats]
+    off += (size_t)n_sats * sizeof(TileRec);
     m.t64 = reinterpret_cast<uint2*>(raw + off);                              // [n_sats][nw64]
     off += (size_t)n_sats * nw64 * 8;
     m.w32 = reinterpret_cast<uint32_t*>(raw + off);                           // [n_sats][nw64 + 1]
     off += (size_t)n_sats * (nw64 + 1) * 4;
-    m.yfix = reinterpret_cast<float*>(raw + off);                             // [n_sats][8]
+    off = (off + 15) & ~(size_t)15;
+    m.clslut = raw + off;                                                     // [lut_den padded to 16]
     return m;
 }
 
@@ -116,45 +151,61 @@ __global__ void __launch_bounds__(kThreads, K <= 5 ? 3 : 2) k_synth(SynthArgs a)
     __shared__ float s_pow[kThreads / 32];
 
     const uint32_t tid = threadIdx.x, lane = tid & 31u;
-    const SynthK KK = make_synth_k(a.delta46, a.kmul, a.cj, a.dsum0, a.spc);
+    const SynthK KK = make_synth_k(a.delta46, a.kmul, a.cj, a.dsum0, a.spc, a.lut_den);
     const PhiloxKeys PK = philox_keys(a.seed);
 
     // kernel-lifetime tables
     for (uint32_t k = tid; k < 32 * kYStride; k += kThreads) sm.ytab[k] = a.ytab[k];
     for (uint32_t k = tid; k < 64; k += kThreads) { sm.taps[k] = a.taps[k]; sm.etab[k] = a.etab[k]; }
     for (uint32_t k = tid; k < a.n_sats * kPerWords; k += kThreads) sm.per[k] = a.perbits[k];
+    for (uint32_t k = tid; k < ((a.lut_den + 15u) >> 4); k += kThreads)
+        reinterpret_cast<uint4*>(sm.clslut)[k] = reinterpret_cast<const uint4*>(a.clslut)[k];
 
     float pow_acc = 0.0f;
     const uint32_t n_tiles = a.tb_count * a.tiles_per_block;
+    const uint32_t rec_f4 = a.n_sats * (uint32_t)(sizeof(TileRec) / 16);        // float4s of one tile's records
+    const float4* recs = reinterpret_cast<const float4*>(a.tiles + (size_t)a.tb_begin * a.tiles_per_block * a.n_sats);
+    // the next tile's records travel in registers while the current tile is rendered
+    float4 pre[2];
+    {
+        const uint32_t tile = blockIdx.x;
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const uint32_t k = tid + (uint32_t)u * kThreads;
+            pre[u] = (tile < n_tiles && k < rec_f4) ? __ldg(recs + (size_t)tile * rec_f4 + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
 
     for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const uint32_t tb = a.tb_begin + tile / a.tiles_per_block;
         const uint32_t chunk = tile % a.tiles_per_block;
         const BlockHdr hd = a.hdr[tb];
         const uint32_t i_begin = chunk * TILE;
-        if (i_begin >= hd.n) continue;
         const uint32_t i_end = min(hd.n, i_begin + TILE);
-        // skip tiles entirely outside the requested output range
-        if (hd.first + i_end <= a.out_first || hd.first + i_begin >= a.out_first + a.out_n) continue;
+        // tiles past the block's end or entirely outside the requested output range are skipped (uniform per CTA)
+        const bool skip = i_begin >= hd.n || hd.first + i_end <= a.out_first || hd.first + i_begin >= a.out_first + a.out_n;
         const BlockSat* row = a.tab + (size_t)tb * a.n_sats;
 
         __syncthreads();   // previous tile's readers are done (and the kernel-lifetime tables are in place)
-        if (tid < a.n_sats) sm.tsat[tid] = tile_sat(row[tid], a.tab, i_begin, KK.d8);
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const uint32_t k = tid + (uint32_t)u * kThreads;
+            if (k < rec_f4) reinterpret_cast<float4*>(sm.trec)[k] = pre[u];
+        }
+        {
+            const uint32_t nt = tile + gridDim.x;
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const uint32_t k = tid + (uint32_t)u * kThreads;
+                if (nt < n_tiles && k < rec_f4) pre[u] = __ldg(recs + (size_t)nt * rec_f4 + k);
+            }
+        }
+        if (skip) continue;
         __syncthreads();
         // half-chip sign words: bit n of word w <-> half-chip hb + 32 w + n
         for (uint32_t k = tid; k < a.n_sats * (a.nw64 + 1); k += kThreads) {
             const uint32_t s = k / (a.nw64 + 1), w = k - s * (a.nw64 + 1);
-            sm.w32[k] = sign_word(sm.per + s * kPerWords, sm.tsat[s].hb, w);
-        }
-        // first 8 samples of a block whose delay differs from its predecessor's
-        if (chunk == 0) {
-            for (uint32_t k = tid; k < a.n_sats * 8; k += kThreads) {
-                const uint32_t s = k >> 3, i = k & 7u;
-                float y = 0.0f;
-                if ((sm.tsat[s].flags & 9u) == 9u && i < hd.n)
-                    y = fir_block_start(row[s], a.tab, sm.per + s * kPerWords, sm.taps, sm.etab, (int)i, KK);
-                sm.yfix[k] = y;
-            }
+            sm.w32[k] = sign_word(sm.per + s * kPerWords, sm.trec[s].ts.hb, w);
         }
         __syncthreads();
         for (uint32_t k = tid; k < a.n_sats * a.nw64; k += kThreads) {
@@ -168,10 +219,10 @@ __global__ void __launch_bounds__(kThreads, K <= 5 ? 3 : 2) k_synth(SynthArgs a)
         for (int k = 0; k < K; ++k) ar[k] = ai[k] = make_float2(0.0f, 0.0f);
 
         for (uint32_t s = 0; s < a.n_sats; ++s) {
-            const TileSat ts = sm.tsat[s];
+            const TileSat ts = sm.trec[s].ts;
             if (!(ts.flags & 1u)) continue;
             const SlowCtx slow{row + s, a.tab, sm.per + s * kPerWords, sm.taps};
-            sat_accumulate<K>(ts, KK, sm.t64 + s * a.nw64, sm.ytab, sm.yfix + s * 8, slow, tid, i_begin, i_end, ar, ai, nullptr);
+            sat_accumulate<K>(ts, KK, sm.t64 + s * a.nw64, sm.ytab, sm.clslut, sm.trec[s].yfix, slow, tid, i_begin, i_end, ar, ai, nullptr);
         }
 
         // noise, power, store.  A tile that lies inside the requested range and starts on a 16-byte boundary of the
@@ -274,7 +325,7 @@ static void launch_synth_t(const SynthArgs& a, int grid, size_t smem, cudaStream
 
 void launch_synth_kernel(const SynthArgs& a, int K, bool cf64, int grid, cudaStream_t st)
 {
-    const size_t smem = synth_smem_bytes(a.n_sats, a.nw64);
+    const size_t smem = synth_smem_bytes(a.n_sats, a.nw64, a.lut_den);
     if (smem > 200 * 1024) fail(R4WB_ERR_NOT_SUPPORTED, "scenario needs %zu bytes of shared memory per CTA", smem);
     if (K == 5) { cf64 ? launch_synth_t<5, true>(a, grid, smem, st) : launch_synth_t<5, false>(a, grid, smem, st); }
     else if (K == 10) { cf64 ? launch_synth_t<10, true>(a, grid, smem, st) : launch_synth_t<10, false>(a, grid, smem, st); }

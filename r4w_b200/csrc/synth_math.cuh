@@ -316,37 +316,28 @@ R4WB_HD void accurate_sincos_cycles(uint64_t ph, float* s, float* c)
 }
 
 // ----------------------------------------------------------------------------------------------
-// per-tile, per-satellite state
-struct TileSat {
-    uint64_t u0;        // half-chip position (18.46) at the newest oversample of the tile's first sample
-    uint64_t phi;
-    long long f, df;
-    uint32_t hb;        // half-chip index of bit 0 of the sign table
-    float amp;
-    uint32_t flags;     // bit0 visible, bit1 ambiguity checks needed, bit2 per-sample sincos (large Doppler rate),
-                        // bit3 first 8 samples of the block come from yfix, bit4 Doppler varies inside the block
-    uint32_t eps_t;
-    float wr, wi;       // e^{j phase advance over 2*kSynthThreads samples}, at the tile's first sample
-    float th1, th2;     // radians: growth of that advance per sample index, and per step of 2*kSynthThreads samples
-};
-
 // constants of one launch, derived from SynthArgs once per thread
 struct SynthK {
     uint64_t delta46, d8;       // half-chips per oversample / per output sample, 2^-46 units
     uint64_t step32;            // half-chips per 2*kSynthThreads samples, 32.32 fixed
     uint32_t d8_32;             // half-chips per output sample, 0.32 fixed (< 1)
     uint32_t kmul, c1, c2, c3, dsum0;
+    uint32_t lut_den;
     double spc;
 };
 
-R4WB_HD SynthK make_synth_k(uint64_t delta46, uint32_t kmul, const uint32_t* cj, uint32_t dsum0, double spc)
+// position of fraction bin q in the class table: bits 2-3 are xor-ed with bits 8-9 so the bins a warp touches
+// (a fixed stride of 16 * 227 mod 20000 between lanes at 5 MHz) spread over the banks
+R4WB_HD uint32_t cls_lut_index(uint32_t q) { return q ^ ((q >> 6) & 0xcu); }
+
+R4WB_HD SynthK make_synth_k(uint64_t delta46, uint32_t kmul, const uint32_t* cj, uint32_t dsum0, double spc, uint32_t lut_den)
 {
     SynthK k;
     k.delta46 = delta46;
     k.d8 = delta46 * (uint64_t)kOversample;
     k.step32 = (k.d8 * (uint64_t)(2 * kSynthThreads)) >> (kFracBits - 32);
     k.d8_32 = (uint32_t)(k.d8 >> (kFracBits - 32));
-    k.kmul = kmul; k.c1 = cj[1]; k.c2 = cj[2]; k.c3 = cj[3]; k.dsum0 = dsum0;
+    k.kmul = kmul; k.c1 = cj[1]; k.c2 = cj[2]; k.c3 = cj[3]; k.dsum0 = dsum0; k.lut_den = lut_den;
     k.spc = spc;
     return k;
 }
@@ -532,9 +523,10 @@ struct SlowCtx {
 //   yfix  first 8 outputs of the block when its window reaches into a block with another delay (flags bit3)
 //   GENERAL = false: no ambiguity checks, phasor recurrence, DYN compile-time (the common case, straight-line code)
 //   GENERAL = true:  checks / per-sample sincos / varying Doppler selected at run time from ts.flags
-template <int NK, bool GENERAL, bool DYN>
+//   LUT: boundary-age classes from the fraction table (only with GENERAL = false)
+template <int NK, bool GENERAL, bool DYN, bool LUT>
 R4WB_HD void sat_accumulate_t(const TileSat& ts, const SynthK& K, const uint2* __restrict__ t64, const float* __restrict__ ytab,
-                            const float* __restrict__ yfix, const SlowCtx& slow, uint32_t tid, uint32_t i_begin, uint32_t i_end,
+                            const uint8_t* __restrict__ clslut, const float* __restrict__ yfix, const SlowCtx& slow, uint32_t tid, uint32_t i_begin, uint32_t i_end,
                             float2 (&ar)[NK], float2 (&ai)[NK], uint64_t* n_ambiguous)
 {
     const uint32_t ia0 = i_begin + 2u * tid;
@@ -573,10 +565,16 @@ R4WB_HD void sat_accumulate_t(const TileSat& ts, const SynthK& K, const uint2* _
         const uint32_t hi = (uint32_t)(pos >> 32), lo = (uint32_t)pos;
         const uint32_t lob = lo + K.d8_32, hib = hi + (lob < lo ? 1u : 0u);
         // boundary-age classes
-        const uint32_t ta0 = umulhi32(lo, K.kmul), ta1 = ta0 + K.c1, ta2 = ta0 + K.c2, ta3 = ta0 + K.c3;
-        const uint32_t tb0 = umulhi32(lob, K.kmul), tb1 = tb0 + K.c1, tb2 = tb0 + K.c2, tb3 = tb0 + K.c3;
-        const uint32_t cls_a = (ta0 >> kTBits) + (ta1 >> kTBits) + (ta2 >> kTBits) + (ta3 >> kTBits) - K.dsum0;
-        const uint32_t cls_b = (tb0 >> kTBits) + (tb1 >> kTBits) + (tb2 >> kTBits) + (tb3 >> kTBits) - K.dsum0;
+        uint32_t ta0 = 0, ta1 = 0, ta2 = 0, ta3 = 0, tb0 = 0, tb1 = 0, tb2 = 0, tb3 = 0, cls_a, cls_b;
+        if (LUT && !GENERAL) {
+            cls_a = clslut[cls_lut_index(umulhi32(lo, K.lut_den))];
+            cls_b = clslut[cls_lut_index(umulhi32(lob, K.lut_den))];
+        } else {
+            ta0 = umulhi32(lo, K.kmul); ta1 = ta0 + K.c1; ta2 = ta0 + K.c2; ta3 = ta0 + K.c3;
+            tb0 = umulhi32(lob, K.kmul); tb1 = tb0 + K.c1; tb2 = tb0 + K.c2; tb3 = tb0 + K.c3;
+            cls_a = (ta0 >> kTBits) + (ta1 >> kTBits) + (ta2 >> kTBits) + (ta3 >> kTBits) - K.dsum0;
+            cls_b = (tb0 >> kTBits) + (tb1 >> kTBits) + (tb2 >> kTBits) + (tb3 >> kTBits) - K.dsum0;
+        }
         // 5-sign patterns out of one 64-bit window
         const uint2 w = *reinterpret_cast<const uint2*>(reinterpret_cast<const unsigned char*>(t64) + ((hi >> 2) & 0x3ffffff8u));
         const uint32_t pa = funnel_r(w.x, w.y, hi) & 31u;
@@ -619,12 +617,17 @@ R4WB_HD void sat_accumulate_t(const TileSat& ts, const SynthK& K, const uint2* _
 
 template <int NK>
 R4WB_HD void sat_accumulate(const TileSat& ts, const SynthK& K, const uint2* __restrict__ t64, const float* __restrict__ ytab,
-                            const float* __restrict__ yfix, const SlowCtx& slow, uint32_t tid, uint32_t i_begin, uint32_t i_end,
-                            float2 (&ar)[NK], float2 (&ai)[NK], uint64_t* n_ambiguous)
+                            const uint8_t* __restrict__ clslut, const float* __restrict__ yfix, const SlowCtx& slow, uint32_t tid,
+                            uint32_t i_begin, uint32_t i_end, float2 (&ar)[NK], float2 (&ai)[NK], uint64_t* n_ambiguous)
 {
-    if (ts.flags & 6u) sat_accumulate_t<NK, true, false>(ts, K, t64, ytab, yfix, slow, tid, i_begin, i_end, ar, ai, n_ambiguous);
-    else if (ts.flags & 16u) sat_accumulate_t<NK, false, true>(ts, K, t64, ytab, yfix, slow, tid, i_begin, i_end, ar, ai, n_ambiguous);
-    else sat_accumulate_t<NK, false, false>(ts, K, t64, ytab, yfix, slow, tid, i_begin, i_end, ar, ai, n_ambiguous);
+    if (ts.flags & 6u) sat_accumulate_t<NK, true, false, false>(ts, K, t64, ytab, clslut, yfix, slow, tid, i_begin, i_end, ar, ai, n_ambiguous);
+    else if (K.lut_den) {
+        if (ts.flags & 16u) sat_accumulate_t<NK, false, true, true>(ts, K, t64, ytab, clslut, yfix, slow, tid, i_begin, i_end, ar, ai, n_ambiguous);
+        else sat_accumulate_t<NK, false, false, true>(ts, K, t64, ytab, clslut, yfix, slow, tid, i_begin, i_end, ar, ai, n_ambiguous);
+    } else {
+        if (ts.flags & 16u) sat_accumulate_t<NK, false, true, false>(ts, K, t64, ytab, clslut, yfix, slow, tid, i_begin, i_end, ar, ai, n_ambiguous);
+        else sat_accumulate_t<NK, false, false, false>(ts, K, t64, ytab, clslut, yfix, slow, tid, i_begin, i_end, ar, ai, n_ambiguous);
+    }
 }
 
 // ----------------------------------------------------------------------------------------------

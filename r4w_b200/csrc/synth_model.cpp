@@ -241,6 +241,28 @@ ScenarioModel::ScenarioModel(const r4wb_scenario_cfg& c_in) : cfg(c_in)
         }
     }
 
+    // Boundary-age class as a table over the half-chip fraction.  Every class boundary sits at a multiple of 1/D
+    // (D = lattice_den: fractions n / S mod 1 with S = ratA / (2 ratB) oversamples per half-chip), so bin q = floor(frac D)
+    // names the class exactly for any sample that is not within the ambiguity band of a lattice point (those blocks
+    // are flagged and take the arithmetic path).  Bin centre evaluated in extended precision.
+    sc.lut_den = 0;
+    if (sc.lattice_den != 0 && sc.lattice_den <= 40960 && !std::getenv("R4WB_SYNTH_NO_LUT")) {
+        const uint32_t D = (uint32_t)sc.lattice_den;
+        sc.lut_den = D;
+        clslut.assign(((size_t)D + 15) & ~(size_t)15, 0);
+        const long double Sl = (long double)sc.ratA / (2.0L * (long double)sc.ratB);
+        for (uint32_t q = 0; q < D; ++q) {
+            const long double t0 = ((long double)q + 0.5L) / (long double)D * Sl;
+            uint32_t dsum = 0;
+            for (int j = 0; j < 4; ++j) dsum += (uint32_t)floorl(t0 + (long double)j * Sl);
+            dsum -= sc.dsum0;
+            if (dsum >= (uint32_t)kYStride) fail(R4WB_ERR_NOT_SUPPORTED, "FIR age class %u out of range", dsum);
+            clslut[cls_lut_index(q)] = (uint8_t)dsum;
+        }
+    } else {
+        clslut.assign(16, 0);
+    }
+
     tile_k = 10;
     if (const char* e = std::getenv("R4WB_SYNTH_TILE_K")) { if (std::atoi(e) == 5) tile_k = 5; }   // tuning hook
     {
@@ -318,15 +340,16 @@ void SeqState::advance(const ScenarioModel& md, const std::vector<BlockSat>& tab
     }
 }
 
-size_t synth_smem_bytes(uint32_t n_sats, uint32_t nw64)
+size_t synth_smem_bytes(uint32_t n_sats, uint32_t nw64, uint32_t lut_den)
 {
     size_t b = ((size_t)(32 * kYStride + 128) * 4 + 15) & ~(size_t)15;   // ytab, taps, etab
     b += (size_t)n_sats * kPerWords * 4;
-    b += (size_t)n_sats * sizeof(TileSat);
+    b += (size_t)n_sats * sizeof(TileRec);
     b += (size_t)n_sats * nw64 * 8;
     b += (size_t)n_sats * (nw64 + 1) * 4;
-    b += (size_t)n_sats * 8 * 4;
-    return (b + 15) & ~(size_t)15;
+    b = (b + 15) & ~(size_t)15;
+    b += ((size_t)lut_den + 15) & ~(size_t)15;
+    return b;
 }
 
 int synth_tile_samples(int K) { return kSynthThreads * 2 * K; }

@@ -74,7 +74,7 @@ struct Emu {
         constexpr int kThreads = kSynthThreads;
         const uint32_t TILE = (uint32_t)synth_tile_samples(K);
         const uint32_t tiles_per_block = (uint32_t)((max_block_n + TILE - 1) / TILE);
-        const SynthK KK = make_synth_k(sc.delta46, sc.kmul, sc.cj, sc.dsum0, sc.spc);
+        const SynthK KK = make_synth_k(sc.delta46, sc.kmul, sc.cj, sc.dsum0, sc.spc, sc.lut_den);
         std::vector<TileSat> tsat(std::max(1u, ns));
         std::vector<uint32_t> w32((size_t)std::max(1u, ns) * (nw64 + 1));
         std::vector<uint2> t64((size_t)std::max(1u, ns) * nw64);
@@ -89,19 +89,20 @@ struct Emu {
             const uint32_t i_end = std::min(hd.n, i_begin + TILE);
             if (hd.first + i_end <= out_first || hd.first + i_begin >= out_first + out_n) continue;
             const BlockSat* row = tb_tab + (size_t)tb * ns;
-            for (uint32_t s = 0; s < ns; ++s) tsat[s] = tile_sat(row[s], tb_tab, i_begin, KK.d8);
+            // k_tile_params
+            for (uint32_t s = 0; s < ns; ++s) {
+                tsat[s] = tile_sat(row[s], tb_tab, i_begin, KK.d8);
+                for (uint32_t i = 0; i < 8; ++i) {
+                    float y = 0.0f;
+                    if (chunk == 0 && (tsat[s].flags & 9u) == 9u && i < hd.n)
+                        y = fir_block_start(row[s], tb_tab, md.perbits.data() + s * kPerWords, md.taps_f, md.etab_f, (int)i, KK);
+                    yfix[s * 8 + i] = y;
+                }
+            }
             for (uint32_t k = 0; k < ns * (nw64 + 1); ++k) {
                 const uint32_t s = k / (nw64 + 1), w = k - s * (nw64 + 1);
                 w32[k] = sign_word(md.perbits.data() + s * kPerWords, tsat[s].hb, w);
             }
-            if (chunk == 0)
-                for (uint32_t k = 0; k < ns * 8; ++k) {
-                    const uint32_t s = k >> 3, i = k & 7u;
-                    float y = 0.0f;
-                    if ((tsat[s].flags & 9u) == 9u && i < hd.n)
-                        y = fir_block_start(row[s], tb_tab, md.perbits.data() + s * kPerWords, md.taps_f, md.etab_f, (int)i, KK);
-                    yfix[k] = y;
-                }
             for (uint32_t k = 0; k < ns * nw64; ++k) {
                 const uint32_t s = k / nw64, w = k - s * nw64;
                 t64[k] = make_uint2(w32[s * (nw64 + 1) + w], w32[s * (nw64 + 1) + w + 1]);
@@ -114,7 +115,7 @@ struct Emu {
                     const TileSat ts = tsat[s];
                     if (!(ts.flags & 1u)) continue;
                     const SlowCtx slow{row + s, tb_tab, md.perbits.data() + s * kPerWords, md.taps_f};
-                    sat_accumulate<K>(ts, KK, t64.data() + s * nw64, md.ytab.data(), yfix.data() + s * 8, slow, tid, i_begin, i_end, ar, ai,
+                    sat_accumulate<K>(ts, KK, t64.data() + s * nw64, md.ytab.data(), md.clslut.data(), yfix.data() + s * 8, slow, tid, i_begin, i_end, ar, ai,
                                       n_ambiguous);
                 }
                 for (int k = 0; k < K; ++k) {
