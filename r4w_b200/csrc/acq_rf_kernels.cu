@@ -99,7 +99,7 @@ k_rf_fwd(AcqGeom g, const void* __restrict__ input, uint32_t in64, uint64_t stri
             }
             a[j] = rf::cmul(P, rf::cadd(x0, rf::cmul(qs, x1)));
         }
-        rf::forward(a, xb, K, t);
+        rf::forward<true>(a, xb, K, t);
         float4* o = o4 + (size_t)r * (M / 2);
         const float inv_n = 1.0f / (float)N;
 #pragma unroll
@@ -175,7 +175,8 @@ k_rf_inv_peak(AcqGeom g, const cf* __restrict__ X, const cf* __restrict__ C, con
         a[2 * s] = rf::cmul(cf{x.x, x.y}, cf{c.x, c.y});
         a[2 * s + 1] = rf::cmul(cf{x.z, x.w}, cf{c.z, c.w});
     }
-    rf::inverse<false>(a, xb, K, t, cf{1.0f, 0.0f});
+    rf::inverse<false, true>(a, xb, K, t, cf{1.0f, 0.0f});   // complex exchange: the E park is still free
+    __syncthreads();                                                 // the complex exchange reached into the park area
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
         e_re[(uint32_t)j * 512u + t] = a[rf::bitrev5(j)].re;
@@ -188,7 +189,7 @@ k_rf_inv_peak(AcqGeom g, const cf* __restrict__ X, const cf* __restrict__ C, con
         a[2 * s] = rf::cmul(cf{x.x, x.y}, cf{c.x, c.y});
         a[2 * s + 1] = rf::cmul(cf{x.z, x.w}, cf{c.z, c.w});
     }
-    rf::inverse<true>(a, xb, K, t, wNt);
+    rf::inverse<true, false>(a, xb, K, t, wNt);
 
     PeakAcc<float> acc;
     peak_init(acc);
@@ -222,7 +223,7 @@ k_rf_inv_peak(AcqGeom g, const cf* __restrict__ X, const cf* __restrict__ C, con
 // ---------------------------------------------------------------------------------------------- launchers
 bool rf_supported(const AcqGeom& g) { return g.logN == rf::kLogM + 1 && g.L <= (uint32_t)rf::kM + 4096u; }
 
-static size_t rf_fwd_smem() { return (size_t)rf::kXbufFloats * 4; }
+static size_t rf_fwd_smem() { return (size_t)rf::kXbufFloats * 8; }   // complex exchange buffer
 static size_t rf_inv_smem() { return (size_t)(rf::kXbufFloats + 2 * rf::kM) * 4; }
 
 void launch_rf_fwd_input(const AcqGeom& g, uint32_t rows, const void* input, uint32_t in64, uint64_t stride, uint32_t take, const cf* W,

@@ -9,7 +9,7 @@
 //   forward  (DIF): natural-order input  z[t + 512 j] in a[j]  ->  spectrum left in registers, "slot" order
 //   inverse  (DIT): slot-order input in registers  ->  natural-order output z[t + 512 j] in a[bitrev5(j)]
 // The slot order is whatever the forward transform ends with: thread t, register rho = 16 gi + i holds
-// X[k1 + 32 k2 + 1024 k3] with g = t + 512 gi, k1 = g >> 5, k2 = g & 31, k3 = bitrev4(i).  Spectra are stored in HBM/L2
+// X[k1 + 32 k2 + 1024 k3] with k1 = 2 (t >> 5) + gi, k2 = t & 31, k3 = bitrev4(i).  Spectra are stored in HBM/L2
 // in that order (element (rho, t) at ((rho >> 1) * 512 + t) * 2 + (rho & 1): one float4 per thread and register
 // pair), the code spectra too, so the element-wise product needs no reordering and the inverse transform is the
 // exact transpose of the forward one.
@@ -27,7 +27,7 @@ constexpr int kNT = 512;                       // threads per CTA
 constexpr int kLogM = 14;
 constexpr int kM = 1 << kLogM;                 // points per transform
 constexpr int kRow = 528;                      // floats per k1 row of the exchange buffer: 512 + 16 puts the next row on the other 16 banks
-constexpr int kXbufFloats = 32 * kRow;         // 16 896 floats = 67 584 bytes
+constexpr int kXbufFloats = 32 * kRow;         // 16 896 floats = 67 584 bytes (twice that for the complex layout)
 
 #ifdef __CUDACC__
 
@@ -181,39 +181,55 @@ __device__ __forceinline__ Consts load_consts(const cf* __restrict__ W /* exp(-2
     return c;
 }
 
-// One component (COMP 0 = re, 1 = im) through the buffer.  The caller brackets with __syncthreads().
-#define R4WB_RF_COMP(v, COMP) ((COMP) == 0 ? (v).re : (v).im)
-
-// Forward 16384-point DFT.  In: a[j] = z[t + 512 j].  Out: a[16 gi + i] = X[k1 + 32 k2 + 1024 bitrev4(i)], g = t + 512 gi.
+// Exchange 1 moves element (k1, t) between the thread that owns t and the thread that owns (k1, t & 15).  With a
+// complex buffer (CPLX: 32 x kRow float2 = 135 KB) it takes one round, with the 66 KB float buffer two (re, then im).
+// Exchange 2 only moves data inside a warp: warp w owns rows k1 = 2w and 2w + 1 of the buffer in both layouts, so it
+// needs __syncwarp() only.
+//
+// Forward 16384-point DFT.  In: a[j] = z[t + 512 j].  Out (slot order): a[16 gi + i] = X[k1 + 32 k2 + 1024 bitrev4(i)]
+// with k1 = 2 (t >> 5) + gi, k2 = t & 31.
+template <bool CPLX>
 __device__ __forceinline__ void forward(cf* a, float* xb, const Consts& c, uint32_t t)
 {
     dif<32, -1>(a);                                      // over j -> k1 at a[bitrev5(k1)]
     apply_powers<32, true, false>(a, c.wM, cf{1.0f, 0.0f});     // w_M^{t k1}
     cf b[32];
     const uint32_t k1p = t >> 4, tl = t & 15u;
-#pragma unroll
-    for (int comp = 0; comp < 2; ++comp) {
+    if (CPLX) {
+        cf* xc = reinterpret_cast<cf*>(xb);
         __syncthreads();
 #pragma unroll
-        for (int k1 = 0; k1 < 32; ++k1) xb[x1_addr(k1, t)] = comp == 0 ? a[bitrev5(k1)].re : a[bitrev5(k1)].im;
+        for (int k1 = 0; k1 < 32; ++k1) st_cx(xc + x1_addr(k1, t), a[bitrev5(k1)]);
         __syncthreads();
 #pragma unroll
-        for (int j2 = 0; j2 < 32; ++j2) {
-            const float v = xb[x1_addr(k1p, tl + 16u * j2)];
-            if (comp == 0) b[j2].re = v; else b[j2].im = v;
+        for (int j2 = 0; j2 < 32; ++j2) b[j2] = ld_cx(xc + x1_addr(k1p, tl + 16u * j2));
+    } else {
+#pragma unroll
+        for (int comp = 0; comp < 2; ++comp) {
+            __syncthreads();
+#pragma unroll
+            for (int k1 = 0; k1 < 32; ++k1) xb[x1_addr(k1, t)] = comp == 0 ? a[bitrev5(k1)].re : a[bitrev5(k1)].im;
+            __syncthreads();
+#pragma unroll
+            for (int j2 = 0; j2 < 32; ++j2) {
+                const float v = xb[x1_addr(k1p, tl + 16u * j2)];
+                if (comp == 0) b[j2].re = v; else b[j2].im = v;
+            }
         }
     }
     dif<32, -1>(b);                                      // over j2 -> k2 at b[bitrev5(k2)]
     apply_powers<32, true, false>(b, c.w512, cf{1.0f, 0.0f});   // w_512^{tl k2}
+    const uint32_t gbase = (t >> 5) * 64u + (t & 31u);   // group of gi = 0; gi = 1 is 32 further (k1 + 1)
 #pragma unroll
     for (int comp = 0; comp < 2; ++comp) {
-        __syncthreads();
+        if (CPLX && comp == 0) __syncthreads();          // complex rows just read overlap other warps' float rows
+        else __syncwarp();
 #pragma unroll
         for (int k2 = 0; k2 < 32; ++k2) xb[x2_addr(k1p * 32u + k2, tl)] = comp == 0 ? b[bitrev5(k2)].re : b[bitrev5(k2)].im;
-        __syncthreads();
+        __syncwarp();
 #pragma unroll
         for (int gi = 0; gi < 2; ++gi) {
-            const uint32_t g = t + 512u * gi;
+            const uint32_t g = gbase + 32u * gi;
 #pragma unroll
             for (int ch = 0; ch < 4; ++ch) {
                 const float4 v = *reinterpret_cast<const float4*>(xb + x2_addr(g, 4u * ch));
@@ -228,22 +244,24 @@ __device__ __forceinline__ void forward(cf* a, float* xb, const Consts& c, uint3
 
 // Inverse (unnormalised) 16384-point DFT, the transpose of forward().  In: slot order.  Out: a[bitrev5(j)] = z[t + 512 j].
 // `f` is folded into the last twiddle (a[k1] *= f * conj(w_M)^{t k1}): the caller's per-thread output factor.
-template <bool HAS_F>
+template <bool HAS_F, bool CPLX>
 __device__ __forceinline__ void inverse(cf* a, float* xb, const Consts& c, uint32_t t, cf f)
 {
     dit<16, +1>(a);                                      // over k3 -> tl, natural
     dit<16, +1>(a + 16);
-    const cf u = cconj(c.w512k);                         // conj(w_512)^{k2 tl}, k2 = g & 31 = t & 31 for both groups
+    const cf u = cconj(c.w512k);                         // conj(w_512)^{k2 tl}, k2 = t & 31 for both groups
     apply_powers<16, false, false>(a, u, cf{1.0f, 0.0f});
     apply_powers<16, false, false>(a + 16, u, cf{1.0f, 0.0f});
     cf b[32];
     const uint32_t k1p = t >> 4, tl = t & 15u;
+    const uint32_t gbase = (t >> 5) * 64u + (t & 31u);
+    __syncthreads();                                     // the buffer's previous readers (any row) are done
 #pragma unroll
     for (int comp = 0; comp < 2; ++comp) {
-        __syncthreads();
+        __syncwarp();
 #pragma unroll
         for (int gi = 0; gi < 2; ++gi) {
-            const uint32_t g = t + 512u * gi;
+            const uint32_t g = gbase + 32u * gi;
 #pragma unroll
             for (int ch = 0; ch < 4; ++ch) {
                 float4 v;
@@ -252,7 +270,7 @@ __device__ __forceinline__ void inverse(cf* a, float* xb, const Consts& c, uint3
                 *reinterpret_cast<float4*>(xb + x2_addr(g, 4u * ch)) = v;
             }
         }
-        __syncthreads();
+        __syncwarp();
 #pragma unroll
         for (int k2 = 0; k2 < 32; ++k2) {
             const float v = xb[x2_addr(k1p * 32u + k2, tl)];
@@ -260,16 +278,26 @@ __device__ __forceinline__ void inverse(cf* a, float* xb, const Consts& c, uint3
         }
     }
     dif<32, +1>(b);                                      // over k2 -> j2 at b[bitrev5(j2)]
+    if (CPLX) {
+        cf* xc = reinterpret_cast<cf*>(xb);
+        __syncthreads();                                 // complex rows overlap other warps' float rows
 #pragma unroll
-    for (int comp = 0; comp < 2; ++comp) {
+        for (int j2 = 0; j2 < 32; ++j2) st_cx(xc + x1_addr(k1p, tl + 16u * j2), b[bitrev5(j2)]);
         __syncthreads();
 #pragma unroll
-        for (int j2 = 0; j2 < 32; ++j2) xb[x1_addr(k1p, tl + 16u * j2)] = comp == 0 ? b[bitrev5(j2)].re : b[bitrev5(j2)].im;
-        __syncthreads();
+        for (int k1 = 0; k1 < 32; ++k1) a[k1] = ld_cx(xc + x1_addr(k1, t));
+    } else {
 #pragma unroll
-        for (int k1 = 0; k1 < 32; ++k1) {
-            const float v = xb[x1_addr(k1, t)];
-            if (comp == 0) a[k1].re = v; else a[k1].im = v;
+        for (int comp = 0; comp < 2; ++comp) {
+            if (comp == 0) __syncwarp(); else __syncthreads();   // rows 2w, 2w+1 were last read by this warp / by everyone
+#pragma unroll
+            for (int j2 = 0; j2 < 32; ++j2) xb[x1_addr(k1p, tl + 16u * j2)] = comp == 0 ? b[bitrev5(j2)].re : b[bitrev5(j2)].im;
+            __syncthreads();
+#pragma unroll
+            for (int k1 = 0; k1 < 32; ++k1) {
+                const float v = xb[x1_addr(k1, t)];
+                if (comp == 0) a[k1].re = v; else a[k1].im = v;
+            }
         }
     }
     apply_powers<32, false, HAS_F>(a, cconj(c.wM), f);   // f * conj(w_M)^{t k1}
