@@ -23,6 +23,7 @@ void launch_inv_peak(const AcqGeom& g, uint32_t rows, const cx<T>* X, const cx<T
 void launch_pair_reduce(const AcqGeom& g, uint32_t n_snap, const RowPeak* peaks, PairPeak* out, cudaStream_t st);
 // register-resident f32 fast path for fft_size 32768 (acq_rf_kernels.cu)
 bool rf_supported(const AcqGeom& g);
+bool rf_use_tmem();
 void launch_rf_fwd_input(const AcqGeom& g, uint32_t rows, const void* input, uint32_t in64, uint64_t stride, uint32_t take,
                          const cx<float>* W, cx<float>* out, cudaStream_t st);
 void launch_rf_fwd_codes(const AcqGeom& g, uint32_t n_codes, const int8_t* codes, uint64_t code_len, uint32_t take, const cx<float>* W,
@@ -43,6 +44,9 @@ static bool rf_enabled()
 static constexpr double kNearTie = 1e-4;
 static constexpr double kNearThreshold = 1e-3;
 static constexpr size_t kSpectraChunkBytes = 96u << 20;   // forward spectra kept per chunk: stays inside the 126 MB L2
+// With the forward spectrum parked in Tensor Memory every row is read from memory once, so L2 residency no longer matters
+// and a chunk is sized to fill many waves of one-CTA-per-row launches instead
+static constexpr size_t kSpectraChunkBytesTmem = (size_t)2 << 30;
 
 Pcps::Pcps(uint64_t code_length, double sample_rate) : code_length_(code_length), fs_(sample_rate)
 {
@@ -151,7 +155,8 @@ void Pcps::run(AcqWork<T>& w, const void* d_input, r4wb_fmt fmt, uint64_t s0, ui
     prof_end();
 
     const size_t row_bytes = (size_t)g.N * sizeof(cx<T>);
-    uint64_t chunk = std::max<uint64_t>(1, kSpectraChunkBytes / (row_bytes * std::max(1u, g.D)));
+    const size_t chunk_bytes = fast && rf_use_tmem() ? kSpectraChunkBytesTmem : kSpectraChunkBytes;
+    uint64_t chunk = std::max<uint64_t>(1, chunk_bytes / (row_bytes * std::max(1u, g.D)));
     chunk = std::min<uint64_t>(chunk, std::max<uint64_t>(1, 0x3fffffffull / ((uint64_t)std::max(1u, g.D) * nc * F)));
     chunk = std::min(chunk, ns);
     w.x.reserve((size_t)chunk * g.D * g.N);

@@ -14,6 +14,8 @@
 // Not tensor-core work (no dense contraction); the bound is FP32 issue with the spectra L2-resident.
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+
 #include "acq.cuh"
 #include "rfft.cuh"
 
@@ -220,6 +222,155 @@ k_rf_inv_peak(AcqGeom g, const cf* __restrict__ X, const cf* __restrict__ C, con
     }
 }
 
+// ---- Tensor Memory as a per-thread park (sm_100a).  TMEM is 128 lanes x 512 columns x 32 bit per SM; a warp reaches
+// the 32 lanes of its quarter (warp % 4) and tcgen05.ld/st.32x32b hands every thread its own lane, so 512 threads get 128
+// private 32-bit words each (columns [(warp / 4) * 128, +128)): exactly one forward-spectrum row in slot order.
+__device__ __forceinline__ void tmem_alloc_512(uint32_t* smem_dst)   // one full warp
+{
+    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(dst) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_512(uint32_t base)      // one full warp
+{
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(base) : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float* v)
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+                 ::"r"(taddr), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]), "f"(v[8]), "f"(v[9]),
+                   "f"(v[10]), "f"(v[11]), "f"(v[12]), "f"(v[13]), "f"(v[14]), "f"(v[15])
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v)
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]), "=f"(v[8]), "=f"(v[9]),
+                   "=f"(v[10]), "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15])
+                 : "r"(taddr)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// One CTA per (snapshot, Doppler) row, all P codes: the row's forward spectrum is read from L2 once and parked in Tensor
+// Memory (all 256 KB), so every further code costs one code-spectrum read (256 KB) instead of two operand reads.
+// peaks[row * P + code] as k_rf_inv_peak.
+__global__ void __launch_bounds__(rf::kNT, 1)
+k_rf_inv_peak_tm(AcqGeom g, const cf* __restrict__ X, const cf* __restrict__ C, const cf* __restrict__ W, RowPeak* __restrict__ peaks)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* xb = reinterpret_cast<float*>(smem_raw);
+    float* e_re = xb + rf::kXbufFloats;
+    float* e_im = e_re + rf::kM;
+    __shared__ PeakAcc<float> s_red[rf::kNT / 32];
+    __shared__ uint32_t s_tmem;
+    constexpr uint32_t M = rf::kM, N = 2u * rf::kM;
+    const uint32_t t = threadIdx.x, warp = t >> 5, row = blockIdx.x;
+    const rf::Consts K = rf::load_consts(W, t);
+    const cf wNt = cconj(W[t]);
+
+    if (warp == 0) tmem_alloc_512(&s_tmem);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tbase = s_tmem + (((warp & 3u) * 32u) << 16) + (warp >> 2) * 128u;
+
+    // park the row: half h, register pair s -> columns h * 64 + 4 s .. + 3
+    {
+        const float4* X4 = reinterpret_cast<const float4*>(X + (size_t)row * N);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+#pragma unroll
+            for (int c4 = 0; c4 < 4; ++c4) {
+                float v[16];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float4 x = __ldg(X4 + (uint32_t)h * (M / 2) + (uint32_t)(4 * c4 + q) * 512u + t);
+                    v[4 * q] = x.x; v[4 * q + 1] = x.y; v[4 * q + 2] = x.z; v[4 * q + 3] = x.w;
+                }
+                tmem_st16(tbase + (uint32_t)(h * 64 + c4 * 16), v);
+            }
+        }
+        tmem_wait_st();
+    }
+
+#pragma unroll 1
+    for (uint32_t code = 0; code < g.P; ++code) {
+        const float4* C4 = reinterpret_cast<const float4*>(C + (size_t)code * N);
+        cf a[32];
+#pragma unroll
+        for (int c4 = 0; c4 < 4; ++c4) {
+            float v[16];
+            tmem_ld16(tbase + (uint32_t)(c4 * 16), v);
+            float4 c[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) c[q] = __ldg(C4 + (uint32_t)(4 * c4 + q) * 512u + t);
+            tmem_wait_ld();
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                a[8 * c4 + 2 * q] = rf::cmul(cf{v[4 * q], v[4 * q + 1]}, cf{c[q].x, c[q].y});
+                a[8 * c4 + 2 * q + 1] = rf::cmul(cf{v[4 * q + 2], v[4 * q + 3]}, cf{c[q].z, c[q].w});
+            }
+        }
+        rf::inverse<false, true>(a, xb, K, t, cf{1.0f, 0.0f});
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            e_re[(uint32_t)j * 512u + t] = a[rf::bitrev5(j)].re;
+            e_im[(uint32_t)j * 512u + t] = a[rf::bitrev5(j)].im;
+        }
+#pragma unroll
+        for (int c4 = 0; c4 < 4; ++c4) {
+            float v[16];
+            tmem_ld16(tbase + (uint32_t)(64 + c4 * 16), v);
+            float4 c[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) c[q] = __ldg(C4 + (M / 2) + (uint32_t)(4 * c4 + q) * 512u + t);
+            tmem_wait_ld();
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                a[8 * c4 + 2 * q] = rf::cmul(cf{v[4 * q], v[4 * q + 1]}, cf{c[q].x, c[q].y});
+                a[8 * c4 + 2 * q + 1] = rf::cmul(cf{v[4 * q + 2], v[4 * q + 3]}, cf{c[q].z, c[q].w});
+            }
+        }
+        rf::inverse<true, false>(a, xb, K, t, wNt);
+
+        PeakAcc<float> acc;
+        peak_init(acc);
+        cf hi[8];
+        RfEpilogue<0>::run(a, hi, e_re, e_im, t, g.L, acc);
+        if (g.L > M) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const uint32_t n = M + t + 512u * (uint32_t)j;
+                if (n < g.L) rf_peak_push(acc, hi[j].re * hi[j].re + hi[j].im * hi[j].im, n);
+            }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) peak_merge(acc, rf_peak_shfl_xor(acc, off));
+        if ((t & 31u) == 0) s_red[t >> 5] = acc;
+        __syncthreads();
+        if (t < 32) {
+            PeakAcc<float> b;
+            peak_init(b);
+            if (t < rf::kNT / 32) b = s_red[t];
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) peak_merge(b, rf_peak_shfl_xor(b, off));
+            if (t == 0) {
+                RowPeak o;
+                o.best = (double)b.best; o.second = (double)b.second; o.sum = (double)b.sum; o.lag = b.idx; o.pad = 0;
+                peaks[(size_t)row * g.P + code] = o;
+            }
+        }
+        // s_red is rewritten only after the next code's transforms, which synchronise the CTA many times
+    }
+
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) tmem_dealloc_512(s_tmem);
+}
+
 // ---------------------------------------------------------------------------------------------- launchers
 bool rf_supported(const AcqGeom& g) { return g.logN == rf::kLogM + 1 && g.L <= (uint32_t)rf::kM + 4096u; }
 
@@ -252,8 +403,27 @@ void launch_rf_fwd_codes(const AcqGeom& g, uint32_t n_codes, const int8_t* codes
     R4WB_LAUNCH_CHECK();
 }
 
+// R4WB_ACQ_TMEM=0 keeps the forward spectrum out of Tensor Memory (one CTA per (row, code), both operands from L2)
+bool rf_use_tmem()
+{
+    static int v = -1;
+    if (v < 0) { const char* e = std::getenv("R4WB_ACQ_TMEM"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v == 1;
+}
+
 void launch_rf_inv_peak(const AcqGeom& g, uint32_t rows, const cf* X, const cf* C, const cf* W, RowPeak* peaks, cudaStream_t st)
 {
+    if (rf_use_tmem()) {
+        static bool attr_tm = false;
+        if (!attr_tm) {
+            R4WB_CUDA(cudaFuncSetAttribute(k_rf_inv_peak_tm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rf_inv_smem()));
+            attr_tm = true;
+        }
+        if (rows == 0) return;
+        k_rf_inv_peak_tm<<<rows, rf::kNT, rf_inv_smem(), st>>>(g, X, C, W, peaks);
+        R4WB_LAUNCH_CHECK();
+        return;
+    }
     static bool attr = false;
     if (!attr) {
         R4WB_CUDA(cudaFuncSetAttribute(k_rf_inv_peak, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rf_inv_smem()));

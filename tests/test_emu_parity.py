@@ -175,3 +175,13 @@ def test_golden_fixtures_cpu(oracle, emu):
         assert (r.code_phase, r.doppler_hz, bool(r.detected)) == (lag, dop, bool(det))
         best, second, total, lin = emu.pcps(20000, 5e6, 5000.0, 250.0, x, oracle.e1c_replica(int(prn), 5e6, 20000))
         assert (lin % 20000, -5000.0 + (lin // 20000) * 250.0) == (lag, dop)
+
+
+def test_class_table_equals_arithmetic_classes(emu, monkeypatch):
+    """the fraction-indexed boundary-age table (synth_model.cpp, lut_den) and the arithmetic floor sums name the same
+    class for every sample: bit-identical replay with the table switched off"""
+    cfg = _cfg("e1c_8prn_60s_cn34_orbital")
+    with_table = emu.EmuScenario(cfg, noise=False).generate_range(7_495_000, 12000)
+    monkeypatch.setenv("R4WB_SYNTH_NO_LUT", "1")
+    without = emu.EmuScenario(cfg, noise=False).generate_range(7_495_000, 12000)
+    assert np.array_equal(with_table, without)

@@ -1,7 +1,10 @@
 """Parity of the CUDA PCPS acquisition path (through the C-ABI) with the oracle: the detected (code phase,
 Doppler bin) indices are the bit-exact contract.  Run on the B200 box: pytest -m gpu."""
+import os
 import numpy as np
 import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 from tests.conftest import config_path
 
@@ -213,3 +216,35 @@ def test_golden_acquisition_cases(gpu):
     for r, (prn, lag, dop, metric, det) in zip(res, rows):
         assert (r.prn, r.code_phase, r.doppler_hz, r.detected) == (int(prn), lag, dop, bool(det))
         assert r.peak_metric == pytest.approx(metric, rel=2e-4)
+
+
+_ACQ_DUMP = """
+import numpy as np, r4w_b200 as R
+from tests.conftest import config_path
+R.init(0)
+cfg = R.load_config(config_path('e1c_8prn_60s_cn34_orbital'), cli_elevation_mask_deg=5.0)
+x = R.GnssScenario(cfg, noise=True).generate_range(40_000_000, 6 * 20000)
+prns = list(range(1, 17))
+codes = np.stack([R.e1c_replica(p, 5e6, 20000) for p in prns])
+acq = R.PcpsAcquisition(20000, 5e6).with_doppler_range(5000.0, 250.0)
+res = acq.acquire_batch(x, 6, 20000, 20000, codes, prns)
+print(';'.join(f'{int(r.code_phase)},{r.doppler_hz},{int(r.detected)}' for s in res for r in s))
+"""
+
+
+def test_register_engine_equals_shared_memory_engine(gpu):
+    """fft_size 32768: the register-resident engine (rfft.cuh) and the in-shared-memory engine (fft.cuh) report the
+    same (lag, Doppler bin, detected) for every (snapshot, PRN) of a noisy 34 dB-Hz scenario, present PRNs or not"""
+    import subprocess
+    import sys
+
+    def run(extra):
+        env = dict(os.environ)
+        env.update(extra)
+        out = subprocess.run([sys.executable, "-c", _ACQ_DUMP], capture_output=True, text=True, env=env, timeout=600,
+                             cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+        assert out.returncode == 0, out.stderr[-2000:]
+        return out.stdout.strip().splitlines()[-1]
+
+    a, b = run({}), run({"R4WB_ACQ_ENGINE": "smem"})
+    assert a == b and a.count(";") == 6 * 16 - 1

@@ -1,6 +1,9 @@
 """Parity of the CUDA synthesis path (through the C-ABI) with the oracle.  Run on the B200 box: pytest -m gpu."""
+import os
 import numpy as np
 import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 from tests.conftest import config_path
 
@@ -190,3 +193,28 @@ def test_unsupported_inputs_fail_loudly(gpu):
     empty = cfg.copy(); empty.satellites = []; empty.output.duration_s = 0.001
     z = gpu.GnssScenario(empty, noise=False).generate()
     assert z.size == 5000 and not z.any()
+
+
+def _run_py(code, env_extra):
+    import subprocess
+    import sys
+    env = dict(os.environ)
+    env.update(env_extra)
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, cwd=ROOT, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    return out.stdout.strip().splitlines()[-1]
+
+
+_SYNTH_HASH = """
+import hashlib, numpy as np, r4w_b200 as R
+from tests.conftest import config_path
+R.init(0)
+cfg = R.load_config(config_path('e1c_8prn_60s_cn34_orbital'), cli_elevation_mask_deg=5.0)
+x = R.GnssScenario(cfg, noise=True).generate_range(9_990_000, 60_000)
+print(hashlib.sha256(np.ascontiguousarray(x).tobytes()).hexdigest())
+"""
+
+
+def test_class_table_path_equals_arithmetic_path(gpu):
+    """k_synth with the boundary-age class table and with the arithmetic floor sums: byte-identical IQ (noise on)"""
+    assert _run_py(_SYNTH_HASH, {}) == _run_py(_SYNTH_HASH, {"R4WB_SYNTH_NO_LUT": "1"})
