@@ -141,7 +141,7 @@ void Pcps::run(AcqWork<T>& w, const void* d_input, r4wb_fmt fmt, uint64_t s0, ui
     const uint32_t take = (uint32_t)std::min<uint64_t>(n_input, g.L);               // input.iter().take(samples_per_code)
     const uint32_t code_take = (uint32_t)std::min<uint64_t>(code_len, g.N);         // code_fft.resize(fft_size)
     // f32, fft_size 32768, no surface dump: the register-resident engine (one CTA per row / per (row, code))
-    const bool fast = sizeof(T) == 4 && d_grid == nullptr && rf_enabled() && rf_supported(g);
+    const bool fast = sizeof(T) == 4 && d_grid == nullptr && rf_enabled() && rf_supported(g) && code_take <= 16384u + 4096u;
     AcqGeom gr = g;                                                                 // geometry of the RowPeak table
     if (fast) gr.logF = 0;
     const uint32_t Fr = 1u << gr.logF;

@@ -79,12 +79,11 @@ k_rf_fwd(AcqGeom g, const void* __restrict__ input, uint32_t in64, uint64_t stri
         const cf Q = phasor_cycles(nu * 512.0);
         const cf qs = r ? cf{-qM.re, -qM.im} : qM;
         cf a[32];
-        cf P = cf{1.0f, 0.0f};
+        // pass 1: every load of the residue is issued before the first use (x[k] lands in a[j], x[k + M] in hi[j])
+        cf hi[8];
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
             const uint32_t k = t + 512u * (uint32_t)j;
-            if ((j & 7) == 0) P = phasor_cycles(nu * (double)k);    // re-anchor: f64 cycle reduction as the reference's f64 phase
-            else P = rf::cmul(P, Q);
             cf x0 = cf{0.0f, 0.0f}, x1 = cf{0.0f, 0.0f};
             if (MODE == 0) {
                 if (k < take) {
@@ -97,9 +96,19 @@ k_rf_fwd(AcqGeom g, const void* __restrict__ input, uint32_t in64, uint64_t stri
                 }
             } else {
                 if (k < take) x0.re = (float)code[k];
-                if (k + M < take) x1.re = (float)code[k + M];
+                if (j < 8 && k + M < take) x1.re = (float)code[k + M];
             }
-            a[j] = rf::cmul(P, rf::cadd(x0, rf::cmul(qs, x1)));
+            a[j] = x0;
+            if (j < 8) hi[j] = x1;
+        }
+        // pass 2: wipe-off / fold phasor, re-anchored in f64 every 8 points
+        cf P = cf{1.0f, 0.0f};
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            const uint32_t k = t + 512u * (uint32_t)j;
+            if ((j & 7) == 0) P = phasor_cycles(nu * (double)k);    // f64 cycle reduction as the reference's f64 phase
+            else P = rf::cmul(P, Q);
+            a[j] = rf::cmul(P, j < 8 ? rf::cadd(a[j], rf::cmul(qs, hi[j])) : a[j]);
         }
         rf::forward<true>(a, xb, K, t);
         float4* o = o4 + (size_t)r * (M / 2);
