@@ -278,6 +278,17 @@ def run_b200(args):
         scen.generate_range_into(first, n, host.value)
     torch.cuda.synchronize()
     ms_syn_e2e = (time.perf_counter() - ts) * 1e3 / e2e_steps
+    # the CLI's integer sink formats, converted in the store epilogue: fewer bytes over PCIe
+    fmt_e2e = {}
+    for name, code, bps in (("ci16", _lib.FMT_CI16, 4), ("ci8", _lib.FMT_CI8, 2)):
+        scen.generate_range_into(first, n, host.value, fmt=code)
+        torch.cuda.synchronize()
+        ts = time.perf_counter()
+        scen.generate_range_into(first, n, host.value, fmt=code)
+        torch.cuda.synchronize()
+        fmt_e2e[name] = {"msamples_per_s": n / (time.perf_counter() - ts) / 1e6, "d2h_bytes_per_step": n * bps}
+    scen.generate_range_into(first, n, host.value)              # host buffer back to cf32 for the acquisition leg
+    torch.cuda.synchronize()
     ts = time.perf_counter()
     for _ in range(e2e_steps):
         pods = acq.acquire_batch_raw(host_np, n_snap, CODE_LENGTH, CODE_LENGTH, codes, prns)
@@ -335,7 +346,8 @@ def run_b200(args):
                          "traffic": ncu_traffic("k_synth"), "peak_source": peak_src, "algorithmic_bytes_per_launch": n * 8,
                          "note": "8 B per output sample (one cf32 store); CUDA events on the launching stream"},
             "e2e": {"value": total_samples / (ms_syn_e2e * 1e-3) / 1e6, "unit": "Msamples/s", "h2d_bytes_per_step": 0,
-                    "d2h_bytes_per_step": n * 8, "api": "r4wb_scenario_generate(..., R4WB_MEM_HOST, CF32) into pinned host memory"},
+                    "d2h_bytes_per_step": n * 8, "api": "r4wb_scenario_generate(..., R4WB_MEM_HOST, CF32) into pinned host memory",
+                    "other_formats_rank0": fmt_e2e},
             "acq": {"metric": "pcps_acq_cells_per_s", "value": cells / (ms_acq * 1e-3), "unit": "cells/s", "ms_per_step": ms_acq,
                     "cells_per_step": cells, "f64_guard_reruns": guards,
                     "kernel_ms": {k: v[0] for k, v in prof.items()}, "kernel_launches": {k: v[1] for k, v in prof.items()},

@@ -40,7 +40,11 @@ typedef struct r4wb_cf32 { float re, im; } r4wb_cf32;   /* IqFormat::Cf32 sample
 typedef struct r4wb_cf64 { double re, im; } r4wb_cf64;  /* num_complex::Complex64 layout (r4w.h:50-55)       */
 
 typedef enum r4wb_mem { R4WB_MEM_HOST = 0, R4WB_MEM_DEVICE = 1 } r4wb_mem;
-typedef enum r4wb_fmt { R4WB_FMT_CF32 = 0, R4WB_FMT_CF64 = 1 } r4wb_fmt;
+/* IqFormat (core/io/format.rs:44-60, write_sample :191-227).  CF32/CF64 are accepted everywhere; the integer sink formats
+ * only as synthesis OUTPUT, converted in the store epilogue with the reference's expressions:
+ *   CI16  (x * 32767).clamp(-32768, 32767) as i16      CI8  (x * 127).clamp(-128, 127) as i8
+ *   CU8   ((x + 1) * 127.5).clamp(0, 255) as u8        (`as` truncates toward zero), interleaved re, im. */
+typedef enum r4wb_fmt { R4WB_FMT_CF32 = 0, R4WB_FMT_CF64 = 1, R4WB_FMT_CI16 = 2, R4WB_FMT_CI8 = 3, R4WB_FMT_CU8 = 4 } r4wb_fmt;
 
 /* gnss/types.rs:33-47 (declaration order) */
 typedef enum r4wb_signal {

@@ -86,6 +86,8 @@ def lib():
         L.orc_pcps_acquire_grid.argtypes = [C.POINTER(PcpsPod), vp, sz, vp, sz, vp]
         L.orc_pcps_acquire_grid.restype = C.c_int64
         L.orc_to_cf32.argtypes = [vp, sz, vp]
+        L.orc_to_int_format.argtypes = [vp, sz, C.c_int, vp]
+        L.orc_to_int_format.restype = C.c_int
         _lib = L
     return _lib
 
@@ -245,6 +247,18 @@ class OracleScenario:
         arr = (SatStatusPod * max(n, 1))()
         lib().orc_scenario_status(self._h, arr, n)
         return [arr[k] for k in range(n)]
+
+
+INT_FORMATS = {"ci16": (2, np.int16), "ci8": (3, np.int8), "cu8": (4, np.uint8)}
+
+
+def to_int_format(x: np.ndarray, fmt: str) -> np.ndarray:
+    """IqFormat::{Ci16, Ci8, Cu8}.write_sample (core/io/format.rs:203-222) -> [n][2] integers (re, im)"""
+    code, dt = INT_FORMATS[fmt]
+    a = np.ascontiguousarray(x, np.complex128)
+    out = np.empty((a.size, 2), dt)
+    assert lib().orc_to_int_format(_ptr(a), a.size, code, _ptr(out)) == 0
+    return out
 
 
 def to_cf32(x: np.ndarray) -> np.ndarray:

@@ -1000,6 +1000,32 @@ int64_t orc_pcps_acquire_grid(const orc_pcps* p, const orc_c64* input, size_t n_
 }
 
 /* IqFormat::Cf32 write_sample, core/io/format.rs:197-200: `(x as f32)` rounds to nearest even */
+/* IqFormat::write_sample for the integer sink formats (core/io/format.rs:203-222): f64 scale, clamp, Rust `as`
+ * (truncation toward zero; NaN -> 0).  fmt: 2 = ci16, 3 = ci8, 4 = cu8 (the r4wb_fmt numbering). */
+static double orc_clamp(double x, double lo, double hi) { return x < lo ? lo : (x > hi ? hi : x); }
+int orc_to_int_format(const orc_c64* in, size_t n, int fmt, void* out)
+{
+    for (size_t i = 0; i < n; ++i) {
+        const double c[2] = {in[i].re, in[i].im};
+        for (int k = 0; k < 2; ++k) {
+            const double x = c[k];
+            if (fmt == 2) {
+                const double v = orc_clamp(x * 32767.0, -32768.0, 32767.0);
+                ((int16_t*)out)[2 * i + k] = (x != x) ? 0 : (int16_t)v;
+            } else if (fmt == 3) {
+                const double v = orc_clamp(x * 127.0, -128.0, 127.0);
+                ((int8_t*)out)[2 * i + k] = (x != x) ? 0 : (int8_t)v;
+            } else if (fmt == 4) {
+                const double v = orc_clamp((x + 1.0) * 127.5, 0.0, 255.0);
+                ((uint8_t*)out)[2 * i + k] = (x != x) ? 0 : (uint8_t)v;
+            } else {
+                return -1;
+            }
+        }
+    }
+    return 0;
+}
+
 void orc_to_cf32(const orc_c64* in, size_t n, float* out)
 {
     for (size_t i = 0; i < n; ++i) { out[2 * i] = (float)in[i].re; out[2 * i + 1] = (float)in[i].im; }

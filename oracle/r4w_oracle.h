@@ -158,6 +158,8 @@ int64_t orc_pcps_acquire_grid(const orc_pcps* p, const orc_c64* input, size_t n_
 
 /* IqFormat::Cf32 sink cast, core/io/format.rs:197-200 */
 void orc_to_cf32(const orc_c64* in, size_t n, float* out_interleaved);
+/* core/io/format.rs:203-222, fmt 2 = ci16, 3 = ci8, 4 = cu8; out = interleaved (re, im) integers */
+int orc_to_int_format(const orc_c64* in, size_t n, int fmt, void* out);
 
 #ifdef __cplusplus
 }

@@ -18,7 +18,7 @@ ERRORS = {0: "Ok", 1: "NullPointer", 2: "InvalidSize", 3: "BufferFull", 4: "Buff
           6: "AllocationFailed", 7: "NotSupported", 100: "Cuda"}
 
 MEM_HOST, MEM_DEVICE = 0, 1
-FMT_CF32, FMT_CF64 = 0, 1
+FMT_CF32, FMT_CF64, FMT_CI16, FMT_CI8, FMT_CU8 = 0, 1, 2, 3, 4
 
 
 class R4wB200Error(RuntimeError):

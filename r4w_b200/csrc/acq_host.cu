@@ -219,7 +219,7 @@ void Pcps::acquire_batch(const void* input, r4wb_fmt fmt, r4wb_mem where, uint64
 {
     if (S == 0 || P == 0) return;
     if (S * (uint64_t)P > 0x7fffffffull) fail(R4WB_ERR_INVALID_SIZE, "too many (snapshot, code) pairs in one call");
-    if (fmt != R4WB_FMT_CF32 && fmt != R4WB_FMT_CF64) fail(R4WB_ERR_INVALID_PARAMETER, "unknown sample format");
+    if (fmt != R4WB_FMT_CF32 && fmt != R4WB_FMT_CF64) fail(R4WB_ERR_INVALID_PARAMETER, "acquisition input must be cf32 or cf64");
     if (code_length_ == 0) fail(R4WB_ERR_INVALID_SIZE, "code_length is 0");
     cudaStream_t st = current_stream();
     const size_t bps = fmt == R4WB_FMT_CF64 ? 16 : 8;
@@ -266,6 +266,7 @@ void Pcps::acquire_batch(const void* input, r4wb_fmt fmt, r4wb_mem where, uint64
 void Pcps::acquire_grid(const void* input, r4wb_fmt fmt, uint64_t n_input, const int8_t* code, uint64_t code_len,
                         double* power_out, uint64_t cap)
 {
+    if (fmt != R4WB_FMT_CF32 && fmt != R4WB_FMT_CF64) fail(R4WB_ERR_INVALID_PARAMETER, "acquisition input must be cf32 or cf64");
     const uint64_t cells = (uint64_t)num_bins() * code_length_;
     if (cap < cells) fail(R4WB_ERR_INVALID_SIZE, "grid buffer holds %llu of %llu cells", (unsigned long long)cap, (unsigned long long)cells);
     if (cells == 0) return;

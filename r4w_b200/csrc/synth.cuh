@@ -126,7 +126,7 @@ struct SynthArgs {
     uint32_t n_sats;
     uint32_t nw64;             // 64-bit words of the per-satellite half-chip sign table
     uint32_t flags;
-    uint32_t out_aligned16;    // out is 16-byte aligned: sample pairs may be stored as one float4
+    uint32_t out_aligned16;    // out is aligned to two samples of the output format: sample pairs may be stored as one vector
     uint64_t delta46;
     uint32_t kmul;
     uint32_t cj[8];
@@ -173,6 +173,12 @@ struct SeqState {
     void make_table(const ScenarioModel& md, uint64_t first, uint32_t n, std::vector<BlockSat>& tab, BlockHdr hdr[2]) const;
     void advance(const ScenarioModel& md, const std::vector<BlockSat>& tab, uint32_t n);
 };
+
+// bytes per complex sample of an output format (IqFormat::bytes_per_sample, core/io/format.rs)
+inline size_t fmt_bytes(r4wb_fmt fmt)
+{
+    switch (fmt) { case R4WB_FMT_CF64: return 16; case R4WB_FMT_CF32: return 8; case R4WB_FMT_CI16: return 4; default: return 2; }
+}
 
 size_t synth_smem_bytes(uint32_t n_sats, uint32_t nw64, uint32_t lut_den);
 int synth_tile_samples(int K);

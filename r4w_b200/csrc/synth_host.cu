@@ -9,8 +9,8 @@
 namespace r4wb {
 
 // launchers (synth_kernels.cu)
-void launch_synth_kernel(const SynthArgs& a, int K, bool cf64, int grid, cudaStream_t st);
-int synth_max_blocks_per_sm(int K, bool cf64, size_t smem);
+void launch_synth_kernel(const SynthArgs& a, int K, r4wb_fmt fmt, int grid, cudaStream_t st);
+int synth_max_blocks_per_sm(int K, r4wb_fmt fmt, size_t smem);
 void launch_block_params(const ScenConst&, const SatConst*, const PhaseSegment*, uint64_t, uint32_t, BlockSat*, BlockHdr*, cudaStream_t);
 void launch_phase_scan(const SatConst*, uint32_t, uint32_t, BlockSat*, cudaStream_t);
 void launch_tile_params(const SynthArgs& a, uint32_t tb_begin, uint32_t tb_count, uint32_t tile_samples, TileRec* out, cudaStream_t st);
@@ -103,7 +103,7 @@ void Scenario::launch_synth(const BlockSat* tab, const BlockHdr* hdr, const Tile
     a.out = d_out; a.power_sum = d_power_.p;
     a.out_first = out_first; a.out_n = out_n;
     a.tb_begin = tb_begin; a.tb_count = tb_count;
-    a.out_aligned16 = ((uintptr_t)d_out & 15u) == 0 ? 1u : 0u;
+    a.out_aligned16 = ((uintptr_t)d_out % (2 * fmt_bytes(fmt))) == 0 ? 1u : 0u;
 
     static int sm_count = 0;
     if (!sm_count) {
@@ -111,19 +111,19 @@ void Scenario::launch_synth(const BlockSat* tab, const BlockHdr* hdr, const Tile
         R4WB_CUDA(cudaGetDevice(&dev));
         R4WB_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
     }
-    const bool cf64 = fmt == R4WB_FMT_CF64;
+    const int tile_k = md_.tile_k;
     const size_t smem = synth_smem_bytes(a.n_sats, a.nw64, a.lut_den);
-    const int per_sm = std::max(1, synth_max_blocks_per_sm(md_.tile_k, cf64, smem));
+    const int per_sm = std::max(1, synth_max_blocks_per_sm(tile_k, fmt, smem));
     const uint64_t n_tiles = (uint64_t)tb_count * a.tiles_per_block;
     const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>(n_tiles, (uint64_t)sm_count * per_sm));
-    launch_synth_kernel(a, md_.tile_k, cf64, grid, current_stream());
+    launch_synth_kernel(a, tile_k, fmt, grid, current_stream());
 }
 
 void Scenario::render_to(uint64_t first, uint64_t n, void* dst, r4wb_mem where, r4wb_fmt fmt)
 {
     const ScenConst& sc = md_.sc;
     cudaStream_t st = current_stream();
-    const size_t bps = fmt == R4WB_FMT_CF64 ? 16 : 8;
+    const size_t bps = fmt_bytes(fmt);
     R4WB_CUDA(cudaMemsetAsync(d_power_.p, 0, sizeof(double), st));
 
     const uint64_t b0 = first / sc.B, b1 = (first + n - 1) / sc.B;
@@ -151,6 +151,7 @@ void Scenario::generate(uint64_t first, uint64_t n, void* dst, r4wb_mem where, r
     const ScenConst& sc = md_.sc;
     if (first > sc.total || n > sc.total - first) fail(R4WB_ERR_INVALID_SIZE, "range [%llu, +%llu) exceeds total_samples %llu",
                                                        (unsigned long long)first, (unsigned long long)n, (unsigned long long)sc.total);
+    if ((unsigned)fmt > (unsigned)R4WB_FMT_CU8) fail(R4WB_ERR_INVALID_PARAMETER, "unknown sample format %d", (int)fmt);
     if (n == 0) return;
     if (!dst) fail(R4WB_ERR_NULL_POINTER, "dst is NULL");
     render_to(first, n, dst, where, fmt);
@@ -164,6 +165,7 @@ uint64_t Scenario::generate_block(uint64_t n_req, void* dst, r4wb_mem where, r4w
     if (n == 0) return 0;
     if (!dst) fail(R4WB_ERR_NULL_POINTER, "dst is NULL");
     if (n > 65536) fail(R4WB_ERR_NOT_SUPPORTED, "generate_block: at most 65536 samples per reference block");
+    if ((unsigned)fmt > (unsigned)R4WB_FMT_CU8) fail(R4WB_ERR_INVALID_PARAMETER, "unknown sample format %d", (int)fmt);
     cudaStream_t st = current_stream();
     std::vector<BlockSat> tab;
     BlockHdr hdr[2];
@@ -171,7 +173,7 @@ uint64_t Scenario::generate_block(uint64_t n_req, void* dst, r4wb_mem where, r4w
     R4WB_CUDA(cudaMemcpyAsync(d_seq_tab_.reserve(tab.size()), tab.data(), tab.size() * sizeof(BlockSat), cudaMemcpyHostToDevice, st));
     R4WB_CUDA(cudaMemcpyAsync(d_seq_hdr_.reserve(2), hdr, sizeof(BlockHdr) * 2, cudaMemcpyHostToDevice, st));
     R4WB_CUDA(cudaMemsetAsync(d_power_.p, 0, sizeof(double), st));
-    const size_t bps = fmt == R4WB_FMT_CF64 ? 16 : 8;
+    const size_t bps = fmt_bytes(fmt);
     void* d_out = where == R4WB_MEM_DEVICE ? dst : (void*)d_stage_.reserve((size_t)n * bps);
     {
         SynthArgs a = base_args(d_seq_tab_.p, d_seq_hdr_.p, n);

@@ -142,7 +142,40 @@ __device__ __forceinline__ SynthSmem carve_smem(unsigned char* raw, uint32_t n_s
     return m;
 }
 
-template <int K, bool CF64>
+// sink conversions of core/io/format.rs:203-222 (Rust `as` = truncation toward zero after the clamp)
+// in f64 like the reference, so the code is exactly what write_sample produces for the f32 sample widened to f64
+__device__ __forceinline__ int to_i16(float x) { return __double2int_rz(fmin(fmax((double)x * 32767.0, -32768.0), 32767.0)); }
+__device__ __forceinline__ int to_i8(float x) { return __double2int_rz(fmin(fmax((double)x * 127.0, -128.0), 127.0)); }
+__device__ __forceinline__ int to_u8(float x) { return __double2int_rz(fmin(fmax(((double)x + 1.0) * 127.5, 0.0), 255.0)); }
+
+// one complex sample (re, im) in output format FMT at sample index o
+template <int FMT>
+__device__ __forceinline__ void store_sample(void* out, uint64_t o, float re, float im)
+{
+    if (FMT == R4WB_FMT_CF64) reinterpret_cast<double2*>(out)[o] = make_double2((double)re, (double)im);
+    else if (FMT == R4WB_FMT_CF32) reinterpret_cast<float2*>(out)[o] = make_float2(re, im);
+    else if (FMT == R4WB_FMT_CI16) reinterpret_cast<uint32_t*>(out)[o] = ((uint32_t)to_i16(re) & 0xffffu) | ((uint32_t)to_i16(im) << 16);
+    else if (FMT == R4WB_FMT_CI8) reinterpret_cast<uint16_t*>(out)[o] = (uint16_t)(((uint32_t)to_i8(re) & 0xffu) | (((uint32_t)to_i8(im) & 0xffu) << 8));
+    else reinterpret_cast<uint16_t*>(out)[o] = (uint16_t)((uint32_t)to_u8(re) | ((uint32_t)to_u8(im) << 8));
+}
+// two adjacent samples at even sample index o (out aligned to the pair)
+template <int FMT>
+__device__ __forceinline__ void store_pair(void* out, uint64_t o, float4 v)
+{
+    if (FMT == R4WB_FMT_CF32) reinterpret_cast<float4*>(out)[o >> 1] = v;
+    else if (FMT == R4WB_FMT_CI16)
+        reinterpret_cast<uint2*>(out)[o >> 1] = make_uint2(((uint32_t)to_i16(v.x) & 0xffffu) | ((uint32_t)to_i16(v.y) << 16),
+                                                           ((uint32_t)to_i16(v.z) & 0xffffu) | ((uint32_t)to_i16(v.w) << 16));
+    else if (FMT == R4WB_FMT_CI8)
+        reinterpret_cast<uint32_t*>(out)[o >> 1] = ((uint32_t)to_i8(v.x) & 0xffu) | (((uint32_t)to_i8(v.y) & 0xffu) << 8) |
+                                                   (((uint32_t)to_i8(v.z) & 0xffu) << 16) | ((uint32_t)to_i8(v.w) << 24);
+    else if (FMT == R4WB_FMT_CU8)
+        reinterpret_cast<uint32_t*>(out)[o >> 1] = (uint32_t)to_u8(v.x) | ((uint32_t)to_u8(v.y) << 8) | ((uint32_t)to_u8(v.z) << 16) |
+                                                   ((uint32_t)to_u8(v.w) << 24);
+    else { store_sample<FMT>(out, o, v.x, v.y); store_sample<FMT>(out, o + 1, v.z, v.w); }
+}
+
+template <int K, int FMT>
 __global__ void __launch_bounds__(kThreads, K <= 5 ? 3 : 2) k_synth(SynthArgs a)
 {
     constexpr int TILE = kThreads * 2 * K;
@@ -229,10 +262,10 @@ __global__ void __launch_bounds__(kThreads, K <= 5 ? 3 : 2) k_synth(SynthArgs a)
         // output (the usual case) stores float4 pairs without per-sample range checks.
         const bool noise_on = !(a.flags & R4WB_FLAG_NOISE_OFF);
         const uint64_t m0 = hd.first + i_begin;
-        const bool tile_plain = !CF64 && a.out_aligned16 && m0 >= a.out_first && hd.first + i_end <= a.out_first + a.out_n &&
+        const bool tile_plain = a.out_aligned16 && m0 >= a.out_first && hd.first + i_end <= a.out_first + a.out_n &&
                                 (((m0 - a.out_first) | (uint64_t)i_end) & 1ull) == 0;
         if (tile_plain) {
-            float4* out = reinterpret_cast<float4*>(reinterpret_cast<float2*>(a.out) + (m0 - a.out_first)) + tid;
+            const uint64_t o0 = (m0 - a.out_first) + 2u * tid;  // even
             const uint64_t ctr0 = (m0 >> 1) + tid;               // m0 is even when out_first is; odd handled below
             const bool m_even = (m0 & 1ull) == 0;
 #pragma unroll
@@ -253,7 +286,7 @@ __global__ void __launch_bounds__(kThreads, K <= 5 ? 3 : 2) k_synth(SynthArgs a)
                     v.z = fmaf(gb2.x, a.noise_std, v.z); v.w = fmaf(gb2.y, a.noise_std, v.w);
                 }
                 pow_acc += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
-                out[kThreads * k] = v;
+                store_pair<FMT>(a.out, o0 + (uint64_t)(2 * kThreads * k), v);
             }
             continue;
         }
@@ -281,18 +314,11 @@ __global__ void __launch_bounds__(kThreads, K <= 5 ? 3 : 2) k_synth(SynthArgs a)
             if (wa) pow_acc += va.x * va.x + va.y * va.y;
             if (wb) pow_acc += vb.x * vb.x + vb.y * vb.y;
             const uint64_t o = m - a.out_first;                  // only meaningful when wa (wraps otherwise)
-            if (CF64) {
-                double2* out = reinterpret_cast<double2*>(a.out);
-                if (wa) out[o] = make_double2((double)va.x, (double)va.y);
-                if (wb) out[o + 1] = make_double2((double)vb.x, (double)vb.y);
+            if (wa && wb && ((o & 1ull) == 0) && a.out_aligned16) {
+                store_pair<FMT>(a.out, o, make_float4(va.x, va.y, vb.x, vb.y));
             } else {
-                float2* out = reinterpret_cast<float2*>(a.out);
-                if (wa && wb && ((o & 1ull) == 0) && a.out_aligned16) {
-                    *reinterpret_cast<float4*>(out + o) = make_float4(va.x, va.y, vb.x, vb.y);
-                } else {
-                    if (wa) out[o] = va;
-                    if (wb) out[o + 1] = vb;
-                }
+                if (wa) store_sample<FMT>(a.out, o, va.x, va.y);
+                if (wb) store_sample<FMT>(a.out, o + 1, vb.x, vb.y);
             }
         }
     }
@@ -311,38 +337,55 @@ __global__ void __launch_bounds__(kThreads, K <= 5 ? 3 : 2) k_synth(SynthArgs a)
 
 // ----------------------------------------------------------------------------------------------
 // launchers (called from synth_host.cu)
-template <int K, bool CF64>
+template <int K, int FMT>
 static void launch_synth_t(const SynthArgs& a, int grid, size_t smem, cudaStream_t st)
 {
     static bool attr_done = false;
     if (!attr_done) {
-        R4WB_CUDA(cudaFuncSetAttribute(k_synth<K, CF64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        R4WB_CUDA(cudaFuncSetAttribute(k_synth<K, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr_done = true;
     }
-    k_synth<K, CF64><<<grid, kThreads, smem, st>>>(a);
+    k_synth<K, FMT><<<grid, kThreads, smem, st>>>(a);
     R4WB_LAUNCH_CHECK();
 }
 
-void launch_synth_kernel(const SynthArgs& a, int K, bool cf64, int grid, cudaStream_t st)
+template <int K, int FMT>
+static int max_blocks_t(size_t smem)
+{
+    int nb = 0;
+    R4WB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_synth<K, FMT>, kThreads, smem));
+    return nb;
+}
+
+// K = 5 (tuning hook) exists for the float formats only
+void launch_synth_kernel(const SynthArgs& a, int K, r4wb_fmt fmt, int grid, cudaStream_t st)
 {
     const size_t smem = synth_smem_bytes(a.n_sats, a.nw64, a.lut_den);
     if (smem > 200 * 1024) fail(R4WB_ERR_NOT_SUPPORTED, "scenario needs %zu bytes of shared memory per CTA", smem);
-    if (K == 5) { cf64 ? launch_synth_t<5, true>(a, grid, smem, st) : launch_synth_t<5, false>(a, grid, smem, st); }
-    else if (K == 10) { cf64 ? launch_synth_t<10, true>(a, grid, smem, st) : launch_synth_t<10, false>(a, grid, smem, st); }
-    else fail(R4WB_ERR_INVALID_PARAMETER, "unsupported tile factor %d", K);
+    if (K == 5 && fmt == R4WB_FMT_CF32) return launch_synth_t<5, R4WB_FMT_CF32>(a, grid, smem, st);
+    if (K == 5 && fmt == R4WB_FMT_CF64) return launch_synth_t<5, R4WB_FMT_CF64>(a, grid, smem, st);
+    if (K != 10) fail(R4WB_ERR_INVALID_PARAMETER, "unsupported tile factor %d for this format", K);
+    switch (fmt) {
+    case R4WB_FMT_CF32: return launch_synth_t<10, R4WB_FMT_CF32>(a, grid, smem, st);
+    case R4WB_FMT_CF64: return launch_synth_t<10, R4WB_FMT_CF64>(a, grid, smem, st);
+    case R4WB_FMT_CI16: return launch_synth_t<10, R4WB_FMT_CI16>(a, grid, smem, st);
+    case R4WB_FMT_CI8: return launch_synth_t<10, R4WB_FMT_CI8>(a, grid, smem, st);
+    case R4WB_FMT_CU8: return launch_synth_t<10, R4WB_FMT_CU8>(a, grid, smem, st);
+    }
+    fail(R4WB_ERR_INVALID_PARAMETER, "unknown sample format %d", (int)fmt);
 }
 
-int synth_max_blocks_per_sm(int K, bool cf64, size_t smem)
+int synth_max_blocks_per_sm(int K, r4wb_fmt fmt, size_t smem)
 {
-    int nb = 0;
-    if (K == 5) {
-        if (cf64) R4WB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_synth<5, true>, kThreads, smem));
-        else R4WB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_synth<5, false>, kThreads, smem));
-    } else {
-        if (cf64) R4WB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_synth<10, true>, kThreads, smem));
-        else R4WB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_synth<10, false>, kThreads, smem));
+    if (K == 5 && fmt == R4WB_FMT_CF32) return max_blocks_t<5, R4WB_FMT_CF32>(smem);
+    if (K == 5 && fmt == R4WB_FMT_CF64) return max_blocks_t<5, R4WB_FMT_CF64>(smem);
+    switch (fmt) {
+    case R4WB_FMT_CF64: return max_blocks_t<10, R4WB_FMT_CF64>(smem);
+    case R4WB_FMT_CI16: return max_blocks_t<10, R4WB_FMT_CI16>(smem);
+    case R4WB_FMT_CI8: return max_blocks_t<10, R4WB_FMT_CI8>(smem);
+    case R4WB_FMT_CU8: return max_blocks_t<10, R4WB_FMT_CU8>(smem);
+    default: return max_blocks_t<10, R4WB_FMT_CF32>(smem);
     }
-    return nb;
 }
 
 void launch_block_params(const ScenConst& sc, const SatConst* d_sats, const PhaseSegment* d_segs, uint64_t blk0, uint32_t nblk,

@@ -138,6 +138,14 @@ class GnssScenario:
                                                      _lib.MEM_HOST, fmt))
         return out[:n]
 
+    def generate_range_format(self, first: int, n: int, fmt: str) -> np.ndarray:
+        """Samples [first, first+n) in one of the CLI's integer sink formats ("ci16", "ci8", "cu8": IqFormat::write_sample,
+        core/io/format.rs:203-222), converted in the kernel's store epilogue -> [n][2] integers (re, im)."""
+        code, dt = {"ci16": (_lib.FMT_CI16, np.int16), "ci8": (_lib.FMT_CI8, np.int8), "cu8": (_lib.FMT_CU8, np.uint8)}[fmt]
+        out = np.empty((int(n), 2), dt)
+        _lib.check(_lib.lib().r4wb_scenario_generate(self._h, int(first), int(n), out.ctypes.data_as(C.c_void_p), _lib.MEM_HOST, code))
+        return out
+
     def generate_range_into(self, first: int, n: int, host_ptr: int, fmt: int = _lib.FMT_CF32):
         """Same, into caller-owned host memory (e.g. pinned, r4wb_host_alloc)."""
         _lib.check(_lib.lib().r4wb_scenario_generate(self._h, int(first), int(n), C.c_void_p(host_ptr), _lib.MEM_HOST, fmt))

@@ -218,3 +218,26 @@ print(hashlib.sha256(np.ascontiguousarray(x).tobytes()).hexdigest())
 def test_class_table_path_equals_arithmetic_path(gpu):
     """k_synth with the boundary-age class table and with the arithmetic floor sums: byte-identical IQ (noise on)"""
     assert _run_py(_SYNTH_HASH, {}) == _run_py(_SYNTH_HASH, {"R4WB_SYNTH_NO_LUT": "1"})
+
+
+@pytest.mark.parametrize("fmt,lsb", [("ci16", 1), ("ci8", 1), ("cu8", 1)])
+def test_integer_sink_formats_match_oracle(gpu, oracle, fmt, lsb):
+    """the CLI's integer sink formats (core/io/format.rs:203-222) fused into the store epilogue.  The
+    oracle converts its f64 samples, the kernel its f32 ones, so a value within 1e-5 of a quantisation step may land one
+    code away: every sample within 1 LSB, and all but a sliver exactly equal.  A weak scenario (C/N0 24 dB-Hz, noise off)
+    keeps the samples inside [-1, 1] so the comparison is not all clipping; the stock config (everything clips) too."""
+    cfg = _cfg("e1c_8prn_20s_clean")
+    weak = cfg.copy()
+    for s in weak.satellites:
+        s.cn0_dbhz = 24.0
+    for c, noise, floor in ((weak, False, 0.995), (cfg, True, 0.9999)):
+        first, n = 4_999_000, 12_001          # odd start and length: pair-misaligned edges
+        got = gpu.GnssScenario(c, noise=noise).generate_range_format(first, n, fmt)
+        ref_f = gpu.GnssScenario(c, noise=noise).generate_range(first, n)          # same f32 samples the kernel converts
+        want = oracle.to_int_format(ref_f.astype(np.complex128), fmt)
+        assert np.array_equal(got, want)                                            # conversion itself: bit-exact on equal input
+        if not noise:
+            true = oracle.to_int_format(oracle.OracleScenario(c, noise=False).generate_range(first, n), fmt)
+            d = np.abs(got.astype(np.int64) - true.astype(np.int64))
+            assert d.max() <= lsb and (d == 0).mean() >= floor
+            assert np.abs(true.astype(np.int64)).max() < (32767 if fmt == "ci16" else 127 if fmt == "ci8" else 255)

@@ -208,3 +208,23 @@ def test_skip_to_equals_sequential(oracle):
     full = np.concatenate([seq.generate_block(5000) for _ in range(20)])
     win = oracle.OracleScenario(cfg).generate_range(62_345, 9_000)
     assert np.array_equal(win, full[62_345:71_345])
+
+
+def test_integer_sink_formats(oracle):
+    """IqFormat::{Ci16, Ci8, Cu8}.write_sample (core/io/format.rs:203-222): scale, clamp, truncate toward zero.  Inputs
+    and tolerances of the reference's test_roundtrip_ci16 / _ci8 / _cu8 (format.rs:545-606: (0.5,-0.5), (-1,1), (0,0) must
+    read back within 1e-4 / 0.02 / 0.02) and test_clamping (:647-663: (2,-3) reads back > 0.99 / < -0.99), plus exact codes."""
+    ref = np.array([0.5 - 0.5j, -1.0 + 1.0j, 0.0 + 0.0j], np.complex128)
+    for fmt, back, tol in (("ci16", lambda v: v / 32768.0, 1e-4), ("ci8", lambda v: v / 128.0, 0.02),
+                           ("cu8", lambda v: (v - 127.5) / 127.5, 0.02)):
+        dec = back(oracle.to_int_format(ref, fmt).astype(np.float64))            # read_sample, format.rs:256-277
+        assert np.abs(dec[:, 0] - ref.real).max() < tol and np.abs(dec[:, 1] - ref.imag).max() < tol
+        clip = back(oracle.to_int_format(np.array([2.0 - 3.0j]), fmt).astype(np.float64))
+        assert clip[0, 0] > 0.99 and clip[0, 1] < -0.99
+    x = np.array([0.5 - 0.25j, 1.0 + 1.0j, -1.0 - 1.0j, 2.0 - 3.0j, 0.0 + 0.999j, -0.00001 + 0.00001j], np.complex128)
+    ci16 = oracle.to_int_format(x, "ci16")
+    assert ci16.tolist() == [[16383, -8191], [32767, 32767], [-32767, -32767], [32767, -32768], [0, 32734], [0, 0]]
+    ci8 = oracle.to_int_format(x, "ci8")
+    assert ci8.tolist() == [[63, -31], [127, 127], [-127, -127], [127, -128], [0, 126], [0, 0]]
+    cu8 = oracle.to_int_format(x, "cu8")
+    assert cu8.tolist() == [[191, 95], [255, 255], [0, 0], [255, 0], [127, 254], [127, 127]]
