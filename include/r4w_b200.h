@@ -104,11 +104,15 @@ typedef struct r4wb_receiver_cfg {
     double traj_speed_mps;
 } r4wb_receiver_cfg;
 
-/* POD mirror of EnvironmentConfig, gnss/scenario_config.rs:417-437.  The Klobuchar / Saastamoinen
- * models are only consulted when a satellite lacks the iono_delay_m / tropo_delay_m override
- * (gnss/scenario.rs:430-439); that combination returns R4WB_ERR_NOT_SUPPORTED in this build. */
+/* POD mirror of EnvironmentConfig, gnss/scenario_config.rs:417-437.  The Klobuchar / Saastamoinen models
+ * (gnss/environment/ionosphere.rs:26-108, troposphere.rs:26-104) are consulted per block for a satellite that lacks
+ * the iono_delay_m / tropo_delay_m override (gnss/scenario.rs:430-439 via SatelliteEmitter::status_at,
+ * satellite_emitter.rs:165-178).  The host fills the model fields with the YAML's `ionosphere_model` /
+ * `troposphere_model` or, when those are null, KlobucharModel::default_broadcast / SaastamoinenModel::standard_atmosphere. */
 typedef struct r4wb_environment_cfg {
     uint32_t ionosphere_enabled, troposphere_enabled, multipath_enabled, multipath_preset;
+    double klobuchar_alpha[4], klobuchar_beta[4];
+    double tropo_height_m, tropo_temperature_k, tropo_pressure_hpa, tropo_relative_humidity;
 } r4wb_environment_cfg;
 
 /* POD mirror of OutputConfig, gnss/scenario_config.rs:455-487 (format/output_path are host-side only) */

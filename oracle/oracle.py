@@ -86,6 +86,13 @@ def lib():
         L.orc_pcps_acquire_grid.argtypes = [C.POINTER(PcpsPod), vp, sz, vp, sz, vp]
         L.orc_pcps_acquire_grid.restype = C.c_int64
         L.orc_to_cf32.argtypes = [vp, sz, vp]
+        d = C.c_double
+        L.orc_klobuchar_delay_s.argtypes = [vp, vp, d, d, d, d, d]
+        L.orc_klobuchar_delay_s.restype = d
+        L.orc_saastamoinen_delay_m.argtypes = [d, d, d, d, d]
+        L.orc_saastamoinen_delay_m.restype = d
+        L.orc_saastamoinen_zenith_m.argtypes = [d, d, d, d, C.c_int]
+        L.orc_saastamoinen_zenith_m.restype = d
         L.orc_to_int_format.argtypes = [vp, sz, C.c_int, vp]
         L.orc_to_int_format.restype = C.c_int
         _lib = L
@@ -247,6 +254,24 @@ class OracleScenario:
         arr = (SatStatusPod * max(n, 1))()
         lib().orc_scenario_status(self._h, arr, n)
         return [arr[k] for k in range(n)]
+
+
+KLOBUCHAR_DEFAULT = ([0.1118e-7, 0.7451e-8, -0.5961e-7, -0.1192e-6], [0.1167e6, -0.4267e5, -0.2621e6, 0.1311e6])
+
+
+def klobuchar_delay_s(el_rad, az_rad, lat_rad, lon_rad, gps_t, alpha=None, beta=None) -> float:
+    """KlobucharModel::delay_seconds (environment/ionosphere.rs:46-108), default_broadcast coefficients unless given"""
+    a = np.asarray(alpha if alpha is not None else KLOBUCHAR_DEFAULT[0], np.float64)
+    b = np.asarray(beta if beta is not None else KLOBUCHAR_DEFAULT[1], np.float64)
+    return float(lib().orc_klobuchar_delay_s(_ptr(a), _ptr(b), el_rad, az_rad, lat_rad, lon_rad, gps_t))
+
+
+def saastamoinen(height_m=0.0, temperature_k=288.15, pressure_hpa=1013.25, relative_humidity=0.5):
+    """SaastamoinenModel (environment/troposphere.rs): returns (zenith dry m, zenith wet m, slant-delay function of el_rad)"""
+    L = lib()
+    args = (height_m, temperature_k, pressure_hpa, relative_humidity)
+    return (float(L.orc_saastamoinen_zenith_m(*args, 0)), float(L.orc_saastamoinen_zenith_m(*args, 1)),
+            lambda el: float(L.orc_saastamoinen_delay_m(*args, el)))
 
 
 INT_FORMATS = {"ci16": (2, np.int16), "ci8": (3, np.int8), "cu8": (4, np.uint8)}

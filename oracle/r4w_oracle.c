@@ -510,9 +510,6 @@ int orc_scenario_new(const orc_scenario_cfg* cfg, orc_scenario** out)
         const orc_sat_cfg* sc = &s->sats[k];
         int rc = emitter_init(&s->emitters[k], sc->signal, sc->prn, sc->plane, sc->slot, sc->tx_power_dbw, sc->nav_data);
         if (rc) { orc_scenario_free(s); return rc; }
-        /* environment models are only needed when the YAML gives no override (scenario.rs:430-439) */
-        if (!(sc->has & ORC_HAS_IONO) && cfg->environment.ionosphere_enabled) { orc_scenario_free(s); return -3; }
-        if (!(sc->has & ORC_HAS_TROPO) && cfg->environment.troposphere_enabled) { orc_scenario_free(s); return -3; }
     }
     s->rng_state = cfg->output.seed > 1 ? cfg->output.seed : 1;
 
@@ -694,9 +691,19 @@ static void phase1(const orc_scenario* s, size_t n, orc_block_params* w)
             d0 = doppler; d1 = doppler;
         } else { d0 = orbital_doppler_start; d1 = orbital_doppler_end; }
 
-        /* without an override and with the model disabled, status_at reports 0 m (satellite_emitter.rs:165-178) */
-        double iono_delay_m = (sc->has & ORC_HAS_IONO) ? sc->iono_delay_m : 0.0;
-        double tropo_delay_m = (sc->has & ORC_HAS_TROPO) ? sc->tropo_delay_m : 0.0;
+        /* scenario.rs:430-439: the override, else SatelliteEmitter::status_at(t_start) (satellite_emitter.rs:165-178): the
+         * models see the ORBIT's look angle (not the YAML elevation override) and GPS seconds of week; 0 m when disabled */
+        const orc_environment_cfg* ev = &s->cfg.environment;
+        const double DEG = 3.14159265358979323846 / 180.0;
+        double iono_delay_m = 0.0, tropo_delay_m = 0.0;
+        if (sc->has & ORC_HAS_IONO) iono_delay_m = sc->iono_delay_m;
+        else if (ev->ionosphere_enabled)
+            iono_delay_m = orc_klobuchar_delay_s(ev->klobuchar_alpha, ev->klobuchar_beta, la_el * DEG, la_az * DEG, rx_lla.lat_deg * DEG,
+                                                 rx_lla.lon_deg * DEG, fmod(t_start, 604800.0)) * SPEED_OF_LIGHT;
+        if (sc->has & ORC_HAS_TROPO) tropo_delay_m = sc->tropo_delay_m;
+        else if (ev->troposphere_enabled)
+            tropo_delay_m = orc_saastamoinen_delay_m(ev->tropo_height_m, ev->tropo_temperature_k, ev->tropo_pressure_hpa,
+                                                     ev->tropo_relative_humidity, la_el * DEG);
         double cn0_dbhz;
         if (sc->has & ORC_HAS_CN0) cn0_dbhz = sc->cn0_dbhz;
         else {
@@ -869,8 +876,20 @@ int orc_scenario_status(const orc_scenario* s, orc_sat_status* out, size_t cap)
                                                    s->cfg.receiver.antenna_beamwidth_deg, o->elevation_deg);
         if (sc->has & ORC_HAS_CN0) o->cn0_dbhz = sc->cn0_dbhz;
         else o->cn0_dbhz = sc->tx_power_dbw - orc_fspl_db(o->range_m, carrier_hz) + o->antenna_gain_dbi + 204.0;
-        o->iono_delay_m = (sc->has & ORC_HAS_IONO) ? sc->iono_delay_m : 0.0;
-        o->tropo_delay_m = (sc->has & ORC_HAS_TROPO) ? sc->tropo_delay_m : 0.0;
+        /* scenario.rs:604-613: override, else the emitter's models at the ORBIT's look angle (status_at, t) */
+        {
+            const orc_environment_cfg* ev = &s->cfg.environment;
+            const double DEG = 3.14159265358979323846 / 180.0;
+            o->iono_delay_m = 0.0; o->tropo_delay_m = 0.0;
+            if (sc->has & ORC_HAS_IONO) o->iono_delay_m = sc->iono_delay_m;
+            else if (ev->ionosphere_enabled)
+                o->iono_delay_m = orc_klobuchar_delay_s(ev->klobuchar_alpha, ev->klobuchar_beta, el * DEG, az * DEG, rx_lla->lat_deg * DEG,
+                                                        rx_lla->lon_deg * DEG, fmod(t, 604800.0)) * SPEED_OF_LIGHT;
+            if (sc->has & ORC_HAS_TROPO) o->tropo_delay_m = sc->tropo_delay_m;
+            else if (ev->troposphere_enabled)
+                o->tropo_delay_m = orc_saastamoinen_delay_m(ev->tropo_height_m, ev->tropo_temperature_k, ev->tropo_pressure_hpa,
+                                                            ev->tropo_relative_humidity, el * DEG);
+        }
         o->visible = o->elevation_deg > 0.0;
         o->clock_correction_s = 0.0;
     }
@@ -1000,6 +1019,56 @@ int64_t orc_pcps_acquire_grid(const orc_pcps* p, const orc_c64* input, size_t n_
 }
 
 /* IqFormat::Cf32 write_sample, core/io/format.rs:197-200: `(x as f32)` rounds to nearest even */
+/* ---- environment models ------------------------------------------------------------------------------ */
+/* KlobucharModel::delay_seconds, environment/ionosphere.rs:46-108 (f64::powi(n) = repeated squaring) */
+double orc_klobuchar_delay_s(const double alpha[4], const double beta[4], double elevation_rad, double azimuth_rad,
+                             double user_lat_rad, double user_lon_rad, double gps_time_s)
+{
+    const double PI = 3.14159265358979323846;
+    double el_sc = elevation_rad / PI, az_sc = azimuth_rad / PI, lat_sc = user_lat_rad / PI, lon_sc = user_lon_rad / PI;
+    double psi = 0.0137 / (el_sc + 0.11) - 0.022;
+    double lat_ipp = lat_sc + psi * cos(az_sc) * PI;          /* sic: cos of the semicircle value, times pi (:60) */
+    if (lat_ipp > 0.416) lat_ipp = 0.416;
+    if (lat_ipp < -0.416) lat_ipp = -0.416;
+    double lon_ipp = lon_sc + psi * sin(az_sc * PI) / cos(lat_ipp * PI);
+    double lat_mag = lat_ipp + 0.064 * cos(lon_ipp - 1.617);  /* sic: no pi here (:72) */
+    double t_local = 43200.0 * lon_ipp + gps_time_s;
+    t_local = fmod(t_local, 86400.0);
+    double d = 0.53 - el_sc;
+    double f_obl = 1.0 + 16.0 * (d * d * d);
+    double lm2 = lat_mag * lat_mag, lm3 = lm2 * lat_mag;
+    double amp = alpha[0] + alpha[1] * lat_mag + alpha[2] * lm2 + alpha[3] * lm3;
+    if (!(amp > 0.0)) amp = 0.0;                              /* f64::max(0.0) */
+    double per = beta[0] + beta[1] * lat_mag + beta[2] * lm2 + beta[3] * lm3;
+    if (!(per > 72000.0)) per = 72000.0;
+    double x = 2.0 * PI * (t_local - 50400.0) / per;
+    if (fabs(x) < 1.57) {
+        double x2 = x * x, x4 = x2 * x2;
+        return f_obl * (5.0e-9 + amp * (1.0 - x * x / 2.0 + x4 / 24.0));
+    }
+    return f_obl * 5.0e-9;
+}
+
+/* SaastamoinenModel, environment/troposphere.rs:52-97.  component: 0 = hydrostatic, 1 = wet, 2 = total */
+double orc_saastamoinen_zenith_m(double height_m, double temperature_k, double pressure_hpa, double relative_humidity, int component)
+{
+    const double PI = 3.14159265358979323846;
+    double h_rad = height_m * (PI / 180.0);                   /* sic: height_m.to_radians() (:54) */
+    double dry = 0.002277 * pressure_hpa / (1.0 - 0.00266 * cos(2.0 * h_rad) - 0.00028 * height_m / 1000.0);
+    double t_c = temperature_k - 273.15;
+    double es = 6.1121 * exp((18.678 - t_c / 234.5) * t_c / (257.14 + t_c));
+    double e = relative_humidity * es;
+    double wet = 0.002277 * (1255.0 / temperature_k + 0.05) * e;
+    return component == 0 ? dry : component == 1 ? wet : dry + wet;
+}
+double orc_saastamoinen_delay_m(double height_m, double temperature_k, double pressure_hpa, double relative_humidity, double elevation_rad)
+{
+    double el = elevation_rad > 0.05 ? elevation_rad : 0.05;  /* f64::max(0.05) */
+    double sin_el = sin(el);
+    double mapping = 1.0 / (sin_el + 0.00143 / tan(0.0455 + sin_el));
+    return orc_saastamoinen_zenith_m(height_m, temperature_k, pressure_hpa, relative_humidity, 2) * mapping;
+}
+
 /* IqFormat::write_sample for the integer sink formats (core/io/format.rs:203-222): f64 scale, clamp, Rust `as`
  * (truncation toward zero; NaN -> 0).  fmt: 2 = ci16, 3 = ci8, 4 = cu8 (the r4wb_fmt numbering). */
 static double orc_clamp(double x, double lo, double hi) { return x < lo ? lo : (x > hi ? hi : x); }

@@ -52,6 +52,8 @@ typedef struct orc_receiver_cfg {
 
 typedef struct orc_environment_cfg {
     uint32_t ionosphere_enabled, troposphere_enabled, multipath_enabled, multipath_preset;
+    double klobuchar_alpha[4], klobuchar_beta[4];   /* KlobucharModel, environment/ionosphere.rs:18-33 */
+    double tropo_height_m, tropo_temperature_k, tropo_pressure_hpa, tropo_relative_humidity;   /* SaastamoinenModel, troposphere.rs:14-36 */
 } orc_environment_cfg;
 
 typedef struct orc_output_cfg {
@@ -158,6 +160,12 @@ int64_t orc_pcps_acquire_grid(const orc_pcps* p, const orc_c64* input, size_t n_
 
 /* IqFormat::Cf32 sink cast, core/io/format.rs:197-200 */
 void orc_to_cf32(const orc_c64* in, size_t n, float* out_interleaved);
+/* KlobucharModel::delay_seconds, environment/ionosphere.rs:46-108 */
+double orc_klobuchar_delay_s(const double alpha[4], const double beta[4], double elevation_rad, double azimuth_rad,
+                             double user_lat_rad, double user_lon_rad, double gps_time_s);
+/* SaastamoinenModel::delay_meters (zenith hydrostatic + wet, Chao mapping), environment/troposphere.rs:52-97 */
+double orc_saastamoinen_delay_m(double height_m, double temperature_k, double pressure_hpa, double relative_humidity, double elevation_rad);
+double orc_saastamoinen_zenith_m(double height_m, double temperature_k, double pressure_hpa, double relative_humidity, int component);
 /* core/io/format.rs:203-222, fmt 2 = ci16, 3 = ci8, 4 = cu8; out = interleaved (re, im) integers */
 int orc_to_int_format(const orc_c64* in, size_t n, int fmt, void* out);
 

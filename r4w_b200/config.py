@@ -63,7 +63,10 @@ class ReceiverCfgPod(C.Structure):
 
 class EnvironmentCfgPod(C.Structure):
     _fields_ = [("ionosphere_enabled", C.c_uint32), ("troposphere_enabled", C.c_uint32),
-                ("multipath_enabled", C.c_uint32), ("multipath_preset", C.c_uint32)]
+                ("multipath_enabled", C.c_uint32), ("multipath_preset", C.c_uint32),
+                ("klobuchar_alpha", C.c_double * 4), ("klobuchar_beta", C.c_double * 4),
+                ("tropo_height_m", C.c_double), ("tropo_temperature_k", C.c_double), ("tropo_pressure_hpa", C.c_double),
+                ("tropo_relative_humidity", C.c_double)]
 
 
 class OutputCfgPod(C.Structure):
@@ -243,6 +246,18 @@ class GnssScenarioConfig:
         e = self.environment
         pod.environment.ionosphere_enabled = 1 if (e.ionosphere_enabled and e.ionosphere_source != "Disabled") else 0
         pod.environment.troposphere_enabled = 1 if e.troposphere_enabled else 0
+        # KlobucharModel::default_broadcast (environment/ionosphere.rs:28-33) / SaastamoinenModel::standard_atmosphere
+        # (troposphere.rs:28-35) when the YAML leaves the model null (scenario.rs:141-150)
+        im = e.ionosphere_model or {}
+        alpha = [float(v) for v in im.get("alpha", [0.1118e-7, 0.7451e-8, -0.5961e-7, -0.1192e-6])]
+        beta = [float(v) for v in im.get("beta", [0.1167e6, -0.4267e5, -0.2621e6, 0.1311e6])]
+        pod.environment.klobuchar_alpha = (C.c_double * 4)(*alpha)
+        pod.environment.klobuchar_beta = (C.c_double * 4)(*beta)
+        tm = e.troposphere_model or {}
+        pod.environment.tropo_height_m = float(tm.get("height_m", 0.0))
+        pod.environment.tropo_temperature_k = float(tm.get("temperature_k", 288.15))
+        pod.environment.tropo_pressure_hpa = float(tm.get("pressure_hpa", 1013.25))
+        pod.environment.tropo_relative_humidity = float(tm.get("relative_humidity", 0.5))
         pod.environment.multipath_enabled = 1 if e.multipath_enabled else 0
         pod.environment.multipath_preset = MULTIPATH_PRESETS.index(e.multipath_preset) if e.multipath_preset in MULTIPATH_PRESETS else 0
         o = self.output

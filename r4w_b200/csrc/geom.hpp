@@ -70,6 +70,45 @@ R4WB_HD double los_rate(const Vec3& op, const Vec3& ov, const Vec3& tp, const Ve
     return rv.x * (d.x / r) + rv.y * (d.y / r) + rv.z * (d.z / r);
 }
 
+// KlobucharModel::delay_seconds, gnss/environment/ionosphere.rs:46-108 (semicircle quirks of the reference kept as written)
+R4WB_HD double klobuchar_delay_s(const double* alpha, const double* beta, double elevation_rad, double azimuth_rad, double lat_rad,
+                                 double lon_rad, double gps_time_s)
+{
+    const double el_sc = elevation_rad / kPi, az_sc = azimuth_rad / kPi, lat_sc = lat_rad / kPi, lon_sc = lon_rad / kPi;
+    const double psi = 0.0137 / (el_sc + 0.11) - 0.022;
+    double lat_ipp = lat_sc + psi * cos(az_sc) * kPi;
+    if (lat_ipp > 0.416) lat_ipp = 0.416;
+    if (lat_ipp < -0.416) lat_ipp = -0.416;
+    const double lon_ipp = lon_sc + psi * sin(az_sc * kPi) / cos(lat_ipp * kPi);
+    const double lat_mag = lat_ipp + 0.064 * cos(lon_ipp - 1.617);
+    const double t_local = fmod(43200.0 * lon_ipp + gps_time_s, 86400.0);
+    const double d = 0.53 - el_sc;
+    const double f_obl = 1.0 + 16.0 * (d * d * d);
+    const double lm2 = lat_mag * lat_mag, lm3 = lm2 * lat_mag;
+    double amp = alpha[0] + alpha[1] * lat_mag + alpha[2] * lm2 + alpha[3] * lm3;
+    if (!(amp > 0.0)) amp = 0.0;
+    double per = beta[0] + beta[1] * lat_mag + beta[2] * lm2 + beta[3] * lm3;
+    if (!(per > 72000.0)) per = 72000.0;
+    const double x = 2.0 * kPi * (t_local - 50400.0) / per;
+    if (fabs(x) < 1.57) {
+        const double x2 = x * x;
+        return f_obl * (5.0e-9 + amp * (1.0 - x * x / 2.0 + (x2 * x2) / 24.0));
+    }
+    return f_obl * 5.0e-9;
+}
+
+// SaastamoinenModel::delay_meters, gnss/environment/troposphere.rs:52-97
+R4WB_HD double saastamoinen_delay_m(double height_m, double temperature_k, double pressure_hpa, double relative_humidity, double elevation_rad)
+{
+    const double dry = 0.002277 * pressure_hpa / (1.0 - 0.00266 * cos(2.0 * (height_m * kDeg)) - 0.00028 * height_m / 1000.0);
+    const double t_c = temperature_k - 273.15;
+    const double es = 6.1121 * exp((18.678 - t_c / 234.5) * t_c / (257.14 + t_c));
+    const double wet = 0.002277 * (1255.0 / temperature_k + 0.05) * (relative_humidity * es);
+    const double el = elevation_rad > 0.05 ? elevation_rad : 0.05;
+    const double sin_el = sin(el);
+    return (dry + wet) * (1.0 / (sin_el + 0.00143 / tan(0.0455 + sin_el)));
+}
+
 R4WB_HD double fspl_db(double dist_m, double freq_hz)
 {
     if (dist_m <= 0.0 || freq_hz <= 0.0) return 0.0;

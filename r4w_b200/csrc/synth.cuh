@@ -54,6 +54,9 @@ struct ScenConst {
     RxModel rx;
     uint32_t antenna;
     double ant_peak, ant_bw, elev_mask_deg;
+    uint32_t iono_enabled, tropo_enabled;    // Klobuchar / Saastamoinen models for satellites without an override
+    double klob_alpha[4], klob_beta[4];
+    double tropo_height_m, tropo_temperature_k, tropo_pressure_hpa, tropo_relative_humidity;
     double chip_rate, spc;          // spc = (8 fs) / chip_rate exactly as the reference computes it (f64)
     uint64_t ratA, ratB;            // (8 fs) / chip_rate == ratA / ratB as exact integers
     double delta;                   // spc == (ratA/ratB) * (1 + delta)

@@ -139,7 +139,7 @@ R4WB_HD void fill_block_sat(const ScenConst& sc, const SatConst& st, const Phase
     const double t_end = t_start + (double)n / fs;
     const double elapsed_end = elapsed + (double)n / fs;
 
-    double la_el = 0.0, la_range = 0.0, dop_s = 0.0, dop_e = 0.0;
+    double la_el = 0.0, la_az = 0.0, la_range = 0.0, dop_s = 0.0, dop_e = 0.0, rx_lat = 0.0, rx_lon = 0.0;
     if (st.needs_orbit) {
         const RxState rx = rx_at(sc.rx, elapsed);
         Vec3 ps, vs, pe, ve;
@@ -147,7 +147,9 @@ R4WB_HD void fill_block_sat(const ScenConst& sc, const SatConst& st, const Phase
         orbit_state(st.orbit, t_end, pe, ve);
         const Look la = look_from(rx.pos, rx.lla, ps);
         la_el = la.elevation_deg;
+        la_az = la.azimuth_deg;
         la_range = la.range_m;
+        rx_lat = rx.lla.lat_deg; rx_lon = rx.lla.lon_deg;
         dop_s = -los_rate(rx.pos, rx.vel, ps, vs) * st.carrier_hz / kC;
         dop_e = -los_rate(rx.pos, rx.vel, pe, ve) * st.carrier_hz / kC;
     }
@@ -177,8 +179,17 @@ R4WB_HD void fill_block_sat(const ScenConst& sc, const SatConst& st, const Phase
         ds = de = -st.range_rate_mps * st.carrier_hz / kC;
     } else { ds = dop_s; de = dop_e; }
 
-    const double iono_s = ((st.has & R4WB_HAS_IONO) ? st.iono_delay_m : 0.0) / kC;
-    const double tropo_s = ((st.has & R4WB_HAS_TROPO) ? st.tropo_delay_m : 0.0) / kC;
+    // scenario.rs:430-439: the override, else SatelliteEmitter::status_at(t_start) (satellite_emitter.rs:165-178): the models see
+    // the ORBIT's look angle (not the YAML elevation) and GPS seconds of week; 0 m when the model is disabled
+    double iono_m = 0.0, tropo_m = 0.0;
+    if (st.has & R4WB_HAS_IONO) iono_m = st.iono_delay_m;
+    else if (sc.iono_enabled)
+        iono_m = klobuchar_delay_s(sc.klob_alpha, sc.klob_beta, la_el * kDeg, la_az * kDeg, rx_lat * kDeg, rx_lon * kDeg, fmod(t_start, 604800.0)) * kC;
+    if (st.has & R4WB_HAS_TROPO) tropo_m = st.tropo_delay_m;
+    else if (sc.tropo_enabled)
+        tropo_m = saastamoinen_delay_m(sc.tropo_height_m, sc.tropo_temperature_k, sc.tropo_pressure_hpa, sc.tropo_relative_humidity, la_el * kDeg);
+    const double iono_s = iono_m / kC;
+    const double tropo_s = tropo_m / kC;
     double cn0 = st.cn0_dbhz;
     if (!(st.has & R4WB_HAS_CN0))
         cn0 = st.tx_power_dbw - fspl_db(range_m, st.carrier_hz) + antenna_gain_dbi(sc.antenna, sc.ant_peak, sc.ant_bw, elevation) + 204.0;

@@ -100,6 +100,11 @@ ScenarioModel::ScenarioModel(const r4wb_scenario_cfg& c_in) : cfg(c_in)
     sc.ant_bw = cfg.receiver.antenna_beamwidth_deg;
     sc.elev_mask_deg = cfg.receiver.elevation_mask_deg;
     sc.seed = oc.seed;
+    sc.iono_enabled = cfg.environment.ionosphere_enabled ? 1u : 0u;
+    sc.tropo_enabled = cfg.environment.troposphere_enabled ? 1u : 0u;
+    for (int i = 0; i < 4; ++i) { sc.klob_alpha[i] = cfg.environment.klobuchar_alpha[i]; sc.klob_beta[i] = cfg.environment.klobuchar_beta[i]; }
+    sc.tropo_height_m = cfg.environment.tropo_height_m; sc.tropo_temperature_k = cfg.environment.tropo_temperature_k;
+    sc.tropo_pressure_hpa = cfg.environment.tropo_pressure_hpa; sc.tropo_relative_humidity = cfg.environment.tropo_relative_humidity;
 
     // receiver model (scenario.rs:160-183, 320-353)
     RxModel& rx = sc.rx;
@@ -154,10 +159,6 @@ ScenarioModel::ScenarioModel(const r4wb_scenario_cfg& c_in) : cfg(c_in)
             fail(R4WB_ERR_NOT_SUPPORTED, "satellite %u: only GalileoE1C is implemented on the GPU path", k);
         if (c.prn < 1 || c.prn > 50) fail(R4WB_ERR_INVALID_PARAMETER, "Galileo PRN must be 1-50, got %u", c.prn);
         if (c.plane >= 3 || c.slot >= 10) fail(R4WB_ERR_INVALID_PARAMETER, "Galileo plane 0-2 / slot 0-9");
-        if (!(c.has & R4WB_HAS_IONO) && cfg.environment.ionosphere_enabled)
-            fail(R4WB_ERR_NOT_SUPPORTED, "satellite %u: Klobuchar model needed (no iono_delay_m override)", k);
-        if (!(c.has & R4WB_HAS_TROPO) && cfg.environment.troposphere_enabled)
-            fail(R4WB_ERR_NOT_SUPPORTED, "satellite %u: Saastamoinen model needed (no tropo_delay_m override)", k);
         SatConst& s = sats[k];
         std::memset(&s, 0, sizeof s);
         s.orbit = nominal_orbit(c.signal, c.plane, c.slot);
@@ -170,7 +171,9 @@ ScenarioModel::ScenarioModel(const r4wb_scenario_cfg& c_in) : cfg(c_in)
         s.iono_delay_m = c.iono_delay_m; s.tropo_delay_m = c.tropo_delay_m;
         const bool doppler_from_orbit = c.orbital_dynamics || (!(c.has & R4WB_HAS_DOPPLER) && !(c.has & R4WB_HAS_RANGE_RATE));
         const bool range_from_orbit = c.orbital_dynamics || !(c.has & R4WB_HAS_RANGE);
-        s.needs_orbit = (doppler_from_orbit || range_from_orbit || !(c.has & R4WB_HAS_ELEVATION)) ? 1u : 0u;
+        const bool env_from_orbit = (!(c.has & R4WB_HAS_IONO) && cfg.environment.ionosphere_enabled) ||
+                                    (!(c.has & R4WB_HAS_TROPO) && cfg.environment.troposphere_enabled);   // the models need the look angle
+        s.needs_orbit = (doppler_from_orbit || range_from_orbit || env_from_orbit || !(c.has & R4WB_HAS_ELEVATION)) ? 1u : 0u;
         const bool const_doppler = !c.orbital_dynamics && (((c.has & R4WB_HAS_DOPPLER) && !(c.has & R4WB_HAS_DOPPLER_RATE)) ||
                                                             (!(c.has & R4WB_HAS_DOPPLER) && (c.has & R4WB_HAS_RANGE_RATE)));
         s.static_phase = (const_doppler && (c.has & R4WB_HAS_ELEVATION)) ? 1u : 0u;
@@ -294,8 +297,16 @@ void ScenarioModel::status(uint64_t current, r4wb_sat_status* out, uint32_t cap,
         o.antenna_gain_dbi = antenna_gain_dbi(sc.antenna, sc.ant_peak, sc.ant_bw, o.elevation_deg);
         o.cn0_dbhz = (c.has & R4WB_HAS_CN0) ? c.cn0_dbhz
                                             : c.tx_power_dbw - fspl_db(o.range_m, sats[k].carrier_hz) + o.antenna_gain_dbi + 204.0;
-        o.iono_delay_m = (c.has & R4WB_HAS_IONO) ? c.iono_delay_m : 0.0;
-        o.tropo_delay_m = (c.has & R4WB_HAS_TROPO) ? c.tropo_delay_m : 0.0;
+        // scenario.rs:604-613: override, else the emitter's models at the ORBIT's look angle
+        o.iono_delay_m = 0.0; o.tropo_delay_m = 0.0;
+        if (c.has & R4WB_HAS_IONO) o.iono_delay_m = c.iono_delay_m;
+        else if (sc.iono_enabled)
+            o.iono_delay_m = klobuchar_delay_s(sc.klob_alpha, sc.klob_beta, la.elevation_deg * kDeg, la.azimuth_deg * kDeg, rx_lla.lat_deg * kDeg,
+                                               rx_lla.lon_deg * kDeg, std::fmod(t, 604800.0)) * kC;
+        if (c.has & R4WB_HAS_TROPO) o.tropo_delay_m = c.tropo_delay_m;
+        else if (sc.tropo_enabled)
+            o.tropo_delay_m = saastamoinen_delay_m(sc.tropo_height_m, sc.tropo_temperature_k, sc.tropo_pressure_hpa, sc.tropo_relative_humidity,
+                                                   la.elevation_deg * kDeg);
         o.visible = o.elevation_deg > 0.0 ? 1 : 0;
         o.clock_correction_s = 0.0;
     }

@@ -43,7 +43,7 @@ def test_error_enum_matches_r4w_ffi():
 def test_pod_layouts_match_header():
     from r4w_b200 import config as K
     assert C.sizeof(K.SatCfgPod) == 96 and C.sizeof(K.LlaPod) == 24
-    assert C.sizeof(K.OutputCfgPod) == 48 and C.sizeof(K.EnvironmentCfgPod) == 16
+    assert C.sizeof(K.OutputCfgPod) == 48 and C.sizeof(K.EnvironmentCfgPod) == 16 + 12 * 8
     assert C.sizeof(K.AcqResultPod) == 48 and C.sizeof(K.SatStatusPod) == 88
     assert C.sizeof(K.ReceiverCfgPod) == 24 + 8 + 5 * 8 + 48 + 8 + 8
 

@@ -29,6 +29,8 @@ def _relrms(a, b):
     ("e1c_8prn_60s_cn34_orbital", 0, 11000),                  # orbital Doppler / range per block
     ("e1c_8prn_60s_cn34_orbital", 2_500_000, 6000),
     ("e1c_prn3_20s_30ms_delay", 0, 11000),
+    ("e1c_60s_cn34_effects", 0, 11000),                       # Klobuchar + Saastamoinen delays evaluated per block
+    ("e1c_8prn_60s_mach3_ftwayne_berne", 149_995_000, 10000), # receiver trajectory (Mach 3)
 ])
 def test_synthesis_replay_matches_oracle(oracle, emu, name, first, n):
     cfg = _cfg(name)

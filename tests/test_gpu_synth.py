@@ -33,6 +33,10 @@ def _relrms(a, b):
     ("e1c_8prn_60s_cn34_orbital", 7_500_000, 10000),
     ("e1c_8prn_20s_cn34_orbital", 50_000_000, 5000),
     ("e1c_prn3_20s_30ms_delay", 0, 20000),
+    ("e1c_60s_cn34_effects", 100_000_000, 15000),             # Klobuchar + Saastamoinen per block
+    ("e1c_8prn_60s_mach3_ftwayne_berne", 200_000_000, 15000), # receiver trajectory
+    ("e1c_60s_clean", 0, 10000),
+    ("e1c_60s_cn34", 299_990_000, 10000),
 ])
 def test_clean_iq_matches_oracle(gpu, oracle, name, first, n):
     cfg = _cfg(name)

@@ -228,3 +228,26 @@ def test_integer_sink_formats(oracle):
     assert ci8.tolist() == [[63, -31], [127, 127], [-127, -127], [127, -128], [0, 126], [0, 0]]
     cu8 = oracle.to_int_format(x, "cu8")
     assert cu8.tolist() == [[191, 95], [255, 255], [0, 0], [255, 0], [127, 254], [127, 127]]
+
+
+def test_klobuchar_and_saastamoinen_models(oracle):
+    """the reference's own model tests: ionosphere.rs:130-172 (test_klobuchar_delay_range, test_low_elevation_more_delay),
+    troposphere.rs:106-148 (test_zenith_delay_standard, test_hydrostatic_dominates, test_low_elevation_more_delay,
+    test_altitude_reduces_delay with at_altitude's lapse-rate atmosphere)"""
+    rad = np.deg2rad
+    d = oracle.klobuchar_delay_s(rad(45.0), 0.0, rad(40.0), rad(-75.0), 43200.0)
+    assert 0.5 < d * 299_792_458.0 < 50.0
+    assert oracle.klobuchar_delay_s(rad(10.0), 0.0, rad(40.0), rad(-75.0), 43200.0) > \
+        oracle.klobuchar_delay_s(rad(80.0), 0.0, rad(40.0), rad(-75.0), 43200.0)
+    dry, wet, slant = oracle.saastamoinen()
+    assert 2.0 < dry + wet < 2.8 and dry > wet
+    assert slant(rad(10.0)) > slant(rad(80.0))
+
+    def at_altitude(h):          # SaastamoinenModel::at_altitude, troposphere.rs:38-49
+        return oracle.saastamoinen(h, 288.15 - 0.0065 * h, 1013.25 * (1.0 - 0.0065 * h / 288.15) ** 5.2561, 0.5)
+    lo, hi = at_altitude(0.0), at_altitude(2000.0)
+    assert lo[0] + lo[1] > hi[0] + hi[1]
+    # independent numpy evaluation of the two formulas at one point
+    el = rad(30.0)
+    m = 1.0 / (np.sin(el) + 0.00143 / np.tan(0.0455 + np.sin(el)))
+    assert slant(el) == pytest.approx((dry + wet) * m, rel=1e-14)
