@@ -206,6 +206,8 @@ r4wb_error r4wb_scenario_status(const r4wb_scenario* h, r4wb_sat_status* out, ui
 /* GalileoE1CodeGenerator::new_e1b / new_e1c + unpack_code, gnss/prn.rs:268-292, galileo_e1_codes.rs:17-25.
  * channel 0 = E1B, 1 = E1C; out[4092] = +1/-1. */
 r4wb_error r4wb_e1_code(uint32_t channel, uint8_t prn, int8_t* out, uint64_t cap);
+/* GpsCaCodeGenerator::generate_code, gnss/prn.rs:34-162; PRN 1-32; out[1023] = +1/-1 */
+r4wb_error r4wb_gps_ca_code(uint8_t prn, int8_t* out, uint64_t cap);
 /* GalileoE1CodeGenerator::secondary_code, galileo_e1_codes.rs:29-31; out[25] */
 r4wb_error r4wb_e1c_secondary(int8_t* out, uint64_t cap);
 /* Sampled local replica code[floor(i*1.023e6/fs) mod 4092] * BOC(1,1) for i in [0, n) (no secondary code) —

@@ -6,4 +6,4 @@ from .config import (GnssScenarioConfig, SatelliteConfig, ReceiverConfig, Enviro
 from ._lib import R4wB200Error, init, kernel_launches, device_count, version, build  # noqa: F401
 from .scenario import GnssScenario, SatelliteStatus  # noqa: F401
 from .acquisition import (PcpsAcquisition, AcquisitionResult, AcquisitionGrid, e1_code, e1c_secondary,  # noqa: F401
-                          e1c_replica)
+                          e1c_replica, gps_ca_code)

@@ -179,6 +179,13 @@ def e1_code(channel: int, prn: int) -> np.ndarray:
     return out
 
 
+def gps_ca_code(prn: int) -> np.ndarray:
+    """1023 chips (+1/-1) of the GPS L1 C/A Gold code, PRN 1-32 (GpsCaCodeGenerator, gnss/prn.rs:34-162)."""
+    out = np.zeros(1023, np.int8)
+    _lib.check(_lib.lib().r4wb_gps_ca_code(int(prn), out.ctypes.data_as(C.c_void_p), out.size))
+    return out
+
+
 def e1c_secondary() -> np.ndarray:
     out = np.zeros(25, np.int8)
     _lib.check(_lib.lib().r4wb_e1c_secondary(out.ctypes.data_as(C.c_void_p), out.size))

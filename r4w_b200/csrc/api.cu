@@ -15,6 +15,7 @@ static thread_local std::string t_error;
 
 cudaStream_t current_stream() { return t_stream; }
 void e1_code_chips(uint32_t channel, uint32_t prn, int8_t* out);
+void gps_ca_code_chips(uint32_t prn, int8_t* out);
 
 template <typename F>
 static r4wb_error guard(F&& body)
@@ -165,6 +166,13 @@ r4wb_error r4wb_e1_code(uint32_t channel, uint8_t prn, int8_t* out, uint64_t cap
     if (cap < 4092) { t_error = "code buffer needs 4092 entries"; return R4WB_ERR_INVALID_SIZE; }
     e1_code_chips(channel, prn, out);
     return R4WB_OK;
+}
+
+r4wb_error r4wb_gps_ca_code(uint8_t prn, int8_t* out, uint64_t cap)
+{
+    if (!out) { t_error = "out is NULL"; return R4WB_ERR_NULL_POINTER; }
+    if (cap < 1023) { t_error = "code buffer needs 1023 entries"; return R4WB_ERR_INVALID_SIZE; }
+    return guard([&] { gps_ca_code_chips(prn, out); });
 }
 
 r4wb_error r4wb_e1c_secondary(int8_t* out, uint64_t cap)

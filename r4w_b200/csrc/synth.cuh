@@ -18,7 +18,7 @@ constexpr int kTBits = 24;            // fraction bits of "oversamples since bou
 constexpr int kMaxSats = 64;
 constexpr int kMaxSegments = 512;
 constexpr int kYStride = 81;          // boundary-age classes per sign pattern (odd: spreads patterns over banks)
-constexpr int kPerBits = 2 * kCodeLen;   // half-chips of one primary-code period
+constexpr int kPerBits = 2 * kCodeLen;   // half-chips of one Galileo E1 primary-code period (the longest supported)
 constexpr int kPerWords = 260;        // 8184 sign bits + 64 wrap-around bits, padded to a multiple of 4 words
 constexpr int kSynthThreads = 256;
 
@@ -31,8 +31,24 @@ struct PhaseSegment {
     double step;
 };
 
+// Code structure of one (virtual) satellite: what SatelliteEmitter::generate_baseband_iq modulates on the real axis
+// (gnss/satellite_emitter.rs:264-343) besides the primary code: BOC(1,1) or not, and a sign per primary-code epoch
+// (E1C: the 25-chip secondary code; E1B / GPS L1 C/A with nav_data: the reference's deterministic nav bit
+// `(epoch / periods_per_bit + prn) % 2`, :286-292).  All supported signals chip at 1.023 MHz.
+struct SatCode {
+    uint64_t epoch_bits;    // bit e (e < epoch_period) set: primary-code epoch e of the cycle is inverted
+    uint32_t code_len;      // chips per primary-code period (4092 Galileo E1, 1023 GPS L1 C/A)
+    uint32_t per_len;       // half-chips per primary-code period = 2 * code_len
+    uint32_t epoch_period;  // epochs after which epoch_bits repeats (25, 2, 40 or 1)
+    uint32_t hc_mod;        // per_len * epoch_period: half-chip positions are kept modulo this (<= 204 600)
+    uint32_t has_boc;       // BOC(1,1): second half of every chip inverted
+    uint32_t pad;
+};
+
 // per-satellite constants (device copy lives in Scenario::d_sat)
 struct SatConst {
+    SatCode code;
+    double amp_scale;            // +1; the two halves of a GalileoE1OS satellite carry +-1/sqrt(2) (satellite_emitter.rs:316-321)
     Orbit orbit;
     double carrier_hz;
     uint32_t has;
@@ -116,6 +132,7 @@ struct SynthArgs {
     const BlockHdr* hdr;       // [n_tab_blocks]
     const TileRec* tiles;      // [n_tab_blocks][tiles_per_block][n_sats]
     const uint32_t* perbits;   // [n_sats][kPerWords] half-chip signs of one primary-code period (code x BOC(1,1)), bit=1 -> -1
+    const SatCode* satcode;    // [n_sats]
     const float* taps;         // [64] h[k] (f32), [63] = 0
     const float* etab;         // [64] E[d] = sum_{k<=d} h[k]  (E[62] = E[63] = 1)
     const float* ytab;         // [32][kYStride] collapsed-FIR outputs per (sign pattern, boundary-age class)
@@ -151,6 +168,8 @@ struct ScenarioModel {
     std::vector<PhaseSegment> segments;
     std::vector<uint32_t> codebits;     // [n_sats][128] packed primary code (bit=1 -> chip -1)
     std::vector<uint32_t> perbits;      // [n_sats][kPerWords]
+    std::vector<SatCode> satcode;       // [n_sats]
+    std::vector<uint32_t> cfg_index;    // virtual satellite -> index into cfg_sats (GalileoE1OS expands to two)
     float taps_f[64];
     float etab_f[64];
     std::vector<float> ytab;            // [32][kYStride]
@@ -223,6 +242,7 @@ private:
     DevBuf<SatConst> d_sat_;
     DevBuf<PhaseSegment> d_segments_;
     DevBuf<uint32_t> d_perbits_;
+    DevBuf<SatCode> d_satcode_;
     DevBuf<float> d_taps_, d_etab_, d_ytab_;
     DevBuf<uint8_t> d_clslut_;
     DevBuf<BlockSat> d_tab_, d_seq_tab_;

@@ -23,6 +23,7 @@ Scenario::Scenario(const r4wb_scenario_cfg& cfg) : md_(cfg)
     R4WB_CUDA(cudaMemcpyAsync(d_sat_.reserve(std::max<size_t>(1, sats.size())), sats.data(), sats.size() * sizeof(SatConst), cudaMemcpyHostToDevice, st));
     R4WB_CUDA(cudaMemcpyAsync(d_segments_.reserve(md_.segments.size()), md_.segments.data(), md_.segments.size() * sizeof(PhaseSegment), cudaMemcpyHostToDevice, st));
     R4WB_CUDA(cudaMemcpyAsync(d_perbits_.reserve(md_.perbits.size()), md_.perbits.data(), md_.perbits.size() * 4, cudaMemcpyHostToDevice, st));
+    R4WB_CUDA(cudaMemcpyAsync(d_satcode_.reserve(md_.satcode.size()), md_.satcode.data(), md_.satcode.size() * sizeof(SatCode), cudaMemcpyHostToDevice, st));
     R4WB_CUDA(cudaMemcpyAsync(d_ytab_.reserve(md_.ytab.size()), md_.ytab.data(), md_.ytab.size() * 4, cudaMemcpyHostToDevice, st));
     R4WB_CUDA(cudaMemcpyAsync(d_taps_.reserve(64), md_.taps_f, sizeof md_.taps_f, cudaMemcpyHostToDevice, st));
     R4WB_CUDA(cudaMemcpyAsync(d_etab_.reserve(64), md_.etab_f, sizeof md_.etab_f, cudaMemcpyHostToDevice, st));
@@ -79,7 +80,7 @@ SynthArgs Scenario::base_args(const BlockSat* tab, const BlockHdr* hdr, uint64_t
 {
     const ScenConst& sc = md_.sc;
     SynthArgs a{};
-    a.tab = tab; a.hdr = hdr; a.perbits = d_perbits_.p; a.taps = d_taps_.p; a.etab = d_etab_.p; a.ytab = d_ytab_.p; a.clslut = d_clslut_.p; a.lut_den = sc.lut_den;
+    a.tab = tab; a.hdr = hdr; a.perbits = d_perbits_.p; a.satcode = d_satcode_.p; a.taps = d_taps_.p; a.etab = d_etab_.p; a.ytab = d_ytab_.p; a.clslut = d_clslut_.p; a.lut_den = sc.lut_den;
     const uint32_t tile = (uint32_t)synth_tile_samples(md_.tile_k);
     a.tiles_per_block = (uint32_t)((max_block_n + tile - 1) / tile);
     a.n_sats = sc.n_sats; a.nw64 = md_.nw64; a.flags = sc.flags;

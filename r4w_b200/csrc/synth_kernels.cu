@@ -97,7 +97,7 @@ __global__ void k_tile_params(SynthArgs a, uint32_t tb_begin, uint32_t tb_count,
     for (int i = 0; i < 8; ++i) {
         float y = 0.0f;
         if (chunk == 0 && (r.ts.flags & 9u) == 9u && (uint32_t)i < hd.n)
-            y = fir_block_start(row[s], a.tab, a.perbits + (size_t)s * kPerWords, a.taps, a.etab, i, KK);
+            y = fir_block_start(row[s], a.tab, a.perbits + (size_t)s * kPerWords, a.taps, a.etab, i, KK, a.satcode[s]);
         r.yfix[i] = y;
     }
     out[((size_t)tb * a.tiles_per_block + chunk) * a.n_sats + s] = r;
@@ -238,7 +238,7 @@ __global__ void __launch_bounds__(kThreads, K <= 5 ? 3 : 2) k_synth(SynthArgs a)
         // half-chip sign words: bit n of word w <-> half-chip hb + 32 w + n
         for (uint32_t k = tid; k < a.n_sats * (a.nw64 + 1); k += kThreads) {
             const uint32_t s = k / (a.nw64 + 1), w = k - s * (a.nw64 + 1);
-            sm.w32[k] = sign_word(sm.per + s * kPerWords, sm.trec[s].ts.hb, w);
+            sm.w32[k] = sign_word(sm.per + s * kPerWords, sm.trec[s].ts.hb, w, a.satcode[s]);
         }
         __syncthreads();
         for (uint32_t k = tid; k < a.n_sats * a.nw64; k += kThreads) {
@@ -254,7 +254,7 @@ __global__ void __launch_bounds__(kThreads, K <= 5 ? 3 : 2) k_synth(SynthArgs a)
         for (uint32_t s = 0; s < a.n_sats; ++s) {
             const TileSat ts = sm.trec[s].ts;
             if (!(ts.flags & 1u)) continue;
-            const SlowCtx slow{row + s, a.tab, sm.per + s * kPerWords, sm.taps};
+            const SlowCtx slow{row + s, a.tab, sm.per + s * kPerWords, sm.taps, a.satcode + s};
             sat_accumulate<K>(ts, KK, sm.t64 + s * a.nw64, sm.ytab, sm.clslut, sm.trec[s].yfix, slow, tid, i_begin, i_end, ar, ai, nullptr);
         }
 

@@ -198,8 +198,9 @@ R4WB_HD void fill_block_sat(const ScenConst& sc, const SatConst& st, const Phase
     // code phase of the block (satellite_emitter.rs:228-242)
     const double total_delay_s = add_rn(add_rn(div_rn(range_m, kC), iono_s), tropo_s);
     const double chips_delay = mul_rn(total_delay_s, sc.chip_rate);
-    const double phase0 = fmod(chips_delay, (double)kCodeLen);
-    const double eq = div_rn(chips_delay, (double)kCodeLen);
+    const SatCode& cd = st.code;
+    const double phase0 = fmod(chips_delay, (double)cd.code_len);
+    const double eq = div_rn(chips_delay, (double)cd.code_len);
     const uint64_t e0 = eq > 0.0 ? (uint64_t)eq : 0ull;
 
     // fixed-point half-chip position of the block's first oversample: exact rational part + f64 corrections
@@ -211,11 +212,12 @@ R4WB_HD void fill_block_sat(const ScenConst& sc, const SatConst& st, const Phase
     const double chips_exact = (double)ci + (double)cr / (double)sc.ratA;
     const double corr_chips = -chips_exact * (sc.delta / (1.0 + sc.delta));
     const long long corrfx = llrint(corr_chips * 140737488355328.0 /* 2^47 */);
-    const uint64_t hc_int = ((e0 % kSecLen) * (uint64_t)(2 * kCodeLen) + 2ull * (ci % (uint64_t)(kCodeLen * kSecLen))) % kHalfChipsPerSec;
+    const uint64_t hc_int = ((e0 % cd.epoch_period) * (uint64_t)cd.per_len + 2ull * (ci % ((uint64_t)cd.code_len * cd.epoch_period))) % cd.hc_mod;
+    const __int128 umod = (__int128)((uint64_t)cd.hc_mod << kFracBits);
     const uint64_t p0fx = (uint64_t)(phase0 * 140737488355328.0);
     __int128 Uw = ((__int128)hc_int << kFracBits) + (__int128)p0fx + (__int128)fracfx + (__int128)corrfx;
-    while (Uw < 0) Uw += (__int128)kUMod;
-    while (Uw >= (__int128)kUMod) Uw -= (__int128)kUMod;
+    while (Uw < 0) Uw += umod;
+    while (Uw >= umod) Uw -= umod;
     const uint64_t U = (uint64_t)Uw;
 
     // ambiguity band: the reference's cf = fl(phase0 + fl(g/spc)) is within ulp(cf) chips of the real value
@@ -261,7 +263,7 @@ R4WB_HD void fill_block_sat(const ScenConst& sc, const SatConst& st, const Phase
     }
 
     o.U = U; o.phi = phi; o.f = f; o.df = df; o.phase0 = phase0; o.G = G; o.n = n; o.e0 = (uint32_t)e0;
-    o.amp = (float)amp; o.flags = flags; o.prev = -1; o.eps46 = (uint32_t)e46; o.eps_t = (uint32_t)et; o.pad = 0;
+    o.amp = (float)(amp * st.amp_scale); o.flags = flags; o.prev = -1; o.eps46 = (uint32_t)e46; o.eps_t = (uint32_t)et; o.pad = 0;
 }
 
 // phase advance of one block (cycles 0.64, wrapping): sum_{i<n} (f + i*df)
@@ -382,58 +384,58 @@ R4WB_HD TileSat tile_sat(const BlockSat& b, const BlockSat* __restrict__ tab, ui
 }
 
 // sign bit (1 <=> -1) of half-chip hc in [0, 204600): primary code x BOC(1,1) from the period table, x secondary code
-R4WB_HD uint32_t halfchip_sign(const uint32_t* __restrict__ per, uint32_t hc)
+R4WB_HD uint32_t halfchip_sign(const uint32_t* __restrict__ per, uint32_t hc, const SatCode& cd)
 {
-    const uint32_t e = hc / (uint32_t)kPerBits, p = hc - e * (uint32_t)kPerBits;
-    return ((per[p >> 5] >> (p & 31u)) ^ (kSecBits >> e)) & 1u;
+    const uint32_t e = hc / cd.per_len, p = hc - e * cd.per_len;
+    return ((per[p >> 5] >> (p & 31u)) ^ (uint32_t)(cd.epoch_bits >> e)) & 1u;
 }
 R4WB_HD uint32_t code_bit(const uint32_t* __restrict__ per, uint32_t c) { return (per[c >> 4] >> ((2u * c) & 31u)) & 1u; }
 
 // word w of the per-tile half-chip sign table: bit n <-> half-chip hb + 32 w + n (1 <=> -1)
-R4WB_HD uint32_t sign_word(const uint32_t* __restrict__ per, uint32_t hb, uint32_t w)
+R4WB_HD uint32_t sign_word(const uint32_t* __restrict__ per, uint32_t hb, uint32_t w, const SatCode& cd)
 {
     int64_t hh = (int64_t)(int32_t)hb + 32 * (int64_t)w;
-    hh %= (int64_t)kHalfChipsPerSec;
-    if (hh < 0) hh += kHalfChipsPerSec;
-    const uint32_t h = (uint32_t)hh, e = h / (uint32_t)kPerBits, p = h - e * (uint32_t)kPerBits;
+    hh %= (int64_t)cd.hc_mod;
+    if (hh < 0) hh += cd.hc_mod;
+    const uint32_t h = (uint32_t)hh, e = h / cd.per_len, p = h - e * cd.per_len;
     const uint32_t bits = funnel_r(per[p >> 5], per[(p >> 5) + 1], p);       // the table repeats its first 64 bits at the end
-    const uint32_t e1 = e + 1 == (uint32_t)kSecLen ? 0u : e + 1;
-    const uint32_t se = 0u - ((kSecBits >> e) & 1u), se1 = 0u - ((kSecBits >> e1) & 1u);
-    const uint32_t nlow = (uint32_t)kPerBits - p;                             // bits of this word inside epoch e
+    const uint32_t e1 = e + 1 == cd.epoch_period ? 0u : e + 1;
+    const uint32_t se = 0u - ((uint32_t)(cd.epoch_bits >> e) & 1u), se1 = 0u - ((uint32_t)(cd.epoch_bits >> e1) & 1u);
+    const uint32_t nlow = cd.per_len - p;                                     // bits of this word inside epoch e
     const uint32_t lowmask = nlow >= 32u ? 0xffffffffu : ((1u << nlow) - 1u);
     return bits ^ ((se & lowmask) | (se1 & ~lowmask));
 }
 
 // sign bit (1 <=> -1) of oversample q (>= 0, relative to the block start) of block entry bs;
 // evaluates the reference expression literally when q is within the rounding band of a boundary.
-R4WB_HD_NOINLINE uint32_t chip_sign_exact(const BlockSat& bs, long long q, const uint32_t* __restrict__ per, double spc)
+R4WB_HD_NOINLINE uint32_t chip_sign_exact(const BlockSat& bs, long long q, const uint32_t* __restrict__ per, double spc, const SatCode& cd)
 {
     const double g = (double)(bs.G + (uint64_t)q);
     const double cf = add_rn(bs.phase0, div_rn(g, spc));                       // satellite_emitter.rs:268
-    const double cm = fmod(cf, (double)kCodeLen);
+    const double cm = fmod(cf, (double)cd.code_len);
     uint32_t c = cm > 0.0 ? (uint32_t)cm : 0u;                                   // :269
-    if (c > (uint32_t)(kCodeLen - 1)) c = kCodeLen - 1;                          // :281
+    if (c > cd.code_len - 1u) c = cd.code_len - 1u;                              // :281
     const double cp = cf - floor(cf);                                            // :270
-    const double eq = div_rn(cf, (double)kCodeLen);
+    const double eq = div_rn(cf, (double)cd.code_len);
     const uint64_t ep = (uint64_t)bs.e0 + (eq > 0.0 ? (uint64_t)eq : 0ull);      // :278
-    const uint32_t boc = fmod(mul_rn(cp, 2.0), 2.0) < 1.0 ? 0u : 1u;             // :303-305
-    return code_bit(per, c) ^ boc ^ ((kSecBits >> (uint32_t)(ep % kSecLen)) & 1u);
+    const uint32_t boc = (cd.has_boc && !(fmod(mul_rn(cp, 2.0), 2.0) < 1.0)) ? 1u : 0u;   // :303-305
+    return code_bit(per, c) ^ boc ^ ((uint32_t)(cd.epoch_bits >> (uint32_t)(ep % cd.epoch_period)) & 1u);
 }
 
-R4WB_HD uint32_t chip_sign(const BlockSat& bs, long long q, const uint32_t* __restrict__ per, uint64_t delta46, double spc)
+R4WB_HD uint32_t chip_sign(const BlockSat& bs, long long q, const uint32_t* __restrict__ per, uint64_t delta46, double spc, const SatCode& cd)
 {
     const uint64_t u = bs.U + (uint64_t)q * delta46;
     const uint64_t fr = u & kFracMask;
-    if (fr < bs.eps46 || fr > kFracMask - bs.eps46) return chip_sign_exact(bs, q, per, spc);
+    if (fr < bs.eps46 || fr > kFracMask - bs.eps46) return chip_sign_exact(bs, q, per, spc, cd);
     uint32_t h = (uint32_t)(u >> kFracBits);
-    if (h >= kHalfChipsPerSec) h -= kHalfChipsPerSec;
-    return halfchip_sign(per, h);
+    if (h >= cd.hc_mod) h -= cd.hc_mod;
+    return halfchip_sign(per, h, cd);
 }
 
 // direct 63-tap evaluation of output sample i of block entry `cur` (history from `prev`): the reference's own loop
 // (fir.rs:392-409 over satellite_emitter.rs:264-330), used for samples whose window touches an ambiguous boundary.
 R4WB_HD_NOINLINE float fir_direct(const BlockSat& cur, const BlockSat* __restrict__ tab, const uint32_t* __restrict__ per,
-                                  const float* __restrict__ taps, int i, uint64_t delta46, double spc)
+                                  const float* __restrict__ taps, int i, uint64_t delta46, double spc, const SatCode& cd)
 {
     float acc = 0.0f;
     const long long g = (long long)kOversample * i;
@@ -441,13 +443,13 @@ R4WB_HD_NOINLINE float fir_direct(const BlockSat& cur, const BlockSat* __restric
         long long q = g - k;
         uint32_t sgn;
         if (q >= 0) {
-            sgn = chip_sign(cur, q, per, delta46, spc);
+            sgn = chip_sign(cur, q, per, delta46, spc, cd);
         } else {
             if (cur.prev < 0) continue;                      // zero-initialised delay line
             const BlockSat& pb = tab[cur.prev];
             q += (long long)kOversample * pb.n;
             if (q < 0) continue;                             // history older than one block: not modelled
-            sgn = chip_sign(pb, q, per, delta46, spc);
+            sgn = chip_sign(pb, q, per, delta46, spc, cd);
         }
         acc += sgn ? -taps[k] : taps[k];
     }
@@ -472,7 +474,8 @@ R4WB_HD void boundary_ages(uint32_t frac32, const SynthK& K, uint32_t d[4])
 
 // Collapsed FIR restricted to taps k <= g of the window whose newest oversample sits at half-chip position u of the
 // code sequence: s_4 E[g] + sum_j (s_j - s_{j+1}) E[min(d_j, g)]   (g = 62 gives the whole window)
-R4WB_HD float fir_collapsed_upto(uint64_t u, uint32_t g, const uint32_t* __restrict__ per, const float* __restrict__ etab, const SynthK& K)
+R4WB_HD float fir_collapsed_upto(uint64_t u, uint32_t g, const uint32_t* __restrict__ per, const float* __restrict__ etab, const SynthK& K,
+                                 const SatCode& cd)
 {
     uint32_t h = (uint32_t)(u >> kFracBits);
     uint32_t d[4];
@@ -480,8 +483,8 @@ R4WB_HD float fir_collapsed_upto(uint64_t u, uint32_t g, const uint32_t* __restr
     float s[kJ + 1];
 #pragma unroll
     for (int j = 0; j <= kJ; ++j) {
-        const uint32_t hc = (h + kHalfChipsPerSec - (uint32_t)j) % kHalfChipsPerSec;
-        s[j] = halfchip_sign(per, hc) ? -1.0f : 1.0f;
+        const uint32_t hc = (h + cd.hc_mod - (uint32_t)j) % cd.hc_mod;
+        s[j] = halfchip_sign(per, hc, cd) ? -1.0f : 1.0f;
     }
     float y = s[kJ] * etab[g];
 #pragma unroll
@@ -494,16 +497,16 @@ R4WB_HD float fir_collapsed_upto(uint64_t u, uint32_t g, const uint32_t* __restr
 // blocks, core/filters/fir.rs:392-409 + gnss/scenario.rs:486-489).  Both parts in collapsed form; the literal 63-tap
 // loop only when either block has a boundary inside the f64 rounding band.
 R4WB_HD float fir_block_start(const BlockSat& cur, const BlockSat* __restrict__ tab, const uint32_t* __restrict__ per,
-                              const float* __restrict__ taps, const float* __restrict__ etab, int i, const SynthK& K)
+                              const float* __restrict__ taps, const float* __restrict__ etab, int i, const SynthK& K, const SatCode& cd)
 {
     const bool has_prev = cur.prev >= 0;
-    if ((cur.flags & 2u) || (has_prev && (tab[cur.prev].flags & 2u))) return fir_direct(cur, tab, per, taps, i, K.delta46, K.spc);
+    if ((cur.flags & 2u) || (has_prev && (tab[cur.prev].flags & 2u))) return fir_direct(cur, tab, per, taps, i, K.delta46, K.spc, cd);
     const uint32_t g = (uint32_t)(kOversample * i);
-    float y = fir_collapsed_upto(cur.U + (uint64_t)g * K.delta46, g, per, etab, K);
+    float y = fir_collapsed_upto(cur.U + (uint64_t)g * K.delta46, g, per, etab, K, cd);
     if (has_prev) {
         const BlockSat& pb = tab[cur.prev];
         const uint64_t up = pb.U + ((uint64_t)kOversample * pb.n + g) * K.delta46;   // the old sequence, continued
-        y += fir_collapsed_upto(up, kTaps - 1, per, etab, K) - fir_collapsed_upto(up, g, per, etab, K);
+        y += fir_collapsed_upto(up, kTaps - 1, per, etab, K, cd) - fir_collapsed_upto(up, g, per, etab, K, cd);
     }
     return y;
 }
@@ -525,6 +528,7 @@ struct SlowCtx {
     const BlockSat* tab;           // whole table (history links)
     const uint32_t* per;           // the satellite's period table
     const float* taps;
+    const SatCode* code;           // the satellite's code structure
 };
 
 // One satellite's contribution to the NK sample pairs thread `tid` owns in a tile: pair k = samples
@@ -597,11 +601,11 @@ R4WB_HD void sat_accumulate_t(const TileSat& ts, const SynthK& K, const uint2* _
             const bool amb_b = ((tb0 + e) & m) < 2 * e || ((tb1 + e) & m) < 2 * e || ((tb2 + e) & m) < 2 * e || ((tb3 + e) & m) < 2 * e;
             const uint32_t ia = ia0 + 2u * (uint32_t)kSynthThreads * (uint32_t)k;
             if (amb_a && ia < i_end) {
-                y.x = fir_direct(*slow.cur, slow.tab, slow.per, slow.taps, (int)ia, K.delta46, K.spc);
+                y.x = fir_direct(*slow.cur, slow.tab, slow.per, slow.taps, (int)ia, K.delta46, K.spc, *slow.code);
                 if (n_ambiguous) ++*n_ambiguous;
             }
             if (amb_b && ia + 1 < i_end) {
-                y.y = fir_direct(*slow.cur, slow.tab, slow.per, slow.taps, (int)ia + 1, K.delta46, K.spc);
+                y.y = fir_direct(*slow.cur, slow.tab, slow.per, slow.taps, (int)ia + 1, K.delta46, K.spc, *slow.code);
                 if (n_ambiguous) ++*n_ambiguous;
             }
         }

@@ -27,6 +27,27 @@ void e1_code_chips(uint32_t channel, uint32_t prn, int8_t* out)
     for (uint32_t i = 0; i < (uint32_t)kCodeLen; ++i) out[i] = e1_sign_bit(channel, prn, i) ? -1 : 1;
 }
 
+// GPS L1 C/A Gold code (gnss/prn.rs:34-162: G1 = x^10 + x^3 + 1, G2 = x^10 + x^9 + x^8 + x^6 + x^3 + x^2 + 1, both all-ones,
+// G2 read through the PRN's two phase-selector taps; bit 0 -> chip +1)
+static const uint8_t kGpsCaTaps[32][2] = {{2, 6}, {3, 7}, {4, 8}, {5, 9}, {1, 9}, {2, 10}, {1, 8}, {2, 9}, {3, 10}, {2, 3}, {3, 4},
+                                          {5, 6}, {6, 7}, {7, 8}, {8, 9}, {9, 10}, {1, 4}, {2, 5}, {3, 6}, {4, 7}, {5, 8}, {6, 9},
+                                          {1, 3}, {4, 6}, {5, 7}, {6, 8}, {7, 9}, {8, 10}, {1, 6}, {2, 7}, {3, 8}, {4, 9}};
+void gps_ca_code_chips(uint32_t prn, int8_t* out /*[1023]*/)
+{
+    if (prn < 1 || prn > 32) fail(R4WB_ERR_INVALID_PARAMETER, "GPS PRN must be 1-32, got %u", prn);
+    uint32_t g1[11], g2[11];                     // stage i = 1..10
+    for (int i = 1; i <= 10; ++i) g1[i] = g2[i] = 1u;
+    const int ta = kGpsCaTaps[prn - 1][0], tb = kGpsCaTaps[prn - 1][1];
+    for (int n = 0; n < 1023; ++n) {
+        const uint32_t bit = g1[10] ^ g2[ta] ^ g2[tb];
+        out[n] = bit ? -1 : 1;
+        const uint32_t f1 = g1[3] ^ g1[10];
+        const uint32_t f2 = g2[2] ^ g2[3] ^ g2[6] ^ g2[8] ^ g2[9] ^ g2[10];
+        for (int i = 10; i > 1; --i) { g1[i] = g1[i - 1]; g2[i] = g2[i - 1]; }
+        g1[1] = f1; g2[1] = f2;
+    }
+}
+
 // 63-tap Blackman windowed-sinc low-pass, unity DC gain (core/filters/fir.rs:458-499, windows.rs:137-151)
 static void design_lowpass(double cutoff_hz, double rate_hz, double* h /*[63]*/)
 {
@@ -150,17 +171,40 @@ ScenarioModel::ScenarioModel(const r4wb_scenario_cfg& c_in) : cfg(c_in)
 
     // satellites
     const RxState rx0 = rx_at(rx, 0.0);
-    sats.resize(cfg.n_sats);
-    codebits.assign((size_t)std::max(1u, cfg.n_sats) * 128, 0u);
-    perbits.assign((size_t)std::max(1u, cfg.n_sats) * kPerWords, 0u);
+    // Virtual satellites: one per configured satellite, two for GalileoE1OS ((e1b - e1c) / sqrt 2 is a sum of two binary
+    // sequences with the same delay and Doppler, and the FIR is linear; satellite_emitter.rs:307-321)
+    struct Virt { uint32_t cfg; uint32_t kind; double scale; };      // kind: 0 GPS C/A, 1 E1B, 2 E1C
+    std::vector<Virt> virt;
     for (uint32_t k = 0; k < cfg.n_sats; ++k) {
         const r4wb_sat_cfg& c = cfg_sats[k];
-        if (c.signal != R4WB_SIG_GALILEO_E1C)
-            fail(R4WB_ERR_NOT_SUPPORTED, "satellite %u: only GalileoE1C is implemented on the GPU path", k);
-        if (c.prn < 1 || c.prn > 50) fail(R4WB_ERR_INVALID_PARAMETER, "Galileo PRN must be 1-50, got %u", c.prn);
-        if (c.plane >= 3 || c.slot >= 10) fail(R4WB_ERR_INVALID_PARAMETER, "Galileo plane 0-2 / slot 0-9");
+        const bool galileo = c.signal == R4WB_SIG_GALILEO_E1 || c.signal == R4WB_SIG_GALILEO_E1C || c.signal == R4WB_SIG_GALILEO_E1OS;
+        if (!galileo && c.signal != R4WB_SIG_GPS_L1CA)
+            fail(R4WB_ERR_NOT_SUPPORTED, "satellite %u: GPS L5 / GLONASS L1OF are not implemented on the GPU path", k);
+        if (galileo) {
+            if (c.prn < 1 || c.prn > 50) fail(R4WB_ERR_INVALID_PARAMETER, "Galileo PRN must be 1-50, got %u", c.prn);
+            if (c.plane >= 3 || c.slot >= 10) fail(R4WB_ERR_INVALID_PARAMETER, "Galileo plane 0-2 / slot 0-9");
+        } else {
+            if (c.prn < 1 || c.prn > 32) fail(R4WB_ERR_INVALID_PARAMETER, "GPS PRN must be 1-32, got %u", c.prn);
+            if (c.plane >= 6 || c.slot >= 6) fail(R4WB_ERR_INVALID_PARAMETER, "GPS plane 0-5 / slot 0-5");
+        }
+        if (c.signal == R4WB_SIG_GPS_L1CA) virt.push_back({k, 0u, 1.0});
+        else if (c.signal == R4WB_SIG_GALILEO_E1) virt.push_back({k, 1u, 1.0});
+        else if (c.signal == R4WB_SIG_GALILEO_E1C) virt.push_back({k, 2u, 1.0});
+        else { const double sc2 = 1.0 / std::sqrt(2.0); virt.push_back({k, 1u, sc2}); virt.push_back({k, 2u, -sc2}); }
+    }
+    if (virt.size() > (size_t)kMaxSats) fail(R4WB_ERR_NOT_SUPPORTED, "at most %d (virtual) satellites per scenario", kMaxSats);
+    sc.n_sats = (uint32_t)virt.size();
+    sats.resize(virt.size());
+    satcode.assign(std::max<size_t>(1, virt.size()), SatCode{});
+    cfg_index.assign(virt.size(), 0u);
+    codebits.assign(std::max<size_t>(1, virt.size()) * 128, 0u);
+    perbits.assign(std::max<size_t>(1, virt.size()) * kPerWords, 0u);
+    for (uint32_t k = 0; k < (uint32_t)virt.size(); ++k) {
+        const r4wb_sat_cfg& c = cfg_sats[virt[k].cfg];
+        cfg_index[k] = virt[k].cfg;
         SatConst& s = sats[k];
         std::memset(&s, 0, sizeof s);
+        s.amp_scale = virt[k].scale;
         s.orbit = nominal_orbit(c.signal, c.plane, c.slot);
         s.carrier_hz = 1575420000.0;
         s.has = c.has;
@@ -194,14 +238,32 @@ ScenarioModel::ScenarioModel(const r4wb_scenario_cfg& c_in) : cfg(c_in)
             segments.insert(segments.end(), segs.begin(), segs.end());
         }
         s.seg_count = (int32_t)segments.size() - s.seg_begin;
-        for (uint32_t i = 0; i < (uint32_t)kCodeLen; ++i)
-            codebits[(size_t)k * 128 + (i >> 5)] |= e1_sign_bit(1, c.prn, i) << (i & 31);
-        // half-chip signs of one primary-code period (code x BOC(1,1): second half of every chip inverted), followed by a
+
+        // code structure (satellite_emitter.rs:248-343)
+        SatCode& cd = s.code;
+        int8_t chips[kCodeLen];
+        if (virt[k].kind == 0) { gps_ca_code_chips(c.prn, chips); cd.code_len = 1023; cd.has_boc = 0; }
+        else { e1_code_chips(virt[k].kind == 1 ? 0u : 1u, c.prn, chips); cd.code_len = (uint32_t)kCodeLen; cd.has_boc = 1; }
+        cd.per_len = 2u * cd.code_len;
+        cd.epoch_period = 1; cd.epoch_bits = 0;
+        if (virt[k].kind == 2) {                              // E1C: 25-chip secondary code, one chip per 4 ms epoch
+            cd.epoch_period = (uint32_t)kSecLen; cd.epoch_bits = kSecBits;
+        } else if (c.nav_data) {                              // nav bit (bit_idx + prn) % 2, bit_idx = epoch / periods_per_bit (:286-292)
+            const uint32_t ppb = virt[k].kind == 0 ? 20u : 1u;   // 1 / (50 bps x 1 ms), 1 / (250 bps x 4 ms)
+            cd.epoch_period = 2u * ppb;
+            for (uint32_t e = 0; e < cd.epoch_period; ++e)
+                if (((e / ppb) + c.prn) % 2u != 0u) cd.epoch_bits |= 1ull << e;
+        }
+        cd.hc_mod = cd.per_len * cd.epoch_period;
+        satcode[k] = cd;
+        for (uint32_t i = 0; i < cd.code_len; ++i)
+            codebits[(size_t)k * 128 + (i >> 5)] |= (chips[i] < 0 ? 1u : 0u) << (i & 31);
+        // half-chip signs of one primary-code period (with BOC(1,1): second half of every chip inverted), followed by a
         // copy of its first 64 bits so a 32-bit window may start anywhere in the period
         uint32_t* per = perbits.data() + (size_t)k * kPerWords;
-        for (uint32_t n = 0; n < (uint32_t)kPerBits + 64u; ++n) {
-            const uint32_t hc = n % (uint32_t)kPerBits;
-            per[n >> 5] |= (e1_sign_bit(1, c.prn, hc >> 1) ^ (hc & 1u)) << (n & 31);
+        for (uint32_t n = 0; n < cd.per_len + 64u; ++n) {
+            const uint32_t hc = n % cd.per_len;
+            per[n >> 5] |= ((chips[hc >> 1] < 0 ? 1u : 0u) ^ (cd.has_boc ? (hc & 1u) : 0u)) << (n & 31);
         }
     }
     if (segments.empty()) segments.push_back(PhaseSegment{0, 0.0, 0.0});
@@ -277,14 +339,15 @@ ScenarioModel::ScenarioModel(const r4wb_scenario_cfg& c_in) : cfg(c_in)
 // GnssScenario::satellite_status (scenario.rs:564-633): static receiver position, zero receiver velocity
 void ScenarioModel::status(uint64_t current, r4wb_sat_status* out, uint32_t cap, uint32_t* n_out) const
 {
-    if (cap < sc.n_sats) fail(R4WB_ERR_INVALID_SIZE, "status buffer holds %u of %u satellites", cap, sc.n_sats);
+    if (cap < cfg.n_sats) fail(R4WB_ERR_INVALID_SIZE, "status buffer holds %u of %u satellites", cap, cfg.n_sats);
     const double t = sc.t0_gps + (double)current / sc.fs;
     const Lla rx_lla = sc.rx.position;
     const Vec3 rx_pos = ecef_of(rx_lla), zero{0.0, 0.0, 0.0};
-    for (uint32_t k = 0; k < sc.n_sats; ++k) {
+    for (uint32_t k = 0; k < cfg.n_sats; ++k) {      // configured satellites (a GalileoE1OS one is two virtual satellites)
         const r4wb_sat_cfg& c = cfg_sats[k];
         Vec3 sp, sv;
-        orbit_state(sats[k].orbit, t, sp, sv);
+        orbit_state(nominal_orbit(c.signal, c.plane, c.slot), t, sp, sv);
+        const double carrier_hz = 1575420000.0;
         const Look la = look_from(rx_pos, rx_lla, sp);
         r4wb_sat_status& o = out[k];
         std::memset(&o, 0, sizeof o);
@@ -293,10 +356,10 @@ void ScenarioModel::status(uint64_t current, r4wb_sat_status* out, uint32_t cap,
         o.elevation_deg = (c.has & R4WB_HAS_ELEVATION) ? c.elevation_deg : la.elevation_deg;
         o.azimuth_deg = (c.has & R4WB_HAS_AZIMUTH) ? c.azimuth_deg : la.azimuth_deg;
         o.range_rate_mps = (c.has & R4WB_HAS_RANGE_RATE) ? c.range_rate_mps : los_rate(rx_pos, zero, sp, sv);
-        o.doppler_hz = (c.has & R4WB_HAS_DOPPLER) ? c.doppler_hz : -o.range_rate_mps * sats[k].carrier_hz / kC;
+        o.doppler_hz = (c.has & R4WB_HAS_DOPPLER) ? c.doppler_hz : -o.range_rate_mps * carrier_hz / kC;
         o.antenna_gain_dbi = antenna_gain_dbi(sc.antenna, sc.ant_peak, sc.ant_bw, o.elevation_deg);
         o.cn0_dbhz = (c.has & R4WB_HAS_CN0) ? c.cn0_dbhz
-                                            : c.tx_power_dbw - fspl_db(o.range_m, sats[k].carrier_hz) + o.antenna_gain_dbi + 204.0;
+                                            : c.tx_power_dbw - fspl_db(o.range_m, carrier_hz) + o.antenna_gain_dbi + 204.0;
         // scenario.rs:604-613: override, else the emitter's models at the ORBIT's look angle
         o.iono_delay_m = 0.0; o.tropo_delay_m = 0.0;
         if (c.has & R4WB_HAS_IONO) o.iono_delay_m = c.iono_delay_m;
@@ -310,7 +373,7 @@ void ScenarioModel::status(uint64_t current, r4wb_sat_status* out, uint32_t cap,
         o.visible = o.elevation_deg > 0.0 ? 1 : 0;
         o.clock_correction_s = 0.0;
     }
-    if (n_out) *n_out = sc.n_sats;
+    if (n_out) *n_out = cfg.n_sats;
 }
 
 // ---------------------------------------------------------------------------------------------- sequential API

@@ -95,13 +95,13 @@ struct Emu {
                 for (uint32_t i = 0; i < 8; ++i) {
                     float y = 0.0f;
                     if (chunk == 0 && (tsat[s].flags & 9u) == 9u && i < hd.n)
-                        y = fir_block_start(row[s], tb_tab, md.perbits.data() + s * kPerWords, md.taps_f, md.etab_f, (int)i, KK);
+                        y = fir_block_start(row[s], tb_tab, md.perbits.data() + s * kPerWords, md.taps_f, md.etab_f, (int)i, KK, md.satcode[s]);
                     yfix[s * 8 + i] = y;
                 }
             }
             for (uint32_t k = 0; k < ns * (nw64 + 1); ++k) {
                 const uint32_t s = k / (nw64 + 1), w = k - s * (nw64 + 1);
-                w32[k] = sign_word(md.perbits.data() + s * kPerWords, tsat[s].hb, w);
+                w32[k] = sign_word(md.perbits.data() + s * kPerWords, tsat[s].hb, w, md.satcode[s]);
             }
             for (uint32_t k = 0; k < ns * nw64; ++k) {
                 const uint32_t s = k / nw64, w = k - s * nw64;
@@ -114,7 +114,7 @@ struct Emu {
                     if (only_sat >= 0 && (int)s != only_sat) continue;
                     const TileSat ts = tsat[s];
                     if (!(ts.flags & 1u)) continue;
-                    const SlowCtx slow{row + s, tb_tab, md.perbits.data() + s * kPerWords, md.taps_f};
+                    const SlowCtx slow{row + s, tb_tab, md.perbits.data() + s * kPerWords, md.taps_f, md.satcode.data() + s};
                     sat_accumulate<K>(ts, KK, t64.data() + s * nw64, md.ytab.data(), md.clslut.data(), yfix.data() + s * 8, slow, tid, i_begin, i_end, ar, ai,
                                       n_ambiguous);
                 }

@@ -97,3 +97,12 @@ def test_product_does_not_import_oracle():
                 text = open(os.path.join(dp, f)).read()
                 assert "from oracle" not in text and "import oracle" not in text and "libr4w_oracle" not in text, f
                 assert "r4w_oracle" not in text and "libr4w_emu" not in text, f
+
+
+def test_gps_ca_codes_match_oracle(L, oracle):
+    """the product's own Gold-code generator (synth_model.cpp) against the oracle's restatement of gnss/prn.rs:34-162"""
+    import r4w_b200 as R
+    for prn in range(1, 33):
+        assert np.array_equal(R.gps_ca_code(prn), oracle.gps_ca_code(prn))
+    with pytest.raises(R.R4wB200Error):
+        R.gps_ca_code(33)

@@ -187,3 +187,33 @@ def test_class_table_equals_arithmetic_classes(emu, monkeypatch):
     monkeypatch.setenv("R4WB_SYNTH_NO_LUT", "1")
     without = emu.EmuScenario(cfg, noise=False).generate_range(7_495_000, 12000)
     assert np.array_equal(with_table, without)
+
+
+def _signal_variant(signals):
+    """e1c_8prn_20s_clean with the first len(signals) satellites re-typed: (signal, prn, nav_data)"""
+    cfg = _cfg("e1c_8prn_20s_clean").copy()
+    cfg.satellites = cfg.satellites[: len(signals)]
+    for s, (sig, prn, nav) in zip(cfg.satellites, signals):
+        s.signal, s.prn, s.nav_data = sig, prn, nav
+        if sig == "GpsL1Ca":
+            s.plane, s.slot = min(s.plane, 5), min(s.slot, 5)
+    return cfg
+
+
+SIGNAL_CASES = {
+    "gps_l1ca": [("GpsL1Ca", 3, True), ("GpsL1Ca", 17, False), ("GpsL1Ca", 32, True)],       # BPSK, 1 ms code, 20 ms nav bits
+    "galileo_e1b": [("GalileoE1", 3, True), ("GalileoE1", 25, False)],                       # BOC(1,1), nav bit per 4 ms epoch
+    "galileo_e1os": [("GalileoE1OS", 8, True), ("GalileoE1OS", 2, False), ("GalileoE1C", 5, False)],   # (e1b - e1c) / sqrt 2
+    "mixed": [("GpsL1Ca", 5, True), ("GalileoE1", 11, True), ("GalileoE1C", 12, False), ("GalileoE1OS", 13, True)],
+}
+
+
+@pytest.mark.parametrize("case", sorted(SIGNAL_CASES))
+def test_other_signals_replay_matches_oracle(oracle, emu, case):
+    """the other emitter branches of generate_baseband_iq (satellite_emitter.rs:248-343) that chip at
+    1.023 MHz — GPS L1 C/A, Galileo E1B, the E1OS composite — through the same kernels (per-satellite code structure)"""
+    cfg = _signal_variant(SIGNAL_CASES[case])
+    for first, n in ((0, 11000), (24_995_000, 12000)):
+        got = emu.EmuScenario(cfg, noise=False).generate_range(first, n)
+        want = oracle.OracleScenario(cfg, noise=False).generate_range(first, n)
+        assert _relrms(got, want) <= TOL

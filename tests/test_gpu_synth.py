@@ -245,3 +245,35 @@ def test_integer_sink_formats_match_oracle(gpu, oracle, fmt, lsb):
             d = np.abs(got.astype(np.int64) - true.astype(np.int64))
             assert d.max() <= lsb and (d == 0).mean() >= floor
             assert np.abs(true.astype(np.int64)).max() < (32767 if fmt == "ci16" else 127 if fmt == "ci8" else 255)
+
+
+@pytest.mark.parametrize("case", ["gps_l1ca", "galileo_e1b", "galileo_e1os", "mixed"])
+def test_other_signals_match_oracle(gpu, oracle, case):
+    """GPS L1 C/A, Galileo E1B and the E1OS composite (satellite_emitter.rs:248-343) on the GPU path"""
+    from tests.test_emu_parity import SIGNAL_CASES, _signal_variant
+    cfg = _signal_variant(SIGNAL_CASES[case])
+    for first, n in ((0, 20000), (49_990_000, 15000)):
+        got = gpu.GnssScenario(cfg, noise=False).generate_range(first, n)
+        want = oracle.OracleScenario(cfg, noise=False).generate_range(first, n)
+        assert _relrms(got, want) <= TOL
+    # block-by-block API on the same scenario
+    g = gpu.GnssScenario(cfg, noise=False)
+    o = oracle.OracleScenario(cfg, noise=False)
+    for bs in (5000, 777, 5000):
+        assert _relrms(g.generate_block(bs), o.generate_block(bs)) <= TOL
+
+
+def test_gps_acquisition_on_gpu_scenario(gpu, oracle):
+    """synthesise GPS L1 C/A at 5 MHz, acquire with the sampled C/A replica (code_length 5000 -> fft_size 8192, the
+    in-shared-memory engine): indices identical to the oracle's acquire on the same samples"""
+    from tests.test_emu_parity import _signal_variant
+    cfg = _signal_variant([("GpsL1Ca", 7, False), ("GpsL1Ca", 19, False)])
+    x = gpu.GnssScenario(cfg, noise=True).generate_range(1_000_000, 5000)
+    acq = gpu.PcpsAcquisition(5000, 5e6).with_doppler_range(5000.0, 250.0)
+    oacq = oracle.OraclePcps(5000, 5e6).with_doppler_range(5000.0, 250.0)
+    idx = (np.arange(5000) * 1.023e6 / 5e6).astype(np.int64) % 1023
+    for prn in (7, 19, 4):
+        code = gpu.gps_ca_code(prn)[idx].astype(np.int8)
+        r = acq.acquire(x, code, prn)
+        o = oacq.acquire(x.astype(np.complex128), code, prn)
+        assert (r.code_phase, r.doppler_hz, r.detected) == (o.code_phase, o.doppler_hz, bool(o.detected))
