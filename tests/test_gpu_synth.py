@@ -184,7 +184,7 @@ def test_satellite_status_matches_oracle(gpu, oracle):
 
 def test_unsupported_inputs_fail_loudly(gpu):
     cfg = _cfg("e1c_prn3_20s_withdoppler")
-    bad = cfg.copy(); bad.satellites[0].signal = "GpsL1Ca"
+    bad = cfg.copy(); bad.satellites[0].signal = "GpsL5"
     with pytest.raises(gpu.R4wB200Error) as e:
         gpu.GnssScenario(bad)
     assert e.value.code == 7                    # NotSupported, never a silent CPU path
