@@ -199,6 +199,10 @@ r4wb_error r4wb_scenario_generate(r4wb_scenario* h, uint64_t first, uint64_t n, 
                                   r4wb_mem where, r4wb_fmt fmt);
 /* Sum of |s|^2 over the last generate / generate_block call (the CLI's avg-power line, main.rs:4494-4509) */
 r4wb_error r4wb_scenario_last_power_sum(const r4wb_scenario* h, double* power_sum);
+/* Which synthesis kernels rendered the bulk of the last generate call: 0 = k_synth (general), 1 = the period-resident
+ * kernels (constant-delay, constant-Doppler scenarios; R4WB_SYNTH_PERIODIC=0 in the environment disables them).
+ * Diagnostic for A/B parity tests; no counterpart in the reference. */
+uint32_t r4wb_scenario_last_path(const r4wb_scenario* h);
 /* GnssScenario::satellite_status, gnss/scenario.rs:564-633 */
 r4wb_error r4wb_scenario_status(const r4wb_scenario* h, r4wb_sat_status* out, uint32_t cap, uint32_t* n);
 

@@ -145,6 +145,8 @@ r4wb_error r4wb_scenario_last_power_sum(const r4wb_scenario* h, double* power_su
     return guard([&] { *power_sum = const_cast<r4wb_scenario*>(h)->impl.last_power_sum(); });
 }
 
+uint32_t r4wb_scenario_last_path(const r4wb_scenario* h) { return h ? h->impl.last_path() : 0u; }
+
 r4wb_error r4wb_scenario_status(const r4wb_scenario* h, r4wb_sat_status* out, uint32_t cap, uint32_t* n)
 {
     if (!h || !out) { t_error = "handle/out is NULL"; return R4WB_ERR_NULL_POINTER; }

@@ -222,13 +222,18 @@ public:
     // one reference block of min(n, remaining) samples at current_sample
     uint64_t generate_block(uint64_t n, void* dst, r4wb_mem where, r4wb_fmt fmt);
     double last_power_sum();
+    uint32_t last_path() const { return last_path_; }
     void status(r4wb_sat_status* out, uint32_t cap, uint32_t* n) const { md_.status(current_, out, cap, n); }
     // test hook: entry of canonical block `block`, satellite `sat` -> 12 doubles
     void debug_block(uint64_t block, uint32_t sat, double* out12);
 
 private:
     void launch_synth(const BlockSat* tab, const BlockHdr* hdr, const TileRec* tiles, uint32_t tb_begin, uint32_t tb_count,
-                      uint64_t out_first, uint64_t out_n, void* d_out, r4wb_fmt fmt, uint64_t max_block_n);
+                      uint64_t out_first, uint64_t out_n, void* d_out, r4wb_fmt fmt, uint64_t max_block_n, cudaStream_t st);
+    // samples [first, first + n) into device memory: period-resident kernels where the scenario allows, else k_synth
+    void render_device(uint64_t first, uint64_t n, void* d_out, r4wb_fmt fmt);
+    bool plan_periodic();                                                // once per block table
+    bool render_periodic(uint64_t first, uint64_t n, void* d_out);      // false: not applicable to this range
     SynthArgs base_args(const BlockSat* tab, const BlockHdr* hdr, uint64_t max_block_n) const;
     void build_tiles(const SynthArgs& a, uint32_t tb_begin, uint32_t tb_count, TileRec* out);
     void build_canonical_table(uint64_t blk_begin, uint64_t blk_end);   // fills d_tab_/d_hdr_ for [blk_begin, blk_end)
@@ -253,6 +258,15 @@ private:
     DevBuf<unsigned char> d_stage_;
     uint64_t tab_blk0_ = 0, tab_blk1_ = 0;   // canonical block range currently held by d_tab_
     bool tab_valid_ = false;
+
+    // period-resident path (synth_periodic.cu): plan + tables, valid for the block table they were derived from
+    struct PeriodicState;
+    PeriodicState* per_ = nullptr;
+    uint32_t last_path_ = 0;
+    DevBuf<unsigned char> d_stage2_;          // second staging buffer of the host-destination pipeline
+    cudaStream_t side_stream_ = nullptr;      // head / tail launches next to the periodic kernel; D2H copies
+    cudaEvent_t ev_fork_ = nullptr, ev_join_ = nullptr, ev_render_[2] = {nullptr, nullptr}, ev_copy_[2] = {nullptr, nullptr};
+    void ensure_side_stream();
 };
 
 }  // namespace r4wb

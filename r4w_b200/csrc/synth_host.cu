@@ -2,9 +2,11 @@
 // launches the prologue + synthesis kernels.  The host-only model lives in synth_model.cpp.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "synth_math.cuh"
+#include "synth_periodic.cuh"
 
 namespace r4wb {
 
@@ -14,6 +16,25 @@ int synth_max_blocks_per_sm(int K, r4wb_fmt fmt, size_t smem);
 void launch_block_params(const ScenConst&, const SatConst*, const PhaseSegment*, uint64_t, uint32_t, BlockSat*, BlockHdr*, cudaStream_t);
 void launch_phase_scan(const SatConst*, uint32_t, uint32_t, BlockSat*, cudaStream_t);
 void launch_tile_params(const SynthArgs& a, uint32_t tb_begin, uint32_t tb_count, uint32_t tile_samples, TileRec* out, cudaStream_t st);
+// launchers (synth_periodic.cu)
+void launch_static_check(const BlockSat*, const SatConst*, uint32_t nblk, uint32_t n_sats, uint64_t B, uint32_t* bad, cudaStream_t);
+void launch_period_tables(const PeriodTableArgs&, uint32_t ns_padded, cudaStream_t);
+void launch_period_phasors(const PeriodicArgs&, uint32_t ns_padded, uint64_t tab_blk1, float4* T, cudaStream_t);
+void launch_synth_periodic(const PeriodicArgs&, uint32_t ns_padded, uint32_t n_cands, cudaStream_t);
+uint32_t periodic_padded_sats(uint32_t n);
+
+struct Scenario::PeriodicState {
+    bool planned = false, ok = false, enabled = true;
+    uint64_t blk0 = 0, blk1 = 0;            // block table the plan belongs to
+    uint32_t L = 0, ns = 0, tile_len = 0, n_tiles = 0, n_cands = 0;
+    uint64_t k_ref = 0;
+    uint64_t T_k0 = 0;
+    uint32_t T_n = 0;
+    DevBuf<float> ys, yb;
+    DevBuf<PerSat> sat;
+    DevBuf<uint32_t> cands, counters;       // counters[0] = precondition violations, [1] = number of patch slots
+    DevBuf<float4> T;
+};
 
 Scenario::Scenario(const r4wb_scenario_cfg& cfg) : md_(cfg)
 {
@@ -33,7 +54,21 @@ Scenario::Scenario(const r4wb_scenario_cfg& cfg) : md_(cfg)
     R4WB_CUDA(cudaStreamSynchronize(st));
 }
 
-Scenario::~Scenario() {}
+Scenario::~Scenario()
+{
+    delete per_;
+    for (cudaEvent_t e : {ev_fork_, ev_join_, ev_render_[0], ev_render_[1], ev_copy_[0], ev_copy_[1]})
+        if (e) cudaEventDestroy(e);
+    if (side_stream_) cudaStreamDestroy(side_stream_);
+}
+
+void Scenario::ensure_side_stream()
+{
+    if (side_stream_) return;
+    R4WB_CUDA(cudaStreamCreateWithFlags(&side_stream_, cudaStreamNonBlocking));
+    for (cudaEvent_t* e : {&ev_fork_, &ev_join_, &ev_render_[0], &ev_render_[1], &ev_copy_[0], &ev_copy_[1]})
+        R4WB_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+}
 
 void Scenario::reset()
 {
@@ -52,6 +87,7 @@ void Scenario::build_canonical_table(uint64_t blk_begin, uint64_t blk_end)
     if (nblk > 0x7fffffffull / std::max(1u, sc.n_sats)) fail(R4WB_ERR_INVALID_SIZE, "too many blocks in one call");
     cudaStream_t st = current_stream();
     tab_valid_ = false;
+    if (per_) per_->planned = false;
     d_tab_.reserve(std::max<size_t>(1, (size_t)nblk * sc.n_sats));
     d_hdr_.reserve(std::max<size_t>(1, nblk));
     launch_block_params(sc, d_sat_.p, d_segments_.p, blk_begin, (uint32_t)nblk, d_tab_.p, d_hdr_.p, st);
@@ -97,7 +133,7 @@ void Scenario::build_tiles(const SynthArgs& a, uint32_t tb_begin, uint32_t tb_co
 }
 
 void Scenario::launch_synth(const BlockSat* tab, const BlockHdr* hdr, const TileRec* tiles, uint32_t tb_begin, uint32_t tb_count,
-                            uint64_t out_first, uint64_t out_n, void* d_out, r4wb_fmt fmt, uint64_t max_block_n)
+                            uint64_t out_first, uint64_t out_n, void* d_out, r4wb_fmt fmt, uint64_t max_block_n, cudaStream_t st)
 {
     SynthArgs a = base_args(tab, hdr, max_block_n);
     a.tiles = tiles;
@@ -117,7 +153,146 @@ void Scenario::launch_synth(const BlockSat* tab, const BlockHdr* hdr, const Tile
     const int per_sm = std::max(1, synth_max_blocks_per_sm(tile_k, fmt, smem));
     const uint64_t n_tiles = (uint64_t)tb_count * a.tiles_per_block;
     const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>(n_tiles, (uint64_t)sm_count * per_sm));
-    launch_synth_kernel(a, tile_k, fmt, grid, current_stream());
+    launch_synth_kernel(a, tile_k, fmt, grid, st);
+}
+
+static bool periodic_enabled()
+{
+    const char* e = std::getenv("R4WB_SYNTH_PERIODIC");      // read per plan so that tests can A/B inside one process
+    return !(e && e[0] == '0');
+}
+
+// Decide once per block table whether the period-resident kernels apply, and build their tables.
+bool Scenario::plan_periodic()
+{
+    if (!per_) per_ = new PeriodicState;
+    PeriodicState& P = *per_;
+    const bool enabled = periodic_enabled();
+    if (P.planned && P.enabled == enabled && P.blk0 == tab_blk0_ && P.blk1 == tab_blk1_) return P.ok;
+    P.enabled = enabled;
+    P.planned = true; P.ok = false; P.blk0 = tab_blk0_; P.blk1 = tab_blk1_; P.T_n = 0;
+    const ScenConst& sc = md_.sc;
+    if (!enabled || sc.n_sats == 0 || md_.any_dynamic || md_.any_var_visibility) return false;
+    P.ns = periodic_padded_sats(sc.n_sats);
+    if (P.ns == 0) return false;
+    // one primary-code period must be a whole number of output samples, the same for every satellite
+    const uint32_t code_len = md_.satcode[0].code_len;
+    for (const SatCode& c : md_.satcode) if (c.code_len != code_len) return false;
+    const unsigned __int128 num = (unsigned __int128)code_len * sc.ratA, den = (unsigned __int128)sc.ratB * kOversample;
+    if (num % den != 0) return false;
+    const uint64_t L = (uint64_t)(num / den);
+    if (L < 1024 || L > (1u << 20) || L % kPerSlotsPerThread != 0) return false;
+    P.L = (uint32_t)L;
+    P.n_tiles = (uint32_t)((L + 1023) / 1024);
+    P.tile_len = (uint32_t)(((L + P.n_tiles - 1) / P.n_tiles + 3) / 4 * 4);
+    // reference period: the first one whose samples and FIR history lie inside the table
+    P.k_ref = ((tab_blk0_ + 1) * sc.B + L - 1) / L;
+    if (P.k_ref == 0) P.k_ref = 1;
+    if ((P.k_ref + 1) * L > tab_blk1_ * sc.B || (P.k_ref + 1) * L > sc.total) return false;
+
+    cudaStream_t st = current_stream();
+    const uint32_t nblk = (uint32_t)(tab_blk1_ - tab_blk0_);
+    P.counters.reserve(2);
+    R4WB_CUDA(cudaMemsetAsync(P.counters.p, 0, 2 * sizeof(uint32_t), st));
+    launch_static_check(d_tab_.p, d_sat_.p, nblk, sc.n_sats, sc.B, P.counters.p, st);
+    P.ys.reserve((size_t)P.ns * L); P.yb.reserve((size_t)P.ns * L);
+    P.sat.reserve(P.ns); P.cands.reserve(kPerMaxCands);
+    R4WB_CUDA(cudaMemsetAsync(P.ys.p, 0, (size_t)P.ns * L * sizeof(float), st));
+    R4WB_CUDA(cudaMemsetAsync(P.yb.p, 0, (size_t)P.ns * L * sizeof(float), st));
+    R4WB_CUDA(cudaMemsetAsync(P.sat.p, 0xff, (size_t)P.ns * sizeof(PerSat), st));
+    PeriodTableArgs ta{};
+    ta.tab = d_tab_.p; ta.perbits = d_perbits_.p; ta.satcode = d_satcode_.p; ta.taps = d_taps_.p;
+    ta.ys = P.ys.p; ta.yb = P.yb.p; ta.sat = P.sat.p; ta.cands = P.cands.p; ta.n_cands = P.counters.p + 1;
+    ta.tab_blk0 = tab_blk0_; ta.B = sc.B; ta.k_ref = P.k_ref; ta.delta46 = sc.delta46;
+    ta.n_sats = sc.n_sats; ta.L = P.L; ta.tile_len = P.tile_len;
+    launch_period_tables(ta, P.ns, st);
+    uint32_t h[2] = {1u, 0u};
+    R4WB_CUDA(cudaMemcpyAsync(h, P.counters.p, sizeof h, cudaMemcpyDeviceToHost, st));
+    R4WB_CUDA(cudaStreamSynchronize(st));
+    P.n_cands = h[1];
+    P.ok = h[0] == 0 && h[1] <= (uint32_t)kPerMaxCands;
+    return P.ok;
+}
+
+// Whole primary-code periods inside [first, first + n) through the period-resident kernels, the partial periods at
+// either end (and the first period of the run, whose FIR starts from a zero delay line) through k_synth on a side stream.
+bool Scenario::render_periodic(uint64_t first, uint64_t n, void* d_out)
+{
+    if (!plan_periodic()) return false;
+    PeriodicState& P = *per_;
+    const ScenConst& sc = md_.sc;
+    const uint64_t L = P.L;
+    const uint64_t k_lo = std::max<uint64_t>(1, (first + L - 1) / L), k_hi = (first + n) / L;
+    if (k_hi < k_lo + 32) return false;
+    const uint64_t head = k_lo * L - first;                               // samples before the first whole period
+    float2* out_fast = reinterpret_cast<float2*>(d_out) + head;
+    if (head % kPerSlotsPerThread != 0 || (uintptr_t)out_fast % 32 != 0) return false;
+    if (k_lo * L / sc.B < tab_blk0_ + (tab_blk0_ > 0 ? 1 : 0)) return false;
+
+    static int sm_count = 0;
+    if (!sm_count) {
+        int dev = 0;
+        R4WB_CUDA(cudaGetDevice(&dev));
+        R4WB_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+    }
+    cudaStream_t st = current_stream();
+    ensure_side_stream();
+    const uint32_t n_periods = (uint32_t)(k_hi - k_lo);
+
+    PeriodicArgs a{};
+    a.ys = P.ys.p; a.yb = P.yb.p; a.sat = P.sat.p; a.cands = P.cands.p; a.n_cands = P.counters.p + 1;
+    a.tab = d_tab_.p; a.satcode = d_satcode_.p;
+    a.out = out_fast; a.power_sum = d_power_.p;
+    a.k0 = k_lo; a.k_ref = P.k_ref; a.tab_blk0 = tab_blk0_; a.B = sc.B;
+    a.n_periods = n_periods; a.L = P.L; a.tile_len = P.tile_len; a.n_tiles = P.n_tiles;
+    a.n_sats = sc.n_sats; a.flags = sc.flags; a.noise_std = sc.noise_std; a.seed = sc.seed;
+    // periods per CTA: about 64, adjusted so that the CTAs fill whole waves of 2 per SM
+    {
+        const uint64_t slots = (uint64_t)sm_count * 2;
+        const uint64_t items0 = (uint64_t)P.n_tiles * ((n_periods + 63) / 64);
+        const uint64_t waves = std::max<uint64_t>(1, (items0 + slots / 2) / slots);
+        uint64_t n_chunks = std::max<uint64_t>(1, waves * slots / P.n_tiles);
+        uint64_t KI = (n_periods + n_chunks - 1) / n_chunks;
+        if (KI > 96) KI = 96;
+        if (KI < 8) KI = std::min<uint64_t>(8, n_periods);
+        a.KI = (uint32_t)KI;
+        a.n_chunks = (uint32_t)((n_periods + KI - 1) / KI);
+    }
+    if (P.T_n != n_periods || P.T_k0 != k_lo) {
+        P.T.reserve((size_t)n_periods * P.ns * 2);
+        launch_period_phasors(a, P.ns, tab_blk1_, P.T.p, st);
+        P.T_n = n_periods; P.T_k0 = k_lo;
+    }
+    a.T = P.T.p;
+
+    // partial periods at the ends: general kernel, next to the periodic one
+    const uint64_t tail_first = k_hi * L, tail_n = first + n - tail_first;
+    if (head > 0 || tail_n > 0) {
+        R4WB_CUDA(cudaEventRecord(ev_fork_, st));
+        R4WB_CUDA(cudaStreamWaitEvent(side_stream_, ev_fork_, 0));
+        if (head > 0) {
+            const uint64_t hb0 = first / sc.B, hb1 = (first + head - 1) / sc.B;
+            launch_synth(d_tab_.p, d_hdr_.p, d_tiles_.p, (uint32_t)(hb0 - tab_blk0_), (uint32_t)(hb1 - hb0 + 1), first, head, d_out, R4WB_FMT_CF32, sc.B, side_stream_);
+        }
+        if (tail_n > 0) {
+            const uint64_t tb0 = tail_first / sc.B, tb1 = (first + n - 1) / sc.B;
+            launch_synth(d_tab_.p, d_hdr_.p, d_tiles_.p, (uint32_t)(tb0 - tab_blk0_), (uint32_t)(tb1 - tb0 + 1), tail_first, tail_n,
+                         reinterpret_cast<float2*>(d_out) + (tail_first - first), R4WB_FMT_CF32, sc.B, side_stream_);
+        }
+        R4WB_CUDA(cudaEventRecord(ev_join_, side_stream_));
+    }
+    launch_synth_periodic(a, P.ns, P.n_cands, st);
+    if (head > 0 || tail_n > 0) R4WB_CUDA(cudaStreamWaitEvent(st, ev_join_, 0));
+    return true;
+}
+
+void Scenario::render_device(uint64_t first, uint64_t n, void* d_out, r4wb_fmt fmt)
+{
+    const ScenConst& sc = md_.sc;
+    if (fmt == R4WB_FMT_CF32 && render_periodic(first, n, d_out)) { last_path_ = 1; return; }
+    last_path_ = 0;
+    const uint64_t b0 = first / sc.B, b1 = (first + n - 1) / sc.B;
+    launch_synth(d_tab_.p, d_hdr_.p, d_tiles_.p, (uint32_t)(b0 - tab_blk0_), (uint32_t)(b1 - b0 + 1), first, n, d_out, fmt, sc.B, current_stream());
 }
 
 void Scenario::render_to(uint64_t first, uint64_t n, void* dst, r4wb_mem where, r4wb_fmt fmt)
@@ -129,22 +304,31 @@ void Scenario::render_to(uint64_t first, uint64_t n, void* dst, r4wb_mem where, 
 
     const uint64_t b0 = first / sc.B, b1 = (first + n - 1) / sc.B;
     build_canonical_table(md_.table_begin(b0), b1 + 1);
-    const uint64_t tb0 = tab_blk0_;
 
     if (where == R4WB_MEM_DEVICE) {
-        launch_synth(d_tab_.p, d_hdr_.p, d_tiles_.p, (uint32_t)(b0 - tb0), (uint32_t)(b1 - b0 + 1), first, n, dst, fmt, sc.B);
+        render_device(first, n, dst, fmt);
         return;
     }
-    // host destination: render chunk by chunk into a device staging buffer and copy out
-    const uint64_t chunk_blocks = std::max<uint64_t>(1, (uint64_t)(32u << 20) / sc.B);   // ~32 Msamples per chunk
-    unsigned char* stage = d_stage_.reserve((size_t)std::min<uint64_t>(n + sc.B, chunk_blocks * sc.B + sc.B) * bps);
-    for (uint64_t cb = b0; cb <= b1; cb += chunk_blocks) {
+    // host destination: render chunk by chunk into two device staging buffers; the copy of one chunk (side stream)
+    // overlaps the rendering of the next
+    ensure_side_stream();
+    const uint64_t chunk_blocks = std::max<uint64_t>(1, (uint64_t)(16u << 20) / sc.B);   // ~16 Msamples per chunk
+    const size_t stage_bytes = (size_t)std::min<uint64_t>(n + sc.B, chunk_blocks * sc.B + sc.B) * bps;
+    unsigned char* stage[2] = {d_stage_.reserve(stage_bytes), d_stage2_.reserve(stage_bytes)};
+    uint32_t c = 0;
+    for (uint64_t cb = b0; cb <= b1; cb += chunk_blocks, ++c) {
         const uint64_t ce = std::min(b1 + 1, cb + chunk_blocks);
         const uint64_t f = std::max(first, cb * sc.B), l = std::min(first + n, ce * sc.B);
-        launch_synth(d_tab_.p, d_hdr_.p, d_tiles_.p, (uint32_t)(cb - tb0), (uint32_t)(ce - cb), f, l - f, stage, fmt, sc.B);
-        R4WB_CUDA(cudaMemcpyAsync((unsigned char*)dst + (f - first) * bps, stage, (l - f) * bps, cudaMemcpyDeviceToHost, st));
-        R4WB_CUDA(cudaStreamSynchronize(st));
+        const uint32_t k = c & 1u;
+        if (c >= 2) R4WB_CUDA(cudaStreamWaitEvent(st, ev_copy_[k], 0));          // the buffer's previous copy is done
+        render_device(f, l - f, stage[k], fmt);
+        R4WB_CUDA(cudaEventRecord(ev_render_[k], st));
+        R4WB_CUDA(cudaStreamWaitEvent(side_stream_, ev_render_[k], 0));
+        R4WB_CUDA(cudaMemcpyAsync((unsigned char*)dst + (f - first) * bps, stage[k], (l - f) * bps, cudaMemcpyDeviceToHost, side_stream_));
+        R4WB_CUDA(cudaEventRecord(ev_copy_[k], side_stream_));
     }
+    R4WB_CUDA(cudaStreamSynchronize(side_stream_));
+    R4WB_CUDA(cudaStreamSynchronize(st));
 }
 
 void Scenario::generate(uint64_t first, uint64_t n, void* dst, r4wb_mem where, r4wb_fmt fmt)
@@ -181,7 +365,7 @@ uint64_t Scenario::generate_block(uint64_t n_req, void* dst, r4wb_mem where, r4w
         d_seq_tiles_.reserve(std::max<size_t>(1, (size_t)2 * a.tiles_per_block * sc.n_sats));
         build_tiles(a, 1, 1, d_seq_tiles_.p);
     }
-    launch_synth(d_seq_tab_.p, d_seq_hdr_.p, d_seq_tiles_.p, 1, 1, current_, n, d_out, fmt, n);
+    launch_synth(d_seq_tab_.p, d_seq_hdr_.p, d_seq_tiles_.p, 1, 1, current_, n, d_out, fmt, n, st);
     if (where != R4WB_MEM_DEVICE) R4WB_CUDA(cudaMemcpyAsync(dst, d_out, (size_t)n * bps, cudaMemcpyDeviceToHost, st));
     R4WB_CUDA(cudaStreamSynchronize(st));   // `tab`/`hdr` are stack/heap temporaries
     seq_.advance(md_, tab, (uint32_t)n);

@@ -165,6 +165,10 @@ class GnssScenario:
         _lib.check(_lib.lib().r4wb_scenario_last_power_sum(self._h, C.byref(v)))
         return float(v.value)
 
+    def last_path(self) -> int:
+        """0: k_synth rendered the last generate call, 1: the period-resident kernels did (diagnostic)."""
+        return int(_lib.lib().r4wb_scenario_last_path(self._h))
+
     def _debug_block_params(self, block: int, sat: int) -> np.ndarray:
         out = np.zeros(12, np.float64)
         _lib.check(_lib.lib().r4wb_debug_block_params(self._h, int(block), int(sat), out.ctypes.data_as(C.c_void_p)))
