@@ -32,7 +32,8 @@ struct Scenario::PeriodicState {
     uint32_t T_n = 0;
     DevBuf<float> ys, yb;
     DevBuf<PerSat> sat;
-    DevBuf<uint32_t> cands, counters;       // counters[0] = precondition violations, [1] = number of patch slots
+    DevBuf<uint2> cands;
+    DevBuf<uint32_t> counters;              // counters[0] = precondition violations, [1] = number of patch slots
     DevBuf<float4> T;
 };
 
@@ -150,7 +151,14 @@ void Scenario::launch_synth(const BlockSat* tab, const BlockHdr* hdr, const Tile
     }
     const int tile_k = md_.tile_k;
     const size_t smem = synth_smem_bytes(a.n_sats, a.nw64, a.lut_den);
-    const int per_sm = std::max(1, synth_max_blocks_per_sm(tile_k, fmt, smem));
+    static int per_sm_cache[2][5] = {};                      // [tile_k == 5][fmt], for the smem size of the first query
+    static size_t per_sm_smem[2][5] = {};
+    int& cached = per_sm_cache[tile_k == 5][(int)fmt];
+    if (!cached || per_sm_smem[tile_k == 5][(int)fmt] != smem) {
+        cached = std::max(1, synth_max_blocks_per_sm(tile_k, fmt, smem));
+        per_sm_smem[tile_k == 5][(int)fmt] = smem;
+    }
+    const int per_sm = cached;
     const uint64_t n_tiles = (uint64_t)tb_count * a.tiles_per_block;
     const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>(n_tiles, (uint64_t)sm_count * per_sm));
     launch_synth_kernel(a, tile_k, fmt, grid, st);
@@ -265,10 +273,12 @@ bool Scenario::render_periodic(uint64_t first, uint64_t n, void* d_out)
     }
     a.T = P.T.p;
 
-    // partial periods at the ends: general kernel, next to the periodic one
+    // the periodic kernels first (the GPU starts on the bulk while the host enqueues the rest); the partial periods at the
+    // ends go through the general kernel on the side stream, forked before and joined after
     const uint64_t tail_first = k_hi * L, tail_n = first + n - tail_first;
+    if (head > 0 || tail_n > 0) R4WB_CUDA(cudaEventRecord(ev_fork_, st));
+    launch_synth_periodic(a, P.ns, P.n_cands, st);
     if (head > 0 || tail_n > 0) {
-        R4WB_CUDA(cudaEventRecord(ev_fork_, st));
         R4WB_CUDA(cudaStreamWaitEvent(side_stream_, ev_fork_, 0));
         if (head > 0) {
             const uint64_t hb0 = first / sc.B, hb1 = (first + head - 1) / sc.B;
@@ -281,7 +291,6 @@ bool Scenario::render_periodic(uint64_t first, uint64_t n, void* d_out)
         }
         R4WB_CUDA(cudaEventRecord(ev_join_, side_stream_));
     }
-    launch_synth_periodic(a, P.ns, P.n_cands, st);
     if (head > 0 || tail_n > 0) R4WB_CUDA(cudaStreamWaitEvent(st, ev_join_, 0));
     return true;
 }

@@ -670,6 +670,14 @@ R4WB_HD void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, c
     r0 = c0; r1 = c1; r2 = c2; r3 = c3;
 }
 
+// one round of Philox4x32 (key words of the round passed in)
+R4WB_HD void philox_round(uint32_t& c0, uint32_t& c1, uint32_t& c2, uint32_t& c3, uint32_t k0, uint32_t k1)
+{
+    const uint32_t hi0 = umulhi32(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = umulhi32(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    c0 = hi1 ^ c1 ^ k0; c1 = lo1; c2 = hi0 ^ c3 ^ k1; c3 = lo0;
+}
+
 // uint32 -> float, rounded toward zero (never reaches 2^32)
 R4WB_HD float u32_to_float_rz(uint32_t a)
 {

@@ -118,15 +118,15 @@ __global__ void k_period_cands(PeriodTableArgs a)
     const uint32_t m = blockIdx.x * blockDim.x + threadIdx.x;
     if (m >= a.L) return;
     const uint32_t wf = period_warp_first(m, a.tile_len);
-    bool need = false;
+    uint32_t smask = 0;                               // satellites that need a patch at this slot
     for (uint32_t s = 0; s < a.n_sats; ++s) {
         const PerSat ps = a.sat[s];
         if (!ps.visible) continue;
-        need = need || a.yb[(size_t)s * a.L + m] != 0.0f || ((m >= ps.mstar) != (wf >= ps.mstar));
+        if (a.yb[(size_t)s * a.L + m] != 0.0f || ((m >= ps.mstar) != (wf >= ps.mstar))) smask |= 1u << s;
     }
-    if (need) {
+    if (smask) {
         const uint32_t k = atomicAdd(a.n_cands, 1u);
-        if (k < (uint32_t)kPerMaxCands) a.cands[k] = m;
+        if (k < (uint32_t)kPerMaxCands) a.cands[k] = make_uint2(m, smask);
     }
 }
 
@@ -223,8 +223,21 @@ __global__ void __launch_bounds__(kPerThreads, 2) k_synth_periodic(PeriodicArgs 
     float* op = reinterpret_cast<float*>(a.out + ((uint64_t)kk0 * a.L + m0));
     const float4* Tp = Tw;
 
+    // The noise of period k+1 is drawn while period k is summed: the ten Philox rounds of the two counters are spread
+    // over the satellite loop (integer work between the packed FMAs), the Box-Muller transforms (MUFU) run at the end
+    // of the iteration and complete under the next iteration's FMAs.
+    float2 n0 = make_float2(0.f, 0.f), n1 = n0, n2 = n0, n3 = n0;         // (re, im) noise of the four samples
+    if (noise_on) {
+        noise_of_counter(g >> 1, PK, n0, n1);
+        noise_of_counter((g >> 1) + 1, PK, n2, n3);
+    }
+
 #pragma unroll 1
-    for (uint32_t kk = kk0; kk < kk1; ++kk, g += a.L, op += 2 * (size_t)a.L, Tp += NS) {
+    for (uint32_t kk = kk0; kk < kk1; ++kk, op += 2 * (size_t)a.L, Tp += NS) {
+        g += a.L;
+        const uint64_t ctr = g >> 1;                                      // next period's first counter (even)
+        uint32_t c0 = (uint32_t)ctr, c1 = (uint32_t)(ctr >> 32), c2 = 0u, c3 = 0u;
+        uint32_t d0 = c0 | 1u, d1 = c1, d2 = 0u, d3 = 0u;
         float2 xr0 = make_float2(0.f, 0.f), xi0 = xr0, yr0 = xr0, yi0 = xr0, xr1 = xr0, xi1 = xr0, yr1 = xr0, yi1 = xr0;
 #pragma unroll
         for (int s = 0; s < NS; ++s) {
@@ -234,20 +247,26 @@ __global__ void __launch_bounds__(kPerThreads, 2) k_synth_periodic(PeriodicArgs 
             yr0 = pk_fma(qi[s][0], trr, yr0); yi0 = pk_fma(qi[s][0], tii, yi0);
             xr1 = pk_fma(qr[s][1], trr, xr1); xi1 = pk_fma(qr[s][1], tii, xi1);
             yr1 = pk_fma(qi[s][1], trr, yr1); yi1 = pk_fma(qi[s][1], tii, yi1);
+            if (noise_on) {
+#pragma unroll
+                for (int r = (10 * s) / NS; r < (10 * (s + 1)) / NS; ++r) {
+                    philox_round(c0, c1, c2, c3, PK.k0[r], PK.k1[r]);
+                    philox_round(d0, d1, d2, d3, PK.k0[r], PK.k1[r]);
+                }
+            }
         }
         // (qr + j qi)(tr + j ti): re = qr tr - qi ti, im = qr ti + qi tr
         float2 re0 = pk_sub(xr0, yi0), im0 = pk_add(xi0, yr0), re1 = pk_sub(xr1, yi1), im1 = pk_add(xi1, yr1);
-        if (noise_on) {
-            float2 n0, n1, n2, n3;                        // (re, im) noise of the four samples
-            noise_of_counter(g >> 1, PK, n0, n1);
-            noise_of_counter((g >> 1) + 1, PK, n2, n3);
-            re0 = pk_fma(make_float2(n0.x, n1.x), sig2, re0); im0 = pk_fma(make_float2(n0.y, n1.y), sig2, im0);
-            re1 = pk_fma(make_float2(n2.x, n3.x), sig2, re1); im1 = pk_fma(make_float2(n2.y, n3.y), sig2, im1);
-        }
+        re0 = pk_fma(make_float2(n0.x, n1.x), sig2, re0); im0 = pk_fma(make_float2(n0.y, n1.y), sig2, im0);
+        re1 = pk_fma(make_float2(n2.x, n3.x), sig2, re1); im1 = pk_fma(make_float2(n2.y, n3.y), sig2, im1);
         pw = pk_fma(re0, re0, pw); pw = pk_fma(im0, im0, pw); pw = pk_fma(re1, re1, pw); pw = pk_fma(im1, im1, pw);
         if (active)
             asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(op), "f"(re0.x), "f"(im0.x), "f"(re0.y), "f"(im0.y),
                          "f"(re1.x), "f"(im1.x), "f"(re1.y), "f"(im1.y) : "memory");
+        if (noise_on) {
+            n0 = gauss_pair(c0, c1); n1 = gauss_pair(c2, c3);
+            n2 = gauss_pair(d0, d1); n3 = gauss_pair(d2, d3);
+        }
     }
 
     if (a.power_sum) {
@@ -267,19 +286,19 @@ __global__ void __launch_bounds__(128) k_periodic_fix(PeriodicArgs a)
     const uint32_t ci = blockIdx.y * blockDim.x + threadIdx.x, kk = blockIdx.x;
     double dp = 0.0;
     if (ci < min(*a.n_cands, (uint32_t)kPerMaxCands)) {
-        const uint32_t m = a.cands[ci];
+        const uint2 cand = a.cands[ci];
+        const uint32_t m = cand.x;
         const uint64_t k = a.k0 + kk, g = k * a.L + m;
         const uint32_t wf = period_warp_first(m, a.tile_len);
         const uint64_t b = g / a.B - a.tab_blk0;
         const uint32_t i = (uint32_t)(g % a.B);
         float dre = 0.0f, dim = 0.0f;
         bool any = false;
-        for (uint32_t s = 0; s < a.n_sats; ++s) {
+        for (uint32_t rest = cand.y; rest; rest &= rest - 1u) {
+            const uint32_t s = (uint32_t)__ffs((int)rest) - 1u;
             const PerSat ps = a.sat[s];
-            if (!ps.visible) continue;
             const uint32_t ot = m >= ps.mstar ? 1u : 0u, ow = wf >= ps.mstar ? 1u : 0u;
             const float Bv = a.yb[(size_t)s * a.L + m];
-            if (Bv == 0.0f && ot == ow) continue;
             const SatCode cd = a.satcode[s];
             const long long P = (long long)cd.epoch_period;
             long long dk = ((long long)k - (long long)a.k_ref) % P;

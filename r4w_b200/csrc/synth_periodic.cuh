@@ -41,7 +41,7 @@ struct PeriodicArgs {
     const float* yb;        // [NS][L] part of ys that belongs to the previous epoch (0 for all but <= 8 slots per satellite)
     const float4* T;        // [n_periods][NS][2]: (re, re, im, im) of sign[e + j] * amp * exp(j phi(k L)), j = 0, 1
     const PerSat* sat;      // [NS]
-    const uint32_t* cands;  // [n_cands] slots patched by k_periodic_fix
+    const uint2* cands;     // [n_cands] (slot, satellite mask) patched by k_periodic_fix
     const uint32_t* n_cands;
     const BlockSat* tab;    // canonical block table, row 0 = block tab_blk0
     const SatCode* satcode; // [n_sats]
@@ -60,7 +60,7 @@ struct PeriodicArgs {
 // arguments of the once-per-table prologue kernels
 struct PeriodTableArgs {
     const BlockSat* tab; const uint32_t* perbits; const SatCode* satcode; const float* taps;
-    float* ys; float* yb; PerSat* sat; uint32_t* cands; uint32_t* n_cands;
+    float* ys; float* yb; PerSat* sat; uint2* cands; uint32_t* n_cands;
     uint64_t tab_blk0, B, k_ref, delta46;
     uint32_t n_sats, L, tile_len;
 };
