@@ -214,6 +214,7 @@ def run_b200(args):
     prns = [s.prn for s in cfg.satellites]
     codes = np.stack([R.e1c_replica(p, 5e6, CODE_LENGTH) for p in prns])
     scen = R.GnssScenario(cfg, noise=True)
+    scen.set_profiling(True)
     first, n = segment_for_rank(scen.total_samples(), CODE_LENGTH, rank, world)
     n_snap_total = n // CODE_LENGTH
     n_snap = n_snap_total if args.acq_snapshots <= 0 else min(args.acq_snapshots, n_snap_total)
@@ -236,7 +237,7 @@ def run_b200(args):
         table = all_gather_table(results_to_table(pods, n_snap, len(prns)))
         e2.record()
         if record is not None:
-            record.append((e0, e1, e2, acq.last_profile(), acq.guard_count()))
+            record.append((e0, e1, e2, acq.last_profile(), acq.guard_count(), scen.last_profile()))
         return table
 
     for _ in range(max(args.warmup, 0)):
@@ -261,6 +262,7 @@ def run_b200(args):
     ms_acq = float(np.mean([r[1].elapsed_time(r[2]) for r in rec]))
     ms_total = t0.elapsed_time(t1) / args.steps
     prof = rec[-1][3]
+    sprof = {k: (float(np.mean([r[5][k][0] for r in rec])), rec[-1][5][k][1]) for k in rec[-1][5]}
     guards = int(np.sum([r[4] for r in rec]))
 
     # ---- e2e: the same step through the C-ABI with HOST buffers (pinned), copies inside the timed region
@@ -308,6 +310,15 @@ def run_b200(args):
     inv_ms, inv_n = prof["inverse_fft_peak"]
     fwd_ms, fwd_n = prof["forward_fft"]
     inv_ms, fwd_ms = rmax(inv_ms), rmax(fwd_ms)
+    # dominant synthesis kernel of the step and the samples it wrote (the period-resident kernel renders whole primary-code
+    # periods, k_synth the partial periods at the ends; k_synth alone when the scenario is not static)
+    syn_kernel = "k_synth_periodic" if sprof["k_synth_periodic"][1] else "k_synth"
+    syn_kernel_ms = rmax(sprof[syn_kernel][0])
+    if syn_kernel == "k_synth_periodic":
+        k_lo, k_hi = max(1, -(-first // CODE_LENGTH)), (first + n) // CODE_LENGTH
+        syn_kernel_samples = (k_hi - k_lo) * CODE_LENGTH
+    else:
+        syn_kernel_samples = n
 
     total_samples = n * world
     cells_rank = n_snap * len(prns) * bins * CODE_LENGTH
@@ -330,7 +341,7 @@ def run_b200(args):
     _lib.check(_lib.lib().r4wb_host_free(host))
 
     if rank == 0:
-        synth_gbs = n * 8 / (ms_syn * 1e-3) / 1e9
+        synth_gbs = syn_kernel_samples * 8 / (syn_kernel_ms * 1e-3) / 1e9
         acq_tflops = cells_rank * FLOP_PER_CELL / ((inv_ms + fwd_ms) * 1e-3) / 1e12 if inv_ms + fwd_ms > 0 else None
         line = {
             "metric": "gnss_iq_synth_msamples_per_s", "value": total_samples / (ms_syn * 1e-3) / 1e6, "unit": "Msamples/s",
@@ -342,17 +353,20 @@ def run_b200(args):
                        "l2": "per-step output 0.8 GB and spectra working set exceed the 126 MB L2 (no explicit flush)",
                        "step": "synth then acquire; ms_per_step/value cover the synthesis half, acq.* the acquisition half, ms_step_total both"},
             "ms_step_total": ms_total,
-            "roofline": {"bound": "hbm", "kernel": "k_synth", "achieved": synth_gbs, "peak": peak, "unit": "GB/s", "frac": synth_gbs / peak,
-                         "traffic": ncu_traffic("k_synth"), "peak_source": peak_src, "algorithmic_bytes_per_launch": n * 8,
-                         "note": "8 B per output sample (one cf32 store); CUDA events on the launching stream"},
+            "roofline": {"bound": "hbm", "kernel": syn_kernel, "achieved": synth_gbs, "peak": peak, "unit": "GB/s", "frac": synth_gbs / peak,
+                         "traffic": ncu_traffic(syn_kernel), "peak_source": peak_src, "algorithmic_bytes_per_launch": syn_kernel_samples * 8,
+                         "kernel_ms": syn_kernel_ms,
+                         "note": "8 B per output sample (one cf32 store) x the samples this kernel wrote / its CUDA-event time on the launching "
+                                 "stream; `value` is over the whole generate call (all kernels + launch gaps)"},
+            "synth_kernel_ms": {k: v[0] for k, v in sprof.items()}, "synth_kernel_launches": {k: v[1] for k, v in sprof.items()},
             "e2e": {"value": total_samples / (ms_syn_e2e * 1e-3) / 1e6, "unit": "Msamples/s", "h2d_bytes_per_step": 0,
                     "d2h_bytes_per_step": n * 8, "api": "r4wb_scenario_generate(..., R4WB_MEM_HOST, CF32) into pinned host memory",
                     "other_formats_rank0": fmt_e2e},
             "acq": {"metric": "pcps_acq_cells_per_s", "value": cells / (ms_acq * 1e-3), "unit": "cells/s", "ms_per_step": ms_acq,
                     "cells_per_step": cells, "f64_guard_reruns": guards,
                     "kernel_ms": {k: v[0] for k, v in prof.items()}, "kernel_launches": {k: v[1] for k, v in prof.items()},
-                    "roofline": {"bound": "fp32", "kernel": "k_rf_inv_peak (+k_rf_fwd)", "achieved": acq_tflops, "peak": FP32_PEAK_TFLOPS,
-                                 "unit": "TFLOP/s", "frac": (acq_tflops / FP32_PEAK_TFLOPS) if acq_tflops else None, "traffic": ncu_traffic("k_rf_inv_peak"),
+                    "roofline": {"bound": "fp32", "kernel": "k_rf_inv_peak_tm (+k_rf_fwd)", "achieved": acq_tflops, "peak": FP32_PEAK_TFLOPS,
+                                 "unit": "TFLOP/s", "frac": (acq_tflops / FP32_PEAK_TFLOPS) if acq_tflops else None, "traffic": ncu_traffic("k_rf_inv_peak_tm"),
                                  "peak_source": "nominal FP32 FMA peak (148 SM x 128 lanes x 2 x 1.965 GHz)",
                                  "note": f"{FLOP_PER_CELL} reference-equivalent flop per cell / summed CUDA-event time of the forward and inverse FFT kernels"},
                     "e2e": {"value": cells / (ms_acq_e2e * 1e-3), "unit": "cells/s", "h2d_bytes_per_step": n_snap * CODE_LENGTH * 8,

@@ -203,6 +203,11 @@ r4wb_error r4wb_scenario_last_power_sum(const r4wb_scenario* h, double* power_su
  * kernels (constant-delay, constant-Doppler scenarios; R4WB_SYNTH_PERIODIC=0 in the environment disables them).
  * Diagnostic for A/B parity tests; no counterpart in the reference. */
 uint32_t r4wb_scenario_last_path(const r4wb_scenario* h);
+/* Optional device-side timing of the last generate call (measurement aid, no reference counterpart): when enabled, CUDA
+ * events bracket every synthesis-kernel launch on its stream.  ms[3] / launches[3] are the summed durations and launch
+ * counts of {k_synth, k_synth_periodic, k_periodic_fix}; last_profile waits for the events. */
+r4wb_error r4wb_scenario_set_profiling(r4wb_scenario* h, int enabled);
+r4wb_error r4wb_scenario_last_profile(r4wb_scenario* h, double* ms, uint64_t* launches);
 /* GnssScenario::satellite_status, gnss/scenario.rs:564-633 */
 r4wb_error r4wb_scenario_status(const r4wb_scenario* h, r4wb_sat_status* out, uint32_t cap, uint32_t* n);
 

@@ -169,6 +169,25 @@ double orc_saastamoinen_zenith_m(double height_m, double temperature_k, double p
 /* core/io/format.rs:203-222, fmt 2 = ci16, 3 = ci8, 4 = cu8; out = interleaved (re, im) integers */
 int orc_to_int_format(const orc_c64* in, size_t n, int fmt, void* out);
 
+/* ---- tracking channel, r4w_oracle_track.c: gnss/tracking.rs:107-337, 365-456 ---- */
+typedef struct orc_track_state {      /* TrackingState, gnss/types.rs:187-210 */
+    double code_phase, carrier_freq_hz, carrier_phase_rad, prompt_i, prompt_q, cn0_dbhz;
+    uint64_t ms_count;
+    uint8_t prn, carrier_lock, code_lock, bit_sync, pad[4];
+} orc_track_state;
+typedef struct orc_tracker orc_tracker;
+orc_tracker* orc_track_new(uint8_t prn, size_t code_length, double sample_rate, double chipping_rate, double initial_code_phase,
+                           double initial_doppler);
+void orc_track_free(orc_tracker* t);
+void orc_track_set_dll_bandwidth(orc_tracker* t, double bw_hz);
+void orc_track_set_pll_bandwidth(orc_tracker* t, double bw_hz);
+void orc_track_process(orc_tracker* t, const orc_c64* samples, size_t n, const int8_t* code, orc_track_state* out);
+void orc_track_state_get(const orc_tracker* t, orc_track_state* out);
+size_t orc_track_nav_bits(const orc_tracker* t, int8_t* out, size_t cap);
+double orc_loop_filter_2nd_run(double bw, double T, double disc, size_t n_updates);
+double orc_loop_filter_3rd_run(double bw, double T, double disc, size_t n_updates);
+void orc_dll_s_curve(double el_spacing, size_t num_points, double* err, double* disc);
+
 #ifdef __cplusplus
 }
 #endif

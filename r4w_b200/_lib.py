@@ -59,6 +59,8 @@ SYMBOLS = {
     "r4wb_scenario_generate": (_int, [_vp, _u64, _u64, _vp, _int, _int]),
     "r4wb_scenario_last_power_sum": (_int, [_vp, C.POINTER(_dbl)]),
     "r4wb_scenario_last_path": (C.c_uint32, [_vp]),
+    "r4wb_scenario_set_profiling": (_int, [_vp, _int]),
+    "r4wb_scenario_last_profile": (_int, [_vp, _vp, _vp]),
     "r4wb_scenario_status": (_int, [_vp, C.POINTER(SatStatusPod), _u32, C.POINTER(_u32)]),
     "r4wb_e1_code": (_int, [_u32, _u8, _vp, _u64]),
     "r4wb_gps_ca_code": (_int, [_u8, _vp, _u64]),

@@ -145,6 +145,19 @@ r4wb_error r4wb_scenario_last_power_sum(const r4wb_scenario* h, double* power_su
     return guard([&] { *power_sum = const_cast<r4wb_scenario*>(h)->impl.last_power_sum(); });
 }
 
+r4wb_error r4wb_scenario_set_profiling(r4wb_scenario* h, int enabled)
+{
+    if (!h) { t_error = "handle is NULL"; return R4WB_ERR_NULL_POINTER; }
+    h->impl.set_profiling(enabled != 0);
+    return R4WB_OK;
+}
+
+r4wb_error r4wb_scenario_last_profile(r4wb_scenario* h, double* ms, uint64_t* launches)
+{
+    if (!h || !ms || !launches) { t_error = "handle/ms/launches is NULL"; return R4WB_ERR_NULL_POINTER; }
+    return guard([&] { h->impl.last_profile(ms, launches); });
+}
+
 uint32_t r4wb_scenario_last_path(const r4wb_scenario* h) { return h ? h->impl.last_path() : 0u; }
 
 r4wb_error r4wb_scenario_status(const r4wb_scenario* h, r4wb_sat_status* out, uint32_t cap, uint32_t* n)

@@ -223,6 +223,8 @@ public:
     uint64_t generate_block(uint64_t n, void* dst, r4wb_mem where, r4wb_fmt fmt);
     double last_power_sum();
     uint32_t last_path() const { return last_path_; }
+    void set_profiling(bool on) { profiling_ = on; }
+    void last_profile(double* ms3, uint64_t* launches3);   // of the last generate call: {k_synth, k_synth_periodic, k_periodic_fix}
     void status(r4wb_sat_status* out, uint32_t cap, uint32_t* n) const { md_.status(current_, out, cap, n); }
     // test hook: entry of canonical block `block`, satellite `sat` -> 12 doubles
     void debug_block(uint64_t block, uint32_t sat, double* out12);
@@ -263,6 +265,12 @@ private:
     struct PeriodicState;
     PeriodicState* per_ = nullptr;
     uint32_t last_path_ = 0;
+    struct Timed { cudaEvent_t a, b; int kind; };
+    bool profiling_ = false;
+    std::vector<cudaEvent_t> event_pool_;
+    std::vector<Timed> timed_;
+    void prof_begin(int kind, cudaStream_t st);
+    void prof_end(cudaStream_t st);
     DevBuf<unsigned char> d_stage2_;          // second staging buffer of the host-destination pipeline
     cudaStream_t side_stream_ = nullptr;      // head / tail launches next to the periodic kernel; D2H copies
     cudaEvent_t ev_fork_ = nullptr, ev_join_ = nullptr, ev_render_[2] = {nullptr, nullptr}, ev_copy_[2] = {nullptr, nullptr};

@@ -20,7 +20,8 @@ void launch_tile_params(const SynthArgs& a, uint32_t tb_begin, uint32_t tb_count
 void launch_static_check(const BlockSat*, const SatConst*, uint32_t nblk, uint32_t n_sats, uint64_t B, uint32_t* bad, cudaStream_t);
 void launch_period_tables(const PeriodTableArgs&, uint32_t ns_padded, cudaStream_t);
 void launch_period_phasors(const PeriodicArgs&, uint32_t ns_padded, uint64_t tab_blk1, float4* T, cudaStream_t);
-void launch_synth_periodic(const PeriodicArgs&, uint32_t ns_padded, uint32_t n_cands, cudaStream_t);
+void launch_synth_periodic(const PeriodicArgs&, uint32_t ns_padded, cudaStream_t);
+void launch_periodic_fix(const PeriodicArgs&, uint32_t n_cands, cudaStream_t);
 uint32_t periodic_padded_sats(uint32_t n);
 
 struct Scenario::PeriodicState {
@@ -61,12 +62,47 @@ Scenario::~Scenario()
     for (cudaEvent_t e : {ev_fork_, ev_join_, ev_render_[0], ev_render_[1], ev_copy_[0], ev_copy_[1]})
         if (e) cudaEventDestroy(e);
     if (side_stream_) cudaStreamDestroy(side_stream_);
+    for (cudaEvent_t e : event_pool_) cudaEventDestroy(e);
+}
+
+// optional CUDA-event timing of the synthesis kernels (measurement aid): kinds 0 = k_synth, 1 = k_synth_periodic, 2 = k_periodic_fix
+void Scenario::prof_begin(int kind, cudaStream_t st)
+{
+    if (!profiling_) return;
+    while (event_pool_.size() < timed_.size() * 2 + 2) {
+        cudaEvent_t e;
+        R4WB_CUDA(cudaEventCreate(&e));
+        event_pool_.push_back(e);
+    }
+    Timed t{event_pool_[timed_.size() * 2], event_pool_[timed_.size() * 2 + 1], kind};
+    R4WB_CUDA(cudaEventRecord(t.a, st));
+    timed_.push_back(t);
+}
+
+void Scenario::prof_end(cudaStream_t st)
+{
+    if (!profiling_) return;
+    R4WB_CUDA(cudaEventRecord(timed_.back().b, st));
+}
+
+void Scenario::last_profile(double* ms3, uint64_t* launches3)
+{
+    for (int k = 0; k < 3; ++k) { ms3[k] = 0.0; launches3[k] = 0; }
+    for (const Timed& t : timed_) {
+        R4WB_CUDA(cudaEventSynchronize(t.b));
+        float ms = 0.0f;
+        R4WB_CUDA(cudaEventElapsedTime(&ms, t.a, t.b));
+        ms3[t.kind] += (double)ms;
+        launches3[t.kind] += 1;
+    }
 }
 
 void Scenario::ensure_side_stream()
 {
     if (side_stream_) return;
-    R4WB_CUDA(cudaStreamCreateWithFlags(&side_stream_, cudaStreamNonBlocking));
+    int prio_lo = 0, prio_hi = 0;
+    R4WB_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    R4WB_CUDA(cudaStreamCreateWithPriority(&side_stream_, cudaStreamNonBlocking, prio_hi));   // its few CTAs go ahead of the bulk's queue
     for (cudaEvent_t* e : {&ev_fork_, &ev_join_, &ev_render_[0], &ev_render_[1], &ev_copy_[0], &ev_copy_[1]})
         R4WB_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
 }
@@ -161,7 +197,9 @@ void Scenario::launch_synth(const BlockSat* tab, const BlockHdr* hdr, const Tile
     const int per_sm = cached;
     const uint64_t n_tiles = (uint64_t)tb_count * a.tiles_per_block;
     const int grid = (int)std::max<uint64_t>(1, std::min<uint64_t>(n_tiles, (uint64_t)sm_count * per_sm));
+    prof_begin(0, st);
     launch_synth_kernel(a, tile_k, fmt, grid, st);
+    prof_end(st);
 }
 
 static bool periodic_enabled()
@@ -277,7 +315,12 @@ bool Scenario::render_periodic(uint64_t first, uint64_t n, void* d_out)
     // ends go through the general kernel on the side stream, forked before and joined after
     const uint64_t tail_first = k_hi * L, tail_n = first + n - tail_first;
     if (head > 0 || tail_n > 0) R4WB_CUDA(cudaEventRecord(ev_fork_, st));
-    launch_synth_periodic(a, P.ns, P.n_cands, st);
+    prof_begin(1, st);
+    launch_synth_periodic(a, P.ns, st);
+    prof_end(st);
+    prof_begin(2, st);
+    launch_periodic_fix(a, P.n_cands, st);
+    prof_end(st);
     if (head > 0 || tail_n > 0) {
         R4WB_CUDA(cudaStreamWaitEvent(side_stream_, ev_fork_, 0));
         if (head > 0) {
@@ -310,6 +353,7 @@ void Scenario::render_to(uint64_t first, uint64_t n, void* dst, r4wb_mem where, 
     cudaStream_t st = current_stream();
     const size_t bps = fmt_bytes(fmt);
     R4WB_CUDA(cudaMemsetAsync(d_power_.p, 0, sizeof(double), st));
+    timed_.clear();
 
     const uint64_t b0 = first / sc.B, b1 = (first + n - 1) / sc.B;
     build_canonical_table(md_.table_begin(b0), b1 + 1);

@@ -7,8 +7,8 @@
 //   cf32 sink cast                           core/io/format.rs:197-200
 // Prologue (once per block table): k_static_check proves the preconditions from the block table itself,
 // k_period_tables evaluates the 63-tap FIR of every slot of one reference period literally (split by primary-code
-// epoch), k_period_cands lists the slots k_periodic_fix has to patch.  Per render: k_period_phasors (one f64 sincos
-// per period and satellite), k_synth_periodic, k_periodic_fix.
+// epoch), k_period_cands lists the slots whose epoch sign needs a patch.  Per render: k_period_phasors (one f64 sincos
+// per period and satellite), k_synth_periodic, k_periodic_fix (patch pass).
 #include <cuda_runtime.h>
 
 #include "synth_math.cuh"
@@ -177,14 +177,11 @@ __device__ __forceinline__ float2 pk_sub(float2 a, float2 b)
 // one 16-byte shared-memory read of the warp's phasor and 8 packed FMAs, then the noise pair of each sample and one
 // 32-byte store.  A warp writes 1 KiB of contiguous output per period.
 template <int NS>
-__global__ void __launch_bounds__(kPerThreads, 2) k_synth_periodic(PeriodicArgs a)
+__device__ __forceinline__ float periodic_render(const PeriodicArgs& a, float4* s_T, uint32_t tile, uint32_t kk0, uint32_t kk1)
 {
-    extern __shared__ float4 s_T[];                       // [warps][KI][NS]
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    const uint32_t tile = blockIdx.x % a.n_tiles, chunk = blockIdx.x / a.n_tiles;
-    const uint32_t kk0 = chunk * a.KI, kk1 = min(a.n_periods, kk0 + a.KI);
     const uint32_t wfirst = tile * a.tile_len + (uint32_t)kPerWarpSlots * warp;
-    if (kk0 >= kk1 || (uint32_t)kPerWarpSlots * warp >= a.tile_len || wfirst >= a.L) return;     // whole warp idle
+    if ((uint32_t)kPerWarpSlots * warp >= a.tile_len || wfirst >= a.L) return 0.0f;               // whole warp idle
     const uint32_t m0 = wfirst + (uint32_t)kPerSlotsPerThread * lane;
     const bool active = (uint32_t)kPerWarpSlots * warp + (uint32_t)kPerSlotsPerThread * lane < a.tile_len && m0 < a.L;
 
@@ -269,62 +266,96 @@ __global__ void __launch_bounds__(kPerThreads, 2) k_synth_periodic(PeriodicArgs 
         }
     }
 
+    return active ? pw.x + pw.y : 0.0f;
+}
+
+// One CTA = (tile of <= 1024 slots, chunk of KI periods).
+template <int NS>
+__global__ void __launch_bounds__(kPerThreads, 2) k_synth_periodic(PeriodicArgs a)
+{
+    extern __shared__ float4 s_T[];                       // [warps][KI][NS]
+    const uint32_t tile = blockIdx.x % a.n_tiles, chunk = blockIdx.x / a.n_tiles;
+    const uint32_t kk0 = chunk * a.KI, kk1 = min(a.n_periods, kk0 + a.KI);
+    if (kk0 >= kk1) return;
+    float p = periodic_render<NS>(a, s_T, tile, kk0, kk1);
     if (a.power_sum) {
-        float p = active ? pw.x + pw.y : 0.0f;
         for (int off = 16; off > 0; off >>= 1) p += __shfl_xor_sync(0xffffffffu, p, off);
-        if (lane == 0) atomicAdd(a.power_sum, (double)p);
+        if ((threadIdx.x & 31u) == 0 && p != 0.0f) atomicAdd(a.power_sum, (double)p);
     }
 }
 
-// ----------------------------------------------------------------------------------------------
-// Patch pass: for every period and every listed slot add (true - rendered) contribution of the satellites whose
-// epoch sign k_synth_periodic could not resolve per warp (slot on the other side of the epoch boundary than the
-// warp's first slot) or whose FIR window straddles the epoch boundary (two signs inside one window).
+// Patch pass.  A thread owns one listed slot in kFixPeriods consecutive periods and adds the (true - rendered)
+// contribution of the satellites whose epoch sign the render kernel could not resolve per warp (slot on the other side
+// of the epoch boundary than the warp's first slot) or whose FIR window straddles the epoch boundary (two signs inside
+// one window).  32-bit index arithmetic, one division per thread; all table reads first, then the loads of the rendered
+// samples, then the stores, so the periods overlap their latency.
+constexpr int kFixPeriods = 8;
+
 __global__ void __launch_bounds__(128) k_periodic_fix(PeriodicArgs a)
 {
     __shared__ double s_dp[4];
-    const uint32_t ci = blockIdx.y * blockDim.x + threadIdx.x, kk = blockIdx.x;
+    const uint32_t ci = blockIdx.y * blockDim.x + threadIdx.x, kkb = blockIdx.x * (uint32_t)kFixPeriods;
     double dp = 0.0;
     if (ci < min(*a.n_cands, (uint32_t)kPerMaxCands)) {
         const uint2 cand = a.cands[ci];
-        const uint32_t m = cand.x;
-        const uint64_t k = a.k0 + kk, g = k * a.L + m;
-        const uint32_t wf = period_warp_first(m, a.tile_len);
-        const uint64_t b = g / a.B - a.tab_blk0;
-        const uint32_t i = (uint32_t)(g % a.B);
-        float dre = 0.0f, dim = 0.0f;
-        bool any = false;
+        const uint32_t m = cand.x, wf = period_warp_first(m, a.tile_len);
+        const uint32_t B = (uint32_t)a.B, Lq = a.L / B, Lr = a.L % B;
+        const uint64_t g0 = (a.k0 + kkb) * (uint64_t)a.L + m;
+        uint32_t b[kFixPeriods], i[kFixPeriods];
+        b[0] = (uint32_t)(g0 / B - a.tab_blk0); i[0] = (uint32_t)(g0 % B);
+#pragma unroll
+        for (int u = 1; u < kFixPeriods; ++u) {
+            i[u] = i[u - 1] + Lr; b[u] = b[u - 1] + Lq;
+            if (i[u] >= B) { i[u] -= B; ++b[u]; }
+        }
+        float dre[kFixPeriods], dim[kFixPeriods];
+        float2 old[kFixPeriods];
+        bool any[kFixPeriods];
+#pragma unroll
+        for (int u = 0; u < kFixPeriods; ++u) { dre[u] = dim[u] = 0.0f; any[u] = false; }
         for (uint32_t rest = cand.y; rest; rest &= rest - 1u) {
             const uint32_t s = (uint32_t)__ffs((int)rest) - 1u;
-            const PerSat ps = a.sat[s];
-            const uint32_t ot = m >= ps.mstar ? 1u : 0u, ow = wf >= ps.mstar ? 1u : 0u;
-            const float Bv = a.yb[(size_t)s * a.L + m];
-            const SatCode cd = a.satcode[s];
-            const long long P = (long long)cd.epoch_period;
-            long long dk = ((long long)k - (long long)a.k_ref) % P;
-            if (dk < 0) dk += P;
-            const uint32_t ek = (uint32_t)(((long long)ps.e_ref + dk) % P);
-            const float sT = ((cd.epoch_bits >> ((ek + ot) % (uint32_t)P)) & 1ull) ? -1.0f : 1.0f;
-            const float sP = ((cd.epoch_bits >> ((ek + ot + (uint32_t)P - 1u) % (uint32_t)P)) & 1ull) ? -1.0f : 1.0f;
-            const float sM = ((cd.epoch_bits >> ((ek + ow) % (uint32_t)P)) & 1ull) ? -1.0f : 1.0f;
-            const float Y = a.ys[(size_t)s * a.L + m];
-            const float coef = (sT * (Y - Bv) + sP * Bv) - sM * Y;
-            if (coef == 0.0f) continue;
-            const BlockSat& r = a.tab[(size_t)b * a.n_sats + s];
-            const uint64_t ph = r.phi + (uint64_t)(i + 1) * (uint64_t)r.f;
-            float sn, cs;
-            accurate_sincos_cycles(ph, &sn, &cs);
-            dre = fmaf(coef * ps.amp, cs, dre);
-            dim = fmaf(coef * ps.amp, sn, dim);
-            any = true;
+            const uint32_t mstar = __ldg(&a.sat[s].mstar), e_ref = __ldg(&a.sat[s].e_ref);
+            const float amp = __ldg(&a.sat[s].amp);
+            const uint32_t ot = m >= mstar ? 1u : 0u, ow = wf >= mstar ? 1u : 0u;
+            const unsigned long long bits = __ldg(reinterpret_cast<const unsigned long long*>(&a.satcode[s].epoch_bits));
+            const uint32_t P = __ldg(&a.satcode[s].epoch_period);
+            const float Bv = __ldg(a.yb + (size_t)s * a.L + m), Y = __ldg(a.ys + (size_t)s * a.L + m);
+            // epoch of the period's slot 0: e_ref + (k - k_ref) mod P, stepped per period
+            const long long dk0 = (long long)(a.k0 + kkb) - (long long)a.k_ref;
+            uint32_t ek = (uint32_t)(dk0 >= 0 ? (uint64_t)dk0 % P : (P - (uint32_t)((uint64_t)(-dk0) % P)) % P);
+            ek = (ek + e_ref) % P;
+#pragma unroll
+            for (int u = 0; u < kFixPeriods; ++u) {
+                const uint32_t eT = ek + ot >= P ? ek + ot - P : ek + ot, eM = ek + ow >= P ? ek + ow - P : ek + ow;
+                const uint32_t eP = eT == 0u ? P - 1u : eT - 1u;
+                const float sT = ((bits >> eT) & 1ull) ? -1.0f : 1.0f, sP = ((bits >> eP) & 1ull) ? -1.0f : 1.0f;
+                const float sM = ((bits >> eM) & 1ull) ? -1.0f : 1.0f;
+                ek = ek + 1u == P ? 0u : ek + 1u;
+                if (kkb + u >= a.n_periods || (sT == sM && sP == sM)) continue;
+                const float coef = (sT * (Y - Bv) + sP * Bv) - sM * Y;
+                if (coef == 0.0f) continue;
+                const BlockSat* r = a.tab + (size_t)b[u] * a.n_sats + s;
+                const uint64_t ph = __ldg(reinterpret_cast<const unsigned long long*>(&r->phi)) +
+                                    (uint64_t)(i[u] + 1u) * (uint64_t)__ldg(reinterpret_cast<const long long*>(&r->f));
+                float sn, cs;
+                accurate_sincos_cycles(ph, &sn, &cs);
+                dre[u] = fmaf(coef * amp, cs, dre[u]);
+                dim[u] = fmaf(coef * amp, sn, dim[u]);
+                any[u] = true;
+            }
         }
-        if (any) {
-            float2* o = a.out + ((uint64_t)kk * a.L + m);
-            const float2 old = *o;
-            const float2 nw = make_float2(old.x + dre, old.y + dim);
-            *o = nw;
-            dp = ((double)nw.x * nw.x + (double)nw.y * nw.y) - ((double)old.x * old.x + (double)old.y * old.y);
-        }
+        float2* o = a.out + ((uint64_t)kkb * a.L + m);
+#pragma unroll
+        for (int u = 0; u < kFixPeriods; ++u)
+            if (any[u]) old[u] = o[(uint64_t)u * a.L];
+#pragma unroll
+        for (int u = 0; u < kFixPeriods; ++u)
+            if (any[u]) {
+                const float2 nw = make_float2(old[u].x + dre[u], old[u].y + dim[u]);
+                o[(uint64_t)u * a.L] = nw;
+                dp += ((double)nw.x * nw.x + (double)nw.y * nw.y) - ((double)old[u].x * old[u].x + (double)old[u].y * old[u].y);
+            }
     }
     if (a.power_sum) {
         for (int off = 16; off > 0; off >>= 1) dp += __shfl_xor_sync(0xffffffffu, dp, off);
@@ -385,7 +416,7 @@ uint32_t periodic_padded_sats(uint32_t n)
     return n <= 1 ? 1u : n <= 2 ? 2u : n <= 4 ? 4u : n <= 8 ? 8u : 0u;
 }
 
-void launch_synth_periodic(const PeriodicArgs& a, uint32_t ns_padded, uint32_t n_cands, cudaStream_t st)
+void launch_synth_periodic(const PeriodicArgs& a, uint32_t ns_padded, cudaStream_t st)
 {
     switch (ns_padded) {
     case 1: launch_periodic_t<1>(a, st); break;
@@ -394,8 +425,12 @@ void launch_synth_periodic(const PeriodicArgs& a, uint32_t ns_padded, uint32_t n
     case 8: launch_periodic_t<8>(a, st); break;
     default: fail(R4WB_ERR_INVALID_PARAMETER, "periodic path: %u satellites", ns_padded);
     }
+}
+
+void launch_periodic_fix(const PeriodicArgs& a, uint32_t n_cands, cudaStream_t st)
+{
     if (n_cands > 0 && a.n_periods > 0) {
-        k_periodic_fix<<<dim3(a.n_periods, (n_cands + 127) / 128), 128, 0, st>>>(a);
+        k_periodic_fix<<<dim3((a.n_periods + kFixPeriods - 1) / kFixPeriods, (n_cands + 127) / 128), 128, 0, st>>>(a);
         R4WB_LAUNCH_CHECK();
     }
 }

@@ -169,6 +169,16 @@ class GnssScenario:
         """0: k_synth rendered the last generate call, 1: the period-resident kernels did (diagnostic)."""
         return int(_lib.lib().r4wb_scenario_last_path(self._h))
 
+    def set_profiling(self, enabled: bool = True):
+        _lib.check(_lib.lib().r4wb_scenario_set_profiling(self._h, int(bool(enabled))))
+
+    def last_profile(self):
+        """{kernel: (summed CUDA-event ms, launches)} of the last generate call (profiling must be enabled)."""
+        ms = np.zeros(3, np.float64)
+        n = np.zeros(3, np.uint64)
+        _lib.check(_lib.lib().r4wb_scenario_last_profile(self._h, ms.ctypes.data_as(C.c_void_p), n.ctypes.data_as(C.c_void_p)))
+        return {k: (float(ms[i]), int(n[i])) for i, k in enumerate(("k_synth", "k_synth_periodic", "k_periodic_fix"))}
+
     def _debug_block_params(self, block: int, sat: int) -> np.ndarray:
         out = np.zeros(12, np.float64)
         _lib.check(_lib.lib().r4wb_debug_block_params(self._h, int(block), int(sat), out.ctypes.data_as(C.c_void_p)))
