@@ -254,6 +254,34 @@ uint64_t r4wb_pcps_guard_count(const r4wb_pcps* h);
 r4wb_error r4wb_pcps_set_profiling(r4wb_pcps* h, int enabled);
 r4wb_error r4wb_pcps_last_profile(const r4wb_pcps* h, double* ms, uint64_t* launches);
 
+/* ---- tracking channels: TrackingChannel, crates/r4w-core/src/waveform/gnss/tracking.rs ---- */
+/* TrackingChannel::new(prn, code_length, sample_rate, chipping_rate, initial_code_phase, initial_doppler) :107-153 plus the
+ * with_dll_bandwidth / with_pll_bandwidth builders :156-167 (<= 0: the reference defaults, 1 Hz and 15 Hz) */
+typedef struct r4wb_track_cfg {
+    double sample_rate, chipping_rate, initial_code_phase, initial_doppler, dll_bandwidth_hz, pll_bandwidth_hz;
+    uint64_t code_length;
+    uint8_t prn, pad[7];
+} r4wb_track_cfg;
+/* TrackingState, gnss/types.rs:187-210 */
+typedef struct r4wb_track_state {
+    double code_phase, carrier_freq_hz, carrier_phase_rad, prompt_i, prompt_q, cn0_dbhz;
+    uint64_t ms_count;
+    uint8_t prn, carrier_lock, code_lock, bit_sync, pad[4];
+} r4wb_track_state;
+typedef struct r4wb_tracker r4wb_tracker;   /* a bank of independent channels, state resident on the GPU */
+r4wb_error r4wb_track_create(const r4wb_track_cfg* cfgs, uint32_t n_channels, r4wb_tracker** out);
+void r4wb_track_destroy(r4wb_tracker* h);
+/* n_periods consecutive TrackingChannel::process(samples, code) calls (:177-313) on every channel.  Channel c reads
+ * samples[c * channel_stride + p * n_per_period ...] for period p (channel_stride = 0: all channels track the same
+ * stream) and the +-1 chips codes[c * code_stride ...]; out is [n_periods][n_channels], the state returned by each call. */
+r4wb_error r4wb_track_process(r4wb_tracker* h, const void* samples, r4wb_fmt fmt, r4wb_mem where, uint64_t n_per_period,
+                              uint64_t n_periods, uint64_t channel_stride, const int8_t* codes, uint64_t code_stride,
+                              r4wb_track_state* out);
+/* TrackingChannel::state :344-358 for every channel */
+r4wb_error r4wb_track_state_get(const r4wb_tracker* h, r4wb_track_state* out, uint32_t cap);
+/* TrackingChannel::nav_bits :339-342: *n = bits detected so far, the first min(cap, *n) copied to out */
+r4wb_error r4wb_track_nav_bits(const r4wb_tracker* h, uint32_t channel, int8_t* out, uint64_t cap, uint64_t* n);
+
 #ifdef __cplusplus
 }
 #endif

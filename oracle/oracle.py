@@ -21,7 +21,8 @@ def build(force: bool = False) -> str:
     """Compile the C restatement (gcc, a second or two)."""
     src = os.path.join(_HERE, "r4w_oracle.c")
     stale = (not os.path.exists(_SO)) or os.path.getmtime(_SO) < max(
-        os.path.getmtime(src), os.path.getmtime(os.path.join(_HERE, "r4w_oracle.h")))
+        os.path.getmtime(src), os.path.getmtime(os.path.join(_HERE, "r4w_oracle_track.c")),
+        os.path.getmtime(os.path.join(_HERE, "r4w_oracle.h")))
     if force or stale:
         subprocess.check_call(["make", "-C", _HERE, "-B", "libr4w_oracle.so"], stdout=subprocess.DEVNULL)
     return _SO
@@ -95,6 +96,16 @@ def lib():
         L.orc_saastamoinen_zenith_m.restype = d
         L.orc_to_int_format.argtypes = [vp, sz, C.c_int, vp]
         L.orc_to_int_format.restype = C.c_int
+        L.orc_track_new.argtypes = [C.c_uint8, sz, d, d, d, d]; L.orc_track_new.restype = vp
+        L.orc_track_free.argtypes = [vp]
+        L.orc_track_set_dll_bandwidth.argtypes = [vp, d]
+        L.orc_track_set_pll_bandwidth.argtypes = [vp, d]
+        L.orc_track_process.argtypes = [vp, vp, sz, vp, vp]
+        L.orc_track_state_get.argtypes = [vp, vp]
+        L.orc_track_nav_bits.argtypes = [vp, vp, sz]; L.orc_track_nav_bits.restype = sz
+        L.orc_loop_filter_2nd_run.argtypes = [d, d, d, sz]; L.orc_loop_filter_2nd_run.restype = d
+        L.orc_loop_filter_3rd_run.argtypes = [d, d, d, sz]; L.orc_loop_filter_3rd_run.restype = d
+        L.orc_dll_s_curve.argtypes = [d, sz, vp, vp]
         _lib = L
     return _lib
 
@@ -328,3 +339,71 @@ class OraclePcps:
         grid = np.zeros((self.num_bins(), int(self.p.code_length)), np.float64)
         lin = lib().orc_pcps_acquire_grid(C.byref(self.p), _ptr(x), x.size, _ptr(c), c.size, _ptr(grid))
         return grid, int(lin)
+
+
+# ---- tracking channel (r4w_oracle_track.c; gnss/tracking.rs) ------------------------------------------------------
+TRACK_STATE_DTYPE = np.dtype([("code_phase", "<f8"), ("carrier_freq_hz", "<f8"), ("carrier_phase_rad", "<f8"), ("prompt_i", "<f8"),
+                              ("prompt_q", "<f8"), ("cn0_dbhz", "<f8"), ("ms_count", "<u8"), ("prn", "u1"), ("carrier_lock", "u1"),
+                              ("code_lock", "u1"), ("bit_sync", "u1"), ("pad", "u1", (4,))])
+
+
+class OracleTrackingChannel:
+    """TrackingChannel (tracking.rs:107-358), f64, one code period per `process` call"""
+
+    def __init__(self, prn, code_length, sample_rate, chipping_rate, initial_code_phase, initial_doppler):
+        self._h = lib().orc_track_new(int(prn), int(code_length), float(sample_rate), float(chipping_rate),
+                                      float(initial_code_phase), float(initial_doppler))
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().orc_track_free(self._h)
+            self._h = None
+
+    def with_dll_bandwidth(self, bw):
+        lib().orc_track_set_dll_bandwidth(self._h, float(bw)); return self
+
+    def with_pll_bandwidth(self, bw):
+        lib().orc_track_set_pll_bandwidth(self._h, float(bw)); return self
+
+    def process(self, samples: np.ndarray, code: np.ndarray):
+        x = np.ascontiguousarray(samples, np.complex128)
+        c = np.ascontiguousarray(code, np.int8)
+        out = np.zeros(1, TRACK_STATE_DTYPE)
+        lib().orc_track_process(self._h, _ptr(x), x.size, _ptr(c), _ptr(out))
+        return out[0]
+
+    def run(self, samples: np.ndarray, code: np.ndarray, n_per_period: int, n_periods: int) -> np.ndarray:
+        """n_periods consecutive process calls -> structured array of the returned states"""
+        x = np.ascontiguousarray(samples, np.complex128)
+        c = np.ascontiguousarray(code, np.int8)
+        out = np.zeros(n_periods, TRACK_STATE_DTYPE)
+        for p in range(n_periods):
+            seg = x[p * n_per_period:(p + 1) * n_per_period]
+            lib().orc_track_process(self._h, _ptr(seg), seg.size, _ptr(c), C.c_void_p(out.ctypes.data + p * TRACK_STATE_DTYPE.itemsize))
+        return out
+
+    def state(self):
+        out = np.zeros(1, TRACK_STATE_DTYPE)
+        lib().orc_track_state_get(self._h, _ptr(out))
+        return out[0]
+
+    def nav_bits(self) -> np.ndarray:
+        n = lib().orc_track_nav_bits(self._h, None, 0)
+        out = np.zeros(int(n), np.int8)
+        if n:
+            lib().orc_track_nav_bits(self._h, _ptr(out), out.size)
+        return out
+
+
+def loop_filter_2nd_run(bw, T, disc, n) -> float:
+    return float(lib().orc_loop_filter_2nd_run(float(bw), float(T), float(disc), int(n)))
+
+
+def loop_filter_3rd_run(bw, T, disc, n) -> float:
+    return float(lib().orc_loop_filter_3rd_run(float(bw), float(T), float(disc), int(n)))
+
+
+def dll_s_curve(el_spacing: float, num_points: int):
+    e = np.zeros(num_points); d = np.zeros(num_points)
+    lib().orc_dll_s_curve(float(el_spacing), int(num_points), _ptr(e), _ptr(d))
+    return e, d

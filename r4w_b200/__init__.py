@@ -5,5 +5,6 @@ from .config import (GnssScenarioConfig, SatelliteConfig, ReceiverConfig, Enviro
                      LlaPosition, AntennaPattern, ReceiverTrajectory, load_config, loads_config)
 from ._lib import R4wB200Error, init, kernel_launches, device_count, version, build  # noqa: F401
 from .scenario import GnssScenario, SatelliteStatus  # noqa: F401
+from .tracking import TrackingChannel, TrackerBank, TrackingState  # noqa: F401
 from .acquisition import (PcpsAcquisition, AcquisitionResult, AcquisitionGrid, e1_code, e1c_secondary,  # noqa: F401
                           e1c_replica, gps_ca_code)

@@ -77,6 +77,11 @@ SYMBOLS = {
     "r4wb_pcps_acquire_batch": (_int, [_vp, _vp, _int, _int, _u64, _u64, _u64, _vp, _u64, _vp, _u32, _vp]),
     "r4wb_pcps_acquire_grid": (_int, [_vp, _vp, _int, _u64, _vp, _u64, _vp, _u64]),
     "r4wb_pcps_guard_count": (_u64, [_vp]),
+    "r4wb_track_create": (_int, [_vp, _u32, C.POINTER(_vp)]),
+    "r4wb_track_destroy": (None, [_vp]),
+    "r4wb_track_process": (_int, [_vp, _vp, _int, _int, _u64, _u64, _u64, _vp, _u64, _vp]),
+    "r4wb_track_state_get": (_int, [_vp, _vp, _u32]),
+    "r4wb_track_nav_bits": (_int, [_vp, _u32, _vp, _u64, C.POINTER(_u64)]),
     "r4wb_pcps_set_profiling": (_int, [_vp, _int]),
     "r4wb_pcps_last_profile": (_int, [_vp, _vp, _vp]),
     # test hook, not part of the drop-in surface

@@ -6,6 +6,7 @@
 
 #include "acq.cuh"
 #include "synth.cuh"
+#include "track.cuh"
 
 namespace r4wb {
 
@@ -53,6 +54,7 @@ using namespace r4wb;
 
 struct r4wb_scenario { Scenario impl; explicit r4wb_scenario(const r4wb_scenario_cfg& c) : impl(c) {} };
 struct r4wb_pcps { Pcps impl; r4wb_pcps(uint64_t n, double fs) : impl(n, fs) {} };
+struct r4wb_tracker { TrackerBank impl; r4wb_tracker(const r4wb_track_cfg* c, uint32_t n) : impl(c, n) {} };
 
 extern "C" {
 
@@ -289,6 +291,39 @@ r4wb_error r4wb_pcps_acquire_grid(r4wb_pcps* h, const void* input, r4wb_fmt fmt,
 {
     if (!h || !input || !code || !power_out) { t_error = "NULL argument"; return R4WB_ERR_NULL_POINTER; }
     return guard([&] { h->impl.acquire_grid(input, fmt, n_input, code, code_len, power_out, cap); });
+}
+
+
+// ---- tracking channels
+r4wb_error r4wb_track_create(const r4wb_track_cfg* cfgs, uint32_t n_channels, r4wb_tracker** out)
+{
+    if (!cfgs || !out) { t_error = "cfgs/out is NULL"; return R4WB_ERR_NULL_POINTER; }
+    *out = nullptr;
+    return guard([&] {
+        require_device();
+        *out = new r4wb_tracker(cfgs, n_channels);
+    });
+}
+
+void r4wb_track_destroy(r4wb_tracker* h) { delete h; }
+
+r4wb_error r4wb_track_process(r4wb_tracker* h, const void* samples, r4wb_fmt fmt, r4wb_mem where, uint64_t n_per_period, uint64_t n_periods,
+                              uint64_t channel_stride, const int8_t* codes, uint64_t code_stride, r4wb_track_state* out)
+{
+    if (!h) { t_error = "handle is NULL"; return R4WB_ERR_NULL_POINTER; }
+    return guard([&] { h->impl.process(samples, fmt, where, n_per_period, n_periods, channel_stride, codes, code_stride, out); });
+}
+
+r4wb_error r4wb_track_state_get(const r4wb_tracker* h, r4wb_track_state* out, uint32_t cap)
+{
+    if (!h || !out) { t_error = "handle/out is NULL"; return R4WB_ERR_NULL_POINTER; }
+    return guard([&] { h->impl.state(out, cap); });
+}
+
+r4wb_error r4wb_track_nav_bits(const r4wb_tracker* h, uint32_t channel, int8_t* out, uint64_t cap, uint64_t* n)
+{
+    if (!h || !n) { t_error = "handle/n is NULL"; return R4WB_ERR_NULL_POINTER; }
+    return guard([&] { *n = h->impl.nav_bits(channel, out, cap); });
 }
 
 }  // extern "C"
