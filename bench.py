@@ -298,6 +298,37 @@ def run_b200(args):
     torch.cuda.synchronize()
     ms_acq_e2e = (time.perf_counter() - ts) * 1e3 / e2e_steps
 
+    # ---- tracking channels, rank 0, outside the timed step: one E1C channel per satellite of the scenario over
+    # the first second of the rendered stream (250 code periods of 20 000 samples), device-resident input
+    track = None
+    if rank == 0 and not args.no_track:
+        # replica per half-chip (E1C chips x BOC(1,1) sub-carrier): 8 184 "chips" at 2.046 Mchip/s, so the reference's per-chip
+        # tracker (gnss/tracking.rs) sees the sub-carrier; start values from the acquisition of the first snapshot
+        e1c = np.stack([np.repeat(R.e1_code(1, p).astype(np.int8), 2) * np.tile(np.array([1, -1], np.int8), 4092) for p in prns])
+        chans = [dict(prn=p, code_length=8184, sample_rate=5e6, chipping_rate=2.046e6,
+                      initial_code_phase=float(((CODE_LENGTH - int(table[0, c, 2])) % CODE_LENGTH) * 2.046e6 / 5e6),
+                      initial_doppler=float(table[0, c, 3])) for c, p in enumerate(prns)]
+        n_per, n_p = CODE_LENGTH, 250
+        R.TrackerBank(chans).process(iq, e1c, n_per, 8)            # warm-up
+        bank = R.TrackerBank(chans)
+        torch.cuda.synchronize()
+        ts = time.perf_counter()
+        st = bank.process(iq, e1c, n_per, n_p)
+        dt = time.perf_counter() - ts
+        track = {"metric": "tracking_channel_periods_per_s", "value": len(prns) * n_p / dt, "unit": "channel-periods/s",
+                 "channels": len(prns), "periods": n_p, "samples_per_period": n_per, "ms": dt * 1e3,
+                 "api": "r4wb_track_process(..., R4WB_MEM_DEVICE): states D2H inside the timed call",
+                 "locked_channels": int(np.sum(st["code_lock"][-1]))}
+        if not args.no_cpu_baseline and world == 1:
+            from oracle import oracle as O
+            O.build()
+            xs = iq[: 25 * n_per].cpu().numpy()
+            tc = time.perf_counter()
+            O.OracleTrackingChannel(prns[0], 8184, 5e6, 2.046e6, chans[0]["initial_code_phase"], chans[0]["initial_doppler"]).run(xs, e1c[0], n_per, 25)
+            dtc = time.perf_counter() - tc
+            track["cpu_baseline"] = {"value": 25 / dtc, "unit": "channel-periods/s", "cores": 1, "kind": "port",
+                                     "sample": f"1 channel x 25 periods ({dtc:.2f} s wall), oracle port, 1 thread"}
+
     # ---- max over ranks
     def rmax(v):
         if world == 1:
@@ -376,6 +407,8 @@ def run_b200(args):
             "gpu_launches": int(launches),
             "clocks": clk,
         }
+        if track is not None:
+            line["track"] = track
         if cpu is not None:
             line["cpu_baseline"] = cpu[0]
             line["acq"]["cpu_baseline"] = cpu[1]
@@ -392,6 +425,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--acq-snapshots", type=int, default=0, help="snapshots per GPU per step (0 = the whole segment)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-track", action="store_true", help="skip the tracking-channel leg (SURVEY.md section 8 f2)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -73,10 +73,13 @@ class TrackerBank:
         _lib.check(_lib.lib().r4wb_track_create(pods, n, C.byref(self._h)))
 
     def __del__(self):
-        h = getattr(self, "_h", None)
-        if h:
-            _lib.lib().r4wb_track_destroy(h)
-            self._h = None
+        try:
+            h = getattr(self, "_h", None)
+            if h:
+                _lib.lib().r4wb_track_destroy(h)
+                self._h = None
+        except Exception:       # interpreter shutdown
+            pass
 
     def channels(self) -> int:
         return self._n
