@@ -17,7 +17,7 @@ constexpr int kFracBits = 46;         // fixed-point fraction of the half-chip p
 constexpr int kTBits = 24;            // fraction bits of "oversamples since boundary" (8 integer bits: up to 256 oversamples)
 constexpr int kMaxSats = 64;
 constexpr int kMaxSegments = 512;
-constexpr int kYStride = 81;          // boundary-age classes per sign pattern (odd: spreads patterns over banks)
+constexpr int kMaxYStride = 241;      // boundary-age classes per sign pattern: < 4 S + 1 (S <= 59.9 oversamples per half-chip at 15.3 MHz)
 constexpr int kPerBits = 2 * kCodeLen;   // half-chips of one Galileo E1 primary-code period (the longest supported)
 constexpr int kPerWords = 260;        // 8184 sign bits + 64 wrap-around bits, padded to a multiple of 4 words
 constexpr int kSynthThreads = 256;
@@ -82,6 +82,7 @@ struct ScenConst {
     uint32_t cj[8];                 // round(j * S * 2^24)
     uint32_t dsum0;                 // (cj[1] >> 24) + (cj[2] >> 24) + (cj[3] >> 24)
     uint32_t lut_den;               // D when the boundary-age class can be read from a D-entry table (0: compute it)
+    uint32_t ystride;               // row stride of ytab: smallest odd number >= the number of boundary-age classes (81 at 5 MHz)
     float noise_std;
     uint64_t seed;
 };
@@ -135,9 +136,10 @@ struct SynthArgs {
     const SatCode* satcode;    // [n_sats]
     const float* taps;         // [64] h[k] (f32), [63] = 0
     const float* etab;         // [64] E[d] = sum_{k<=d} h[k]  (E[62] = E[63] = 1)
-    const float* ytab;         // [32][kYStride] collapsed-FIR outputs per (sign pattern, boundary-age class)
+    const float* ytab;         // [32][ystride] collapsed-FIR outputs per (sign pattern, boundary-age class)
     const uint8_t* clslut;     // [lut_den, padded to 16] boundary-age class of half-chip fraction bin q (swizzled, see cls_lut_index)
     uint32_t lut_den;
+    uint32_t ystride;
     void* out;                 // cf32 or cf64, out[0] <-> sample out_first
     double* power_sum;         // optional accumulator of |s|^2
     uint64_t out_first, out_n; // only samples in [out_first, out_first + out_n) are written
@@ -172,7 +174,7 @@ struct ScenarioModel {
     std::vector<uint32_t> cfg_index;    // virtual satellite -> index into cfg_sats (GalileoE1OS expands to two)
     float taps_f[64];
     float etab_f[64];
-    std::vector<float> ytab;            // [32][kYStride]
+    std::vector<float> ytab;            // [32][sc.ystride]
     std::vector<uint8_t> clslut;        // [lut_den padded to 16]
     int tile_k = 10;                    // samples per tile = 256 threads * 2 * tile_k
     uint32_t nw64 = 0;
@@ -202,7 +204,7 @@ inline size_t fmt_bytes(r4wb_fmt fmt)
     switch (fmt) { case R4WB_FMT_CF64: return 16; case R4WB_FMT_CF32: return 8; case R4WB_FMT_CI16: return 4; default: return 2; }
 }
 
-size_t synth_smem_bytes(uint32_t n_sats, uint32_t nw64, uint32_t lut_den);
+size_t synth_smem_bytes(uint32_t n_sats, uint32_t nw64, uint32_t lut_den, uint32_t ystride);
 int synth_tile_samples(int K);
 
 class Scenario {

@@ -153,7 +153,7 @@ SynthArgs Scenario::base_args(const BlockSat* tab, const BlockHdr* hdr, uint64_t
 {
     const ScenConst& sc = md_.sc;
     SynthArgs a{};
-    a.tab = tab; a.hdr = hdr; a.perbits = d_perbits_.p; a.satcode = d_satcode_.p; a.taps = d_taps_.p; a.etab = d_etab_.p; a.ytab = d_ytab_.p; a.clslut = d_clslut_.p; a.lut_den = sc.lut_den;
+    a.tab = tab; a.hdr = hdr; a.perbits = d_perbits_.p; a.satcode = d_satcode_.p; a.taps = d_taps_.p; a.etab = d_etab_.p; a.ytab = d_ytab_.p; a.clslut = d_clslut_.p; a.lut_den = sc.lut_den; a.ystride = sc.ystride;
     const uint32_t tile = (uint32_t)synth_tile_samples(md_.tile_k);
     a.tiles_per_block = (uint32_t)((max_block_n + tile - 1) / tile);
     a.n_sats = sc.n_sats; a.nw64 = md_.nw64; a.flags = sc.flags;
@@ -186,7 +186,7 @@ void Scenario::launch_synth(const BlockSat* tab, const BlockHdr* hdr, const Tile
         R4WB_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
     }
     const int tile_k = md_.tile_k;
-    const size_t smem = synth_smem_bytes(a.n_sats, a.nw64, a.lut_den);
+    const size_t smem = synth_smem_bytes(a.n_sats, a.nw64, a.lut_den, a.ystride);
     static int per_sm_cache[2][5] = {};                      // [tile_k == 5][fmt], for the smem size of the first query
     static size_t per_sm_smem[2][5] = {};
     int& cached = per_sm_cache[tile_k == 5][(int)fmt];

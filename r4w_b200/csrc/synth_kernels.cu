@@ -19,63 +19,7 @@
 namespace r4wb {
 
 // ----------------------------------------------------------------------------------------------
-// prologue kernels
-__global__ void k_block_params(ScenConst sc, const SatConst* __restrict__ sats, const PhaseSegment* __restrict__ segs,
-                               uint64_t blk0, uint32_t nblk, BlockSat* __restrict__ tab, BlockHdr* __restrict__ hdr)
-{
-    const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (uint64_t)nblk * sc.n_sats) return;
-    const uint32_t tb = (uint32_t)(idx / sc.n_sats), s = (uint32_t)(idx % sc.n_sats);
-    const uint64_t first = (blk0 + tb) * sc.B;
-    const uint64_t rem = sc.total - first;
-    const uint32_t n = (uint32_t)(rem < sc.B ? rem : sc.B);
-    BlockSat o;
-    fill_block_sat(sc, sats[s], segs, first, n, /*visible samples so far (constant visibility)*/ first, o);
-    o.prev = tb > 0 ? (int32_t)((tb - 1) * sc.n_sats + s) : -1;
-    if (!sats[s].static_phase) o.phi = (o.flags & 1u) ? block_advance(o) : 0ull;   // scanned by k_phase_scan
-    tab[idx] = o;
-    if (s == 0) hdr[tb] = BlockHdr{first, n, 0};
-}
-
-// One CTA per satellite: exclusive scan of the per-block phase advance (dynamic satellites) and of the
-// "last visible block" pointer (satellites whose visibility can change).  Table must start at block 0.
-__global__ void __launch_bounds__(1024) k_phase_scan(const SatConst* __restrict__ sats, uint32_t n_sats, uint32_t nblk,
-                                                      BlockSat* __restrict__ tab)
-{
-    __shared__ uint64_t s_sum[1024];
-    __shared__ int s_last[1024];
-    const uint32_t s = blockIdx.x, t = threadIdx.x;
-    const bool dynamic = !sats[s].static_phase;
-    const uint32_t chunk = (nblk + 1023u) / 1024u;
-    const uint32_t lo = t * chunk, hi = min(nblk, lo + chunk);
-    uint64_t sum = 0;
-    int last = -1;
-    for (uint32_t b = lo; b < hi; ++b) {
-        const BlockSat& e = tab[(size_t)b * n_sats + s];
-        if (dynamic) sum += e.phi;
-        if (e.flags & 1u) last = (int)b;
-    }
-    s_sum[t] = sum;
-    s_last[t] = last;
-    __syncthreads();
-    for (int off = 1; off < 1024; off <<= 1) {
-        uint64_t v = 0;
-        int l = -1;
-        if ((int)t >= off) { v = s_sum[t - off]; l = s_last[t - off]; }
-        __syncthreads();
-        if ((int)t >= off) { s_sum[t] += v; s_last[t] = max(s_last[t], l); }
-        __syncthreads();
-    }
-    uint64_t run = t > 0 ? s_sum[t - 1] : 0ull;
-    int prev = t > 0 ? s_last[t - 1] : -1;
-    for (uint32_t b = lo; b < hi; ++b) {
-        BlockSat& e = tab[(size_t)b * n_sats + s];
-        const uint64_t adv = e.phi;
-        if (dynamic) { e.phi = run; run += adv; }
-        e.prev = prev >= 0 ? (int32_t)((uint32_t)prev * n_sats + s) : -1;
-        if (e.flags & 1u) prev = (int)b;
-    }
-}
+// (k_block_params / k_phase_scan: synth_prologue.cu, compiled without FMA contraction)
 
 // Per (table block, chunk, satellite): everything k_synth needs about the tile that costs latency to derive (f64 phasor
 // of the rotation step, link to the previous block, the collapsed block-start fix-up), so the synthesis kernel's per-tile
@@ -88,7 +32,7 @@ __global__ void k_tile_params(SynthArgs a, uint32_t tb_begin, uint32_t tb_count,
     const uint32_t s = (uint32_t)(idx % a.n_sats);
     const uint32_t tile = (uint32_t)(idx / a.n_sats);
     const uint32_t tb = tb_begin + tile / a.tiles_per_block, chunk = tile % a.tiles_per_block;
-    const SynthK KK = make_synth_k(a.delta46, a.kmul, a.cj, a.dsum0, a.spc, a.lut_den);
+    const SynthK KK = make_synth_k(a.delta46, a.kmul, a.cj, a.dsum0, a.spc, a.lut_den, a.ystride);
     const BlockSat* row = a.tab + (size_t)tb * a.n_sats;
     const BlockHdr hd = a.hdr[tb];
     TileRec r;
@@ -122,13 +66,13 @@ struct SynthSmem {
     float* ytab; float* taps; float* etab; uint32_t* per; TileRec* trec; uint2* t64; uint32_t* w32; uint8_t* clslut;
 };
 
-__device__ __forceinline__ SynthSmem carve_smem(unsigned char* raw, uint32_t n_sats, uint32_t nw64)
+__device__ __forceinline__ SynthSmem carve_smem(unsigned char* raw, uint32_t n_sats, uint32_t nw64, uint32_t ystride)
 {
     SynthSmem m;
-    m.ytab = reinterpret_cast<float*>(raw);                                   // [32][kYStride]
-    m.taps = m.ytab + 32 * kYStride;                                          // [64]
+    m.ytab = reinterpret_cast<float*>(raw);                                   // [32][ystride]
+    m.taps = m.ytab + 32 * ystride;                                          // [64]
     m.etab = m.taps + 64;                                                     // [64]
-    size_t off = ((size_t)(32 * kYStride + 128) * 4 + 15) & ~(size_t)15;
+    size_t off = ((size_t)(32 * ystride + 128) * 4 + 15) & ~(size_t)15;
     m.per = reinterpret_cast<uint32_t*>(raw + off);                           // [n_sats][kPerWords]
     off += (size_t)n_sats * kPerWords * 4;
     m.trec = reinterpret_cast<TileRec*>(raw + off);                           // [n_sats]
@@ -180,15 +124,15 @@ __global__ void __launch_bounds__(kThreads, K <= 5 ? 3 : 2) k_synth(SynthArgs a)
 {
     constexpr int TILE = kThreads * 2 * K;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const SynthSmem sm = carve_smem(smem_raw, a.n_sats, a.nw64);
+    const SynthSmem sm = carve_smem(smem_raw, a.n_sats, a.nw64, a.ystride);
     __shared__ float s_pow[kThreads / 32];
 
     const uint32_t tid = threadIdx.x, lane = tid & 31u;
-    const SynthK KK = make_synth_k(a.delta46, a.kmul, a.cj, a.dsum0, a.spc, a.lut_den);
+    const SynthK KK = make_synth_k(a.delta46, a.kmul, a.cj, a.dsum0, a.spc, a.lut_den, a.ystride);
     const PhiloxKeys PK = philox_keys(a.seed);
 
     // kernel-lifetime tables
-    for (uint32_t k = tid; k < 32 * kYStride; k += kThreads) sm.ytab[k] = a.ytab[k];
+    for (uint32_t k = tid; k < 32 * a.ystride; k += kThreads) sm.ytab[k] = a.ytab[k];
     for (uint32_t k = tid; k < 64; k += kThreads) { sm.taps[k] = a.taps[k]; sm.etab[k] = a.etab[k]; }
     for (uint32_t k = tid; k < a.n_sats * kPerWords; k += kThreads) sm.per[k] = a.perbits[k];
     for (uint32_t k = tid; k < ((a.lut_den + 15u) >> 4); k += kThreads)
@@ -360,7 +304,7 @@ static int max_blocks_t(size_t smem)
 // K = 5 (tuning hook) exists for the float formats only
 void launch_synth_kernel(const SynthArgs& a, int K, r4wb_fmt fmt, int grid, cudaStream_t st)
 {
-    const size_t smem = synth_smem_bytes(a.n_sats, a.nw64, a.lut_den);
+    const size_t smem = synth_smem_bytes(a.n_sats, a.nw64, a.lut_den, a.ystride);
     if (smem > 200 * 1024) fail(R4WB_ERR_NOT_SUPPORTED, "scenario needs %zu bytes of shared memory per CTA", smem);
     if (K == 5 && fmt == R4WB_FMT_CF32) return launch_synth_t<5, R4WB_FMT_CF32>(a, grid, smem, st);
     if (K == 5 && fmt == R4WB_FMT_CF64) return launch_synth_t<5, R4WB_FMT_CF64>(a, grid, smem, st);
@@ -386,23 +330,6 @@ int synth_max_blocks_per_sm(int K, r4wb_fmt fmt, size_t smem)
     case R4WB_FMT_CU8: return max_blocks_t<10, R4WB_FMT_CU8>(smem);
     default: return max_blocks_t<10, R4WB_FMT_CF32>(smem);
     }
-}
-
-void launch_block_params(const ScenConst& sc, const SatConst* d_sats, const PhaseSegment* d_segs, uint64_t blk0, uint32_t nblk,
-                         BlockSat* d_tab, BlockHdr* d_hdr, cudaStream_t st)
-{
-    const uint64_t total = (uint64_t)nblk * sc.n_sats;
-    if (total == 0) return;
-    const int threads = 128;
-    k_block_params<<<(unsigned)((total + threads - 1) / threads), threads, 0, st>>>(sc, d_sats, d_segs, blk0, nblk, d_tab, d_hdr);
-    R4WB_LAUNCH_CHECK();
-}
-
-void launch_phase_scan(const SatConst* d_sats, uint32_t n_sats, uint32_t nblk, BlockSat* d_tab, cudaStream_t st)
-{
-    if (nblk == 0 || n_sats == 0) return;
-    k_phase_scan<<<n_sats, 1024, 0, st>>>(d_sats, n_sats, nblk, d_tab);
-    R4WB_LAUNCH_CHECK();
 }
 
 }  // namespace r4wb

@@ -335,7 +335,7 @@ struct SynthK {
     uint64_t step32;            // half-chips per 2*kSynthThreads samples, 32.32 fixed
     uint32_t d8_32;             // half-chips per output sample, 0.32 fixed (< 1)
     uint32_t kmul, c1, c2, c3, dsum0;
-    uint32_t lut_den;
+    uint32_t lut_den, ystride;
     double spc;
 };
 
@@ -343,14 +343,14 @@ struct SynthK {
 // (a fixed stride of 16 * 227 mod 20000 between lanes at 5 MHz) spread over the banks
 R4WB_HD uint32_t cls_lut_index(uint32_t q) { return q ^ ((q >> 6) & 0xcu); }
 
-R4WB_HD SynthK make_synth_k(uint64_t delta46, uint32_t kmul, const uint32_t* cj, uint32_t dsum0, double spc, uint32_t lut_den)
+R4WB_HD SynthK make_synth_k(uint64_t delta46, uint32_t kmul, const uint32_t* cj, uint32_t dsum0, double spc, uint32_t lut_den, uint32_t ystride)
 {
     SynthK k;
     k.delta46 = delta46;
     k.d8 = delta46 * (uint64_t)kOversample;
     k.step32 = (k.d8 * (uint64_t)(2 * kSynthThreads)) >> (kFracBits - 32);
     k.d8_32 = (uint32_t)(k.d8 >> (kFracBits - 32));
-    k.kmul = kmul; k.c1 = cj[1]; k.c2 = cj[2]; k.c3 = cj[3]; k.dsum0 = dsum0; k.lut_den = lut_den;
+    k.kmul = kmul; k.c1 = cj[1]; k.c2 = cj[2]; k.c3 = cj[3]; k.dsum0 = dsum0; k.lut_den = lut_den; k.ystride = ystride;
     k.spc = spc;
     return k;
 }
@@ -534,7 +534,7 @@ struct SlowCtx {
 // One satellite's contribution to the NK sample pairs thread `tid` owns in a tile: pair k = samples
 // (i_begin + 2 tid + 2 kSynthThreads k, +1).  ar[k] / ai[k] accumulate (re_a, re_b) / (im_a, im_b).
 //   t64   [nw64] per-tile sign table as overlapping 64-bit windows (word k = bits 32k .. 32k+63)
-//   ytab  [32][kYStride] collapsed-FIR outputs per (sign pattern, boundary-age class)
+//   ytab  [32][K.ystride] collapsed-FIR outputs per (sign pattern, boundary-age class)
 //   yfix  first 8 outputs of the block when its window reaches into a block with another delay (flags bit3)
 //   GENERAL = false: no ambiguity checks, phasor recurrence, DYN compile-time (the common case, straight-line code)
 //   GENERAL = true:  checks / per-sample sincos / varying Doppler selected at run time from ts.flags
@@ -594,7 +594,7 @@ R4WB_HD void sat_accumulate_t(const TileSat& ts, const SynthK& K, const uint2* _
         const uint2 w = *reinterpret_cast<const uint2*>(reinterpret_cast<const unsigned char*>(t64) + ((hi >> 2) & 0x3ffffff8u));
         const uint32_t pa = funnel_r(w.x, w.y, hi) & 31u;
         const uint32_t pb = funnel_rc(w.x, w.y, (hi & 31u) + (hib - hi)) & 31u;
-        float2 y = make_float2(ytab[pa * (uint32_t)kYStride + cls_a], ytab[pb * (uint32_t)kYStride + cls_b]);
+        float2 y = make_float2(ytab[pa * K.ystride + cls_a], ytab[pb * K.ystride + cls_b]);
         if (check) {
             const uint32_t m = (1u << kTBits) - 1u, e = ts.eps_t;
             const bool amb_a = ((ta0 + e) & m) < 2 * e || ((ta1 + e) & m) < 2 * e || ((ta2 + e) & m) < 2 * e || ((ta3 + e) & m) < 2 * e;

@@ -283,7 +283,6 @@ ScenarioModel::ScenarioModel(const r4wb_scenario_cfg& c_in) : cfg(c_in)
     // that sum (minus its minimum) names the age class.  Entry = s_4 + sum_j (s_j - s_{j+1}) E[min(d_j, 62)],
     // evaluated in f64 and rounded once.
     sc.dsum0 = (sc.cj[1] >> kTBits) + (sc.cj[2] >> kTBits) + (sc.cj[3] >> kTBits);
-    ytab.assign((size_t)32 * kYStride, 0.0f);
     {
         std::vector<uint64_t> starts{0};
         const uint64_t one = 1ull << kTBits;
@@ -291,17 +290,27 @@ ScenarioModel::ScenarioModel(const r4wb_scenario_cfg& c_in) : cfg(c_in)
             for (uint64_t n = 1; n * one < (uint64_t)sc.kmul + sc.cj[j] + one; ++n)
                 if (n * one >= sc.cj[j] && n * one - sc.cj[j] < sc.kmul) starts.push_back(n * one - sc.cj[j]);
         std::sort(starts.begin(), starts.end());
+        // classes are numbered 0 .. (steps of d_0 + d_1 + d_2 + d_3 over one half-chip) <= 4 S; odd row stride spreads the
+        // sign patterns over the shared-memory banks (81 at 5 MHz)
+        uint32_t max_cls = 0;
+        for (uint64_t t0 : starts) {
+            uint32_t dsum = 0;
+            for (int j = 0; j < 4; ++j) dsum += (uint32_t)((t0 + sc.cj[j]) >> kTBits);
+            max_cls = std::max(max_cls, dsum - sc.dsum0);
+        }
+        if (max_cls >= (uint32_t)kMaxYStride) fail(R4WB_ERR_NOT_SUPPORTED, "FIR age class %u out of range", max_cls);
+        sc.ystride = (max_cls + 2u) | 1u;
+        ytab.assign((size_t)32 * sc.ystride, 0.0f);
         for (uint64_t t0 : starts) {
             uint32_t d[4], dsum = 0;
             for (int j = 0; j < 4; ++j) { d[j] = (uint32_t)((t0 + sc.cj[j]) >> kTBits); dsum += d[j]; }
-            dsum -= d[0] * 0 + sc.dsum0;
-            if (dsum >= (uint32_t)kYStride) fail(R4WB_ERR_NOT_SUPPORTED, "FIR age class %u out of range", dsum);
+            dsum -= sc.dsum0;
             for (uint32_t pat = 0; pat < 32; ++pat) {
                 double sgn[kJ + 1];
                 for (int j = 0; j <= kJ; ++j) sgn[j] = ((pat >> (kJ - j)) & 1u) ? -1.0 : 1.0;
                 double y = sgn[kJ];
                 for (int j = 0; j < kJ; ++j) y += (sgn[j] - sgn[j + 1]) * etab[d[j] < 62u ? d[j] : 62u];
-                ytab[(size_t)pat * kYStride + dsum] = (float)y;
+                ytab[(size_t)pat * sc.ystride + dsum] = (float)y;
             }
         }
     }
@@ -321,7 +330,7 @@ ScenarioModel::ScenarioModel(const r4wb_scenario_cfg& c_in) : cfg(c_in)
             uint32_t dsum = 0;
             for (int j = 0; j < 4; ++j) dsum += (uint32_t)floorl(t0 + (long double)j * Sl);
             dsum -= sc.dsum0;
-            if (dsum >= (uint32_t)kYStride) fail(R4WB_ERR_NOT_SUPPORTED, "FIR age class %u out of range", dsum);
+            if (dsum >= sc.ystride) fail(R4WB_ERR_NOT_SUPPORTED, "FIR age class %u out of range", dsum);
             clslut[cls_lut_index(q)] = (uint8_t)dsum;
         }
     } else {
@@ -414,9 +423,9 @@ void SeqState::advance(const ScenarioModel& md, const std::vector<BlockSat>& tab
     }
 }
 
-size_t synth_smem_bytes(uint32_t n_sats, uint32_t nw64, uint32_t lut_den)
+size_t synth_smem_bytes(uint32_t n_sats, uint32_t nw64, uint32_t lut_den, uint32_t ystride)
 {
-    size_t b = ((size_t)(32 * kYStride + 128) * 4 + 15) & ~(size_t)15;   // ytab, taps, etab
+    size_t b = ((size_t)(32 * ystride + 128) * 4 + 15) & ~(size_t)15;   // ytab, taps, etab
     b += (size_t)n_sats * kPerWords * 4;
     b += (size_t)n_sats * sizeof(TileRec);
     b += (size_t)n_sats * nw64 * 8;

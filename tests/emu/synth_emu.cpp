@@ -74,7 +74,7 @@ struct Emu {
         constexpr int kThreads = kSynthThreads;
         const uint32_t TILE = (uint32_t)synth_tile_samples(K);
         const uint32_t tiles_per_block = (uint32_t)((max_block_n + TILE - 1) / TILE);
-        const SynthK KK = make_synth_k(sc.delta46, sc.kmul, sc.cj, sc.dsum0, sc.spc, sc.lut_den);
+        const SynthK KK = make_synth_k(sc.delta46, sc.kmul, sc.cj, sc.dsum0, sc.spc, sc.lut_den, sc.ystride);
         std::vector<TileSat> tsat(std::max(1u, ns));
         std::vector<uint32_t> w32((size_t)std::max(1u, ns) * (nw64 + 1));
         std::vector<uint2> t64((size_t)std::max(1u, ns) * nw64);

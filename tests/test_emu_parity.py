@@ -217,3 +217,19 @@ def test_other_signals_replay_matches_oracle(oracle, emu, case):
         got = emu.EmuScenario(cfg, noise=False).generate_range(first, n)
         want = oracle.OracleScenario(cfg, noise=False).generate_range(first, n)
         assert _relrms(got, want) <= TOL
+
+
+@pytest.mark.parametrize("fs", [4_000_000.0, 4_092_000.0, 8_000_000.0, 12_500_000.0])
+def test_other_sample_rates_replay_matches_oracle(oracle, emu, fs):
+    """sample rates other than the configs' 5 MHz: samples per half-chip S = 4 fs / 1.023e6 changes the number of boundary-age
+    classes (4 S: 63 at 4 MHz, 196 at 12.5 MHz; row stride of the collapsed-FIR table follows), the code period in samples
+    and, at 4.092 MHz (exactly 4 samples per chip), puts every sample ON a chip boundary (literal-expression path)"""
+    for name in ("e1c_8prn_20s_clean", "e1c_8prn_60s_cn34_orbital"):
+        cfg = _cfg(name).copy()
+        cfg.output.sample_rate = fs
+        cfg.output.lpf_cutoff_hz = 0.0                     # -> fs / 2 (scenario.rs:210-214)
+        B = int(np.ceil(fs * 0.001))
+        first, n = 500 * B - 7, B + 13
+        got = emu.EmuScenario(cfg, noise=False).generate_range(first, n)
+        want = oracle.OracleScenario(cfg, noise=False).generate_range(first, n)
+        assert _relrms(got, want) <= TOL

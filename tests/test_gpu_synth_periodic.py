@@ -102,3 +102,23 @@ def test_periodic_device_output_full_config(gpu, monkeypatch):
     assert float((a - b).abs().max()) <= 2e-4
     assert pa == pytest.approx(sb.last_power_sum(), rel=1e-6)
     assert float(torch.view_as_real(a).square().sum(dtype=torch.float64)) == pytest.approx(pa, rel=1e-6)
+
+
+@pytest.mark.parametrize("fs,periodic", [(4_000_000.0, True), (4_092_000.0, True), (8_000_000.0, True), (12_500_000.0, True)])
+def test_other_sample_rates(gpu, oracle, monkeypatch, fs, periodic):
+    """both kernel families at other sample rates (code period 16 000 / 16 368 / 32 000 / 50 000 samples; 63-196 boundary-age
+    classes; 4.092 MHz = exactly 4 samples per chip).  The orbital config at 4 / 8 MHz is also the regression test for the
+    FMA-contraction bug of the f64 prologue (synth_prologue.cu): an oversample 5e-7 half-chips from a boundary."""
+    for name, dynamic in (("e1c_8prn_20s_clean", False), ("e1c_8prn_60s_cn34_orbital", True)):
+        cfg = _cfg(name).copy()
+        cfg.output.sample_rate = fs
+        cfg.output.lpf_cutoff_hz = 0.0
+        L = int(round(fs * 0.004))
+        first, n = 100 * L, 40 * L
+        x, _, path = _render(gpu, monkeypatch, cfg, first, n, False, True)
+        assert path == (1 if periodic and not dynamic else 0)
+        m = 3 * L
+        want = oracle.OracleScenario(cfg, noise=False).generate_range(first + n - m, m)
+        assert _relrms(x[n - m:], want) <= TOL
+        want = oracle.OracleScenario(cfg, noise=False).generate_range(first, L)
+        assert _relrms(x[:L], want) <= TOL
