@@ -187,6 +187,24 @@ def test_satellite_status_matches_oracle(gpu, oracle):
             assert getattr(g, f) == pytest.approx(getattr(w, f), rel=1e-9, abs=1e-6), f
 
 
+def test_device_prologue_rounds_like_host(gpu, emu):
+    """k_block_params (f64, device) against the same arithmetic on the host: the code delay of every sampled (block, satellite)
+    agrees to 1e-8 half-chips.  One ulp of the mean anomaly at t ~ 1.44e9 s is 1e-6 half-chips, which is what an FMA
+    contraction of M0 + n dt used to cost in some blocks (synth_prologue.cu is compiled with -fmad=false)."""
+    for name in ("e1c_8prn_60s_cn34_orbital", "e1c_60s_all_prns", "e1c_8prn_60s_mach3_ftwayne_berne"):
+        cfg = _cfg(name)
+        g, e = gpu.GnssScenario(cfg), emu.EmuScenario(cfg)
+        worst = 0.0
+        for block in reversed(range(0, 60000, 1499)):      # descending: the device table is built once
+            for sat in range(0, 8, 3):
+                a, b = g._debug_block_params(block, sat), e.block_params(block, sat)
+                d = abs(a[1] - b[1])
+                worst = max(worst, min(d, 204600.0 - d))
+                assert a[6] == b[6] and a[8] == b[8]                      # epoch offset, flags
+                assert abs(a[5] - b[5]) < 1e-8                            # phase0 (chips)
+        assert worst < 1e-8, worst
+
+
 def test_unsupported_inputs_fail_loudly(gpu):
     cfg = _cfg("e1c_prn3_20s_withdoppler")
     bad = cfg.copy(); bad.satellites[0].signal = "GpsL5"
