@@ -274,7 +274,8 @@ private:
     void prof_begin(int kind, cudaStream_t st);
     void prof_end(cudaStream_t st);
     DevBuf<unsigned char> d_stage2_;          // second staging buffer of the host-destination pipeline
-    cudaStream_t side_stream_ = nullptr;      // head / tail launches next to the periodic kernel; D2H copies
+    cudaStream_t side_stream_ = nullptr;      // head / tail launches next to the periodic kernel
+    cudaStream_t copy_stream_ = nullptr;      // D2H copies of the host-destination pipeline
     cudaEvent_t ev_fork_ = nullptr, ev_join_ = nullptr, ev_render_[2] = {nullptr, nullptr}, ev_copy_[2] = {nullptr, nullptr};
     void ensure_side_stream();
 };

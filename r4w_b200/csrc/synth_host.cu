@@ -62,6 +62,7 @@ Scenario::~Scenario()
     for (cudaEvent_t e : {ev_fork_, ev_join_, ev_render_[0], ev_render_[1], ev_copy_[0], ev_copy_[1]})
         if (e) cudaEventDestroy(e);
     if (side_stream_) cudaStreamDestroy(side_stream_);
+    if (copy_stream_) cudaStreamDestroy(copy_stream_);
     for (cudaEvent_t e : event_pool_) cudaEventDestroy(e);
 }
 
@@ -103,6 +104,7 @@ void Scenario::ensure_side_stream()
     int prio_lo = 0, prio_hi = 0;
     R4WB_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
     R4WB_CUDA(cudaStreamCreateWithPriority(&side_stream_, cudaStreamNonBlocking, prio_hi));   // its few CTAs go ahead of the bulk's queue
+    R4WB_CUDA(cudaStreamCreateWithFlags(&copy_stream_, cudaStreamNonBlocking));
     for (cudaEvent_t* e : {&ev_fork_, &ev_join_, &ev_render_[0], &ev_render_[1], &ev_copy_[0], &ev_copy_[1]})
         R4WB_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
 }
@@ -365,22 +367,26 @@ void Scenario::render_to(uint64_t first, uint64_t n, void* dst, r4wb_mem where, 
     // host destination: render chunk by chunk into two device staging buffers; the copy of one chunk (side stream)
     // overlaps the rendering of the next
     ensure_side_stream();
-    const uint64_t chunk_blocks = std::max<uint64_t>(1, (uint64_t)(16u << 20) / sc.B);   // ~16 Msamples per chunk
+    uint64_t chunk_blocks = std::max<uint64_t>(1, (uint64_t)(16u << 20) / sc.B);   // ~16 Msamples per chunk
+    if (fmt == R4WB_FMT_CF32 && plan_periodic() && per_->L % sc.B == 0) {
+        const uint64_t bpp = per_->L / sc.B;                                      // chunk edges on primary-code periods:
+        chunk_blocks = std::max<uint64_t>(bpp, chunk_blocks / bpp * bpp);         // no partial periods inside the range
+    }
     const size_t stage_bytes = (size_t)std::min<uint64_t>(n + sc.B, chunk_blocks * sc.B + sc.B) * bps;
     unsigned char* stage[2] = {d_stage_.reserve(stage_bytes), d_stage2_.reserve(stage_bytes)};
     uint32_t c = 0;
-    for (uint64_t cb = b0; cb <= b1; cb += chunk_blocks, ++c) {
-        const uint64_t ce = std::min(b1 + 1, cb + chunk_blocks);
+    for (uint64_t cb = b0, ce; cb <= b1; cb = ce, ++c) {
+        ce = std::min(b1 + 1, (cb / chunk_blocks + 1) * chunk_blocks);
         const uint64_t f = std::max(first, cb * sc.B), l = std::min(first + n, ce * sc.B);
         const uint32_t k = c & 1u;
         if (c >= 2) R4WB_CUDA(cudaStreamWaitEvent(st, ev_copy_[k], 0));          // the buffer's previous copy is done
         render_device(f, l - f, stage[k], fmt);
         R4WB_CUDA(cudaEventRecord(ev_render_[k], st));
-        R4WB_CUDA(cudaStreamWaitEvent(side_stream_, ev_render_[k], 0));
-        R4WB_CUDA(cudaMemcpyAsync((unsigned char*)dst + (f - first) * bps, stage[k], (l - f) * bps, cudaMemcpyDeviceToHost, side_stream_));
-        R4WB_CUDA(cudaEventRecord(ev_copy_[k], side_stream_));
+        R4WB_CUDA(cudaStreamWaitEvent(copy_stream_, ev_render_[k], 0));
+        R4WB_CUDA(cudaMemcpyAsync((unsigned char*)dst + (f - first) * bps, stage[k], (l - f) * bps, cudaMemcpyDeviceToHost, copy_stream_));
+        R4WB_CUDA(cudaEventRecord(ev_copy_[k], copy_stream_));
     }
-    R4WB_CUDA(cudaStreamSynchronize(side_stream_));
+    R4WB_CUDA(cudaStreamSynchronize(copy_stream_));
     R4WB_CUDA(cudaStreamSynchronize(st));
 }
 

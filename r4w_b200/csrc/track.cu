@@ -6,7 +6,7 @@
 //   estimate_cn0 :316-337, LoopFilter2nd :365-397, LoopFilter3rd :399-437
 // The reference runs one channel at a time, one code period per call; the loop feedback makes the periods of a channel
 // sequential, the channels are independent.  k_track: one CTA per channel walks its periods in order; inside a period
-// the 256 threads split the samples (carrier wipe-off + the three code look-ups in f64 with the reference's own
+// the 512 threads split the samples (carrier wipe-off + the three code look-ups in f64 with the reference's own
 // expressions, never contracted into FMAs, so the chip indices are the reference's), a fixed-order tree reduces the six
 // correlator sums, thread 0 runs the loop update exactly as :219-313 and publishes the state for the next period.
 // Only the summation order differs from the reference (pairwise instead of sequential): states agree to ~1e-12.
@@ -20,12 +20,17 @@
 
 namespace r4wb {
 
-constexpr int kTrackThreads = 256;
+constexpr int kTrackThreads = 512;
 constexpr double kTwoPi = 6.283185307179586476925286766559;
 
 __device__ __forceinline__ double rem_euclid_d(double a, double b)
 {
-    const double r = fmod(a, b);
+    // f64::rem_euclid: r = a % b (fmod), r < 0 -> r + |b|.  For 0 <= a < 2b (every chip position of a code period) fmod is
+    // a or a - b, and that subtraction is exact (Sterbenz), so the shortcut is bit-identical to the library routine.
+    double r;
+    if (a >= 0.0 && a < b) r = a;
+    else if (a >= b && a < __dadd_rn(b, b)) r = __dadd_rn(a, -b);
+    else r = fmod(a, b);
     return r < 0.0 ? __dadd_rn(r, fabs(b)) : r;
 }
 __device__ __forceinline__ uint32_t as_index(double x, uint32_t code_length)
