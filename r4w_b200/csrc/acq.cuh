@@ -160,6 +160,12 @@ private:
     AcqWork<float> w32_;
     AcqWork<double> w64_;
     DevBuf<unsigned char> d_in_;
+    // host input: the H2D copy runs in pieces on its own stream and the snapshot chunks wait only for the pieces they read
+    cudaStream_t copy_stream_ = nullptr;
+    std::vector<cudaEvent_t> h2d_events_;
+    size_t h2d_piece_ = 0, h2d_pieces_ = 0, h2d_waited_ = 0;
+    void h2d_start(const void* host, size_t bytes, cudaStream_t st, const int8_t* codes, size_t code_bytes);
+    void h2d_wait(size_t end_byte, cudaStream_t st);     // stream st may read bytes [0, end_byte) of d_in_ afterwards
     DevBuf<int8_t> d_codes_;
     DevBuf<RowPeak> d_rowpeaks_;
     DevBuf<PairPeak> d_pairpeaks_;

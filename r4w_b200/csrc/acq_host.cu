@@ -62,6 +62,46 @@ Pcps::Pcps(uint64_t code_length, double sample_rate) : code_length_(code_length)
 Pcps::~Pcps()
 {
     for (cudaEvent_t e : event_pool_) cudaEventDestroy(e);
+    for (cudaEvent_t e : h2d_events_) cudaEventDestroy(e);
+    if (copy_stream_) cudaStreamDestroy(copy_stream_);
+}
+
+// Host input of acquire_batch: copied in 32 MB pieces on a copy stream (after the work already queued on st, which may
+// still read the buffer), one event per piece.
+void Pcps::h2d_start(const void* host, size_t bytes, cudaStream_t st, const int8_t* codes, size_t code_bytes)
+{
+    if (!copy_stream_) {
+        int lo = 0, hi = 0;
+        R4WB_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        R4WB_CUDA(cudaStreamCreateWithPriority(&copy_stream_, cudaStreamNonBlocking, hi));
+    }
+    h2d_piece_ = (size_t)32 << 20;
+    h2d_pieces_ = (bytes + h2d_piece_ - 1) / h2d_piece_;
+    h2d_waited_ = 0;
+    while (h2d_events_.size() < h2d_pieces_ + 2) {
+        cudaEvent_t e;
+        R4WB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        h2d_events_.push_back(e);
+    }
+    R4WB_CUDA(cudaEventRecord(h2d_events_[h2d_pieces_], st));
+    R4WB_CUDA(cudaStreamWaitEvent(copy_stream_, h2d_events_[h2d_pieces_], 0));
+    if (code_bytes) {
+        R4WB_CUDA(cudaMemcpyAsync(d_codes_.p, codes, code_bytes, cudaMemcpyHostToDevice, copy_stream_));
+        R4WB_CUDA(cudaEventRecord(h2d_events_[h2d_pieces_ + 1], copy_stream_));
+        R4WB_CUDA(cudaStreamWaitEvent(st, h2d_events_[h2d_pieces_ + 1], 0));
+    }
+    for (size_t k = 0; k < h2d_pieces_; ++k) {
+        const size_t off = k * h2d_piece_, len = std::min(h2d_piece_, bytes - off);
+        R4WB_CUDA(cudaMemcpyAsync(d_in_.p + off, static_cast<const unsigned char*>(host) + off, len, cudaMemcpyHostToDevice, copy_stream_));
+        R4WB_CUDA(cudaEventRecord(h2d_events_[k], copy_stream_));
+    }
+}
+
+void Pcps::h2d_wait(size_t end_byte, cudaStream_t st)
+{
+    if (h2d_pieces_ == 0) return;
+    const size_t need = std::min(h2d_pieces_, (end_byte + h2d_piece_ - 1) / h2d_piece_);
+    for (; h2d_waited_ < need; ++h2d_waited_) R4WB_CUDA(cudaStreamWaitEvent(st, h2d_events_[h2d_waited_], 0));
 }
 
 void Pcps::prof_begin(int kind)
@@ -165,6 +205,7 @@ void Pcps::run(AcqWork<T>& w, const void* d_input, r4wb_fmt fmt, uint64_t s0, ui
     for (uint64_t s = 0; s < ns; s += chunk) {
         const uint32_t cs = (uint32_t)std::min<uint64_t>(chunk, ns - s);
         const unsigned char* in = static_cast<const unsigned char*>(d_input) + (s0 + s) * stride * bps;
+        if (d_input == d_in_.p) h2d_wait(((s0 + s + cs - 1) * stride + n_input) * bps, st);
         prof_begin(1);
         if (fast)
             launch_rf_fwd_input(g, cs * g.D, in, fmt == R4WB_FMT_CF64 ? 1u : 0u, stride, take, reinterpret_cast<const cx<float>*>(w.tw.p),
@@ -223,15 +264,26 @@ void Pcps::acquire_batch(const void* input, r4wb_fmt fmt, r4wb_mem where, uint64
     if (code_length_ == 0) fail(R4WB_ERR_INVALID_SIZE, "code_length is 0");
     cudaStream_t st = current_stream();
     const size_t bps = fmt == R4WB_FMT_CF64 ? 16 : 8;
+    d_codes_.reserve(std::max<size_t>((size_t)P * code_len, 16));
+    bool codes_copied = false;
     const void* d_input = input;
     if (where == R4WB_MEM_HOST) {
         const size_t bytes = ((S - 1) * stride + n_input) * bps;
         d_in_.reserve(std::max<size_t>(bytes, 16));
-        if (bytes) R4WB_CUDA(cudaMemcpyAsync(d_in_.p, input, bytes, cudaMemcpyHostToDevice, st));
+        h2d_pieces_ = 0;
+        static const bool pipelined = [] { const char* e = std::getenv("R4WB_ACQ_H2D_PIPELINE"); return !(e && e[0] == '0'); }();
+        if (bytes && pipelined) {
+            // The compute stream must not touch the H2D copy engine in this call: after an H2D copy on st the driver places
+            // st's next event record on that engine's queue, behind the input pieces, and the first kernel then starts only
+            // when the whole input has arrived (measured: 14.6 ms).  So the codes travel on the copy stream too, ahead of the
+            // pieces, and st waits for their event.
+            h2d_start(input, bytes, st, codes, (size_t)P * code_len);
+            codes_copied = true;
+        }
+        else if (bytes) R4WB_CUDA(cudaMemcpyAsync(d_in_.p, input, bytes, cudaMemcpyHostToDevice, st));
         d_input = d_in_.p;
     }
-    d_codes_.reserve(std::max<size_t>((size_t)P * code_len, 16));
-    if (code_len) R4WB_CUDA(cudaMemcpyAsync(d_codes_.p, codes, (size_t)P * code_len, cudaMemcpyHostToDevice, st));
+    if (!codes_copied && code_len) R4WB_CUDA(cudaMemcpyAsync(d_codes_.p, codes, (size_t)P * code_len, cudaMemcpyHostToDevice, st));
     const size_t pairs = (size_t)S * P;
     d_pairpeaks_.reserve(pairs + 1);
 
@@ -273,6 +325,7 @@ void Pcps::acquire_grid(const void* input, r4wb_fmt fmt, uint64_t n_input, const
     cudaStream_t st = current_stream();
     const size_t bps = fmt == R4WB_FMT_CF64 ? 16 : 8;
     d_in_.reserve(std::max<size_t>(n_input * bps, 16));
+    h2d_pieces_ = 0;                                       // plain in-stream copy: nothing to wait for
     if (n_input) R4WB_CUDA(cudaMemcpyAsync(d_in_.p, input, n_input * bps, cudaMemcpyHostToDevice, st));
     d_codes_.reserve(std::max<size_t>(code_len, 16));
     if (code_len) R4WB_CUDA(cudaMemcpyAsync(d_codes_.p, code, code_len, cudaMemcpyHostToDevice, st));
