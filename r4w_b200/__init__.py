@@ -2,7 +2,8 @@
 FFT-based PCPS acquisition.  Host-side mirror of the reference's `GnssScenarioConfig` / `GnssScenario` /
 `PcpsAcquisition` surface over the C-ABI library libr4w_b200.so (include/r4w_b200.h)."""
 from .config import (GnssScenarioConfig, SatelliteConfig, ReceiverConfig, EnvironmentConfig, OutputConfig,  # noqa: F401
-                     LlaPosition, AntennaPattern, ReceiverTrajectory, load_config, loads_config)
+                     LlaPosition, AntennaPattern, ReceiverTrajectory, load_config, loads_config, preset_config, PRESETS,
+                     gps_time_from_utc)
 from ._lib import R4wB200Error, init, kernel_launches, device_count, version, build  # noqa: F401
 from .scenario import GnssScenario, SatelliteStatus  # noqa: F401
 from .tracking import TrackingChannel, TrackerBank, TrackingState  # noqa: F401

@@ -160,13 +160,27 @@ class EnvironmentConfig:
     ephemeris_source: str = "Nominal"
 
 
+def _julian_day(year: int, month: int, day: int) -> int:
+    """scenario_config.rs:509-517 (integer division truncates like Rust's for these positive operands)"""
+    a = (14 - month) // 12
+    y2 = year + 4800 - a
+    m2 = month + 12 * a - 3
+    return day + (153 * m2 + 2) // 5 + 365 * y2 + y2 // 4 - y2 // 100 + y2 // 400 - 32045
+
+
+def gps_time_from_utc(year: int, month: int, day: int, hour: int, minute: int, sec: float) -> float:
+    """gps_time_from_utc, scenario_config.rs:498-506: seconds since the GPS epoch, 18 leap seconds"""
+    days = float(_julian_day(year, month, day) - _julian_day(1980, 1, 6))
+    return days * 86400.0 + hour * 3600.0 + minute * 60.0 + sec + 18.0
+
+
 @dataclass
 class OutputConfig:
     sample_rate: float = 5_000_000.0
     duration_s: float = 0.001
     block_size: int = 0
     seed: int = 42
-    start_time_gps_s: float = 0.0
+    start_time_gps_s: float = field(default_factory=lambda: gps_time_from_utc(2026, 2, 4, 20, 0, 0.0))   # OutputConfig::default, :519-533
     format: str = "cf32"
     lpf_cutoff_hz: float = 0.0
     output_path: Optional[str] = None
@@ -377,3 +391,69 @@ def load_config(path, cli_elevation_mask_deg: Optional[float] = None) -> GnssSce
 
 def loads_config(text: str) -> GnssScenarioConfig:
     return config_from_dict(yaml.load(text, Loader=_Loader))
+
+
+# ---- constellation tables and presets (scenario_config.rs:36-135, 199-241, 549-700) ----------------------------------------
+# (PRN, plane, slot): GPS from NAVCEN, Galileo from the GSC (the reference's lookup tables, restated as data)
+GPS_CONSTELLATION = [
+    (24, 0, 0), (31, 0, 1), (30, 0, 2), (7, 0, 3), (28, 0, 5),
+    (16, 1, 0), (25, 1, 1), (22, 1, 2), (12, 1, 3), (26, 1, 4), (14, 1, 5),
+    (29, 2, 0), (27, 2, 1), (8, 2, 2), (17, 2, 3), (19, 2, 4),
+    (2, 3, 0), (1, 3, 1), (6, 3, 3), (11, 3, 4), (18, 3, 5),
+    (3, 4, 0), (10, 4, 1), (5, 4, 2), (23, 4, 4), (21, 4, 5),
+    (32, 5, 0), (15, 5, 1), (9, 5, 2), (4, 5, 3), (13, 5, 5),
+]
+GALILEO_CONSTELLATION = [
+    (31, 0, 0), (23, 0, 1), (21, 0, 2), (27, 0, 3), (30, 0, 4), (2, 0, 5), (25, 0, 6), (16, 0, 7),
+    (13, 1, 0), (15, 1, 1), (34, 1, 2), (36, 1, 3), (11, 1, 4), (12, 1, 5), (33, 1, 6), (26, 1, 7),
+    (5, 2, 0), (9, 2, 1), (4, 2, 2), (19, 2, 3), (29, 2, 4), (7, 2, 5), (8, 2, 6), (3, 2, 7),
+]
+
+
+def lookup_prn(table, plane: int, slot: int) -> int:
+    """SatelliteConfig::lookup_prn (:199-211): 0 when no satellite sits in the slot"""
+    for prn, p, s in table:
+        if p == plane and s == slot:
+            return prn
+    return 0
+
+
+def gps_l1ca(plane: int, slot: int) -> SatelliteConfig:
+    """SatelliteConfig::gps_l1ca (:214-226): everything else from the nominal orbit and the link budget"""
+    prn = lookup_prn(GPS_CONSTELLATION, plane, slot)
+    if prn == 0:
+        raise ValueError(f"No GPS satellite at plane={plane} slot={slot}")
+    return SatelliteConfig("GpsL1Ca", prn, plane, slot, 14.3, True)
+
+
+def galileo_e1(plane: int, slot: int) -> SatelliteConfig:
+    """SatelliteConfig::galileo_e1 (:229-241)"""
+    prn = lookup_prn(GALILEO_CONSTELLATION, plane, slot)
+    if prn == 0:
+        raise ValueError(f"No Galileo satellite at plane={plane} slot={slot}")
+    return SatelliteConfig("GalileoE1", prn, plane, slot, 15.0, True)
+
+
+PRESETS = ("OpenSky", "UrbanCanyon", "Driving", "Walking", "HighDynamics", "MultiConstellation")
+_GPS8 = [(4, 2), (2, 3), (1, 4), (3, 3), (2, 4), (1, 3), (4, 1), (5, 2)]
+
+
+def preset_config(name: str) -> GnssScenarioConfig:
+    """GnssScenarioPreset::to_config (:581-700): the six presets of `r4w gnss scenario --preset`"""
+    gps = lambda n: [gps_l1ca(p, s) for p, s in _GPS8[:n]]           # noqa: E731
+    if name == "OpenSky":
+        return GnssScenarioConfig(gps(8))
+    if name == "UrbanCanyon":
+        return GnssScenarioConfig(gps(8), receiver=ReceiverConfig(elevation_mask_deg=15.0),
+                                  environment=EnvironmentConfig(multipath_preset="UrbanCanyon", multipath_enabled=True))
+    if name == "Driving":
+        return GnssScenarioConfig(gps(7), environment=EnvironmentConfig(multipath_preset="Suburban", multipath_enabled=True),
+                                  output=OutputConfig(duration_s=0.01))
+    if name == "Walking":
+        return GnssScenarioConfig(gps(6), output=OutputConfig(duration_s=0.01))
+    if name == "HighDynamics":
+        return GnssScenarioConfig(gps(8), output=OutputConfig(duration_s=0.001))
+    if name == "MultiConstellation":
+        gal = [galileo_e1(p, s) for p, s in ((0, 7), (1, 5), (0, 0), (1, 6), (1, 4), (0, 6))]
+        return GnssScenarioConfig(gps(5) + gal)
+    raise ValueError(f"unknown preset {name!r}; one of {PRESETS}")

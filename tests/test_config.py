@@ -70,3 +70,20 @@ def test_segments_cover_and_align():
     assert [snapshots_for_rank(10, r, 4) for r in range(4)] == [(0, 3), (3, 3), (6, 2), (8, 2)]
     with pytest.raises(ValueError):
         segment_for_rank(10, 1, 2, 2)
+
+
+def test_presets_and_constellation_tables():
+    """GnssScenarioPreset::to_config + lookup_prn (scenario_config.rs:199-241, 581-700): PRNs as the reference's comments state,
+    default start time = 2026-02-04 20:00 UTC in GPS seconds"""
+    from r4w_b200.config import PRESETS, preset_config, gps_time_from_utc, gps_l1ca, galileo_e1
+    assert gps_time_from_utc(2026, 2, 4, 20, 0, 0.0) == 1454270418.0
+    assert gps_time_from_utc(1980, 1, 6, 0, 0, 0.0) == 18.0
+    assert [gps_l1ca(p, s).prn for p, s in ((4, 2), (2, 3), (1, 4), (3, 3), (2, 4), (1, 3), (4, 1), (5, 2))] == [5, 17, 26, 6, 19, 12, 10, 9]
+    assert [galileo_e1(p, s).prn for p, s in ((0, 7), (1, 5), (0, 0), (1, 6), (1, 4), (0, 6))] == [16, 12, 31, 33, 11, 25]
+    with pytest.raises(ValueError):
+        gps_l1ca(0, 4)                                      # no satellite in slot A-5
+    sizes = {n: (len(preset_config(n).satellites), preset_config(n).total_samples()) for n in PRESETS}
+    assert sizes == {"OpenSky": (8, 5000), "UrbanCanyon": (8, 5000), "Driving": (7, 50000), "Walking": (6, 50000),
+                     "HighDynamics": (8, 5000), "MultiConstellation": (11, 5000)}
+    assert preset_config("UrbanCanyon").receiver.elevation_mask_deg == 15.0
+    assert preset_config("OpenSky").to_pod()[0].output.start_time_gps_s == 1454270418.0

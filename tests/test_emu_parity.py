@@ -233,3 +233,21 @@ def test_other_sample_rates_replay_matches_oracle(oracle, emu, fs):
         got = emu.EmuScenario(cfg, noise=False).generate_range(first, n)
         want = oracle.OracleScenario(cfg, noise=False).generate_range(first, n)
         assert _relrms(got, want) <= TOL
+
+
+@pytest.mark.parametrize("name", ["OpenSky", "UrbanCanyon", "Driving", "Walking", "HighDynamics", "MultiConstellation"])
+def test_presets_replay_matches_oracle(oracle, emu, name):
+    """GnssScenarioPreset::to_config (scenario_config.rs:581-700): GPS L1 C/A (and Galileo E1B) satellites with no overrides,
+    so geometry, Doppler, C/N0 (link budget + patch antenna), Klobuchar and Saastamoinen all come from the nominal orbits"""
+    from r4w_b200.config import preset_config
+    cfg = preset_config(name)
+    n = cfg.total_samples()
+    got = emu.EmuScenario(cfg, noise=False).generate_range(0, n)
+    want = oracle.OracleScenario(cfg, noise=False).generate_range(0, n)
+    assert got.size == n and np.abs(want).max() > 0
+    assert _relrms(got, want) <= TOL
+    longer = cfg.copy()
+    longer.output.duration_s = 0.5
+    got = emu.EmuScenario(longer, noise=False).generate_range(2_400_000, 7000)
+    want = oracle.OracleScenario(longer, noise=False).generate_range(2_400_000, 7000)
+    assert _relrms(got, want) <= TOL

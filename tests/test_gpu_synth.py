@@ -301,3 +301,24 @@ def test_gps_acquisition_on_gpu_scenario(gpu, oracle):
         r = acq.acquire(x, code, prn)
         o = oacq.acquire(x.astype(np.complex128), code, prn)
         assert (r.code_phase, r.doppler_hz, r.detected) == (o.code_phase, o.doppler_hz, bool(o.detected))
+
+
+@pytest.mark.parametrize("name", ["OpenSky", "UrbanCanyon", "Driving", "Walking", "HighDynamics", "MultiConstellation"])
+def test_presets_match_oracle(gpu, oracle, name):
+    """the six scenario presets of `r4w gnss scenario --preset` (scenario_config.rs:581-700) on the GPU path:
+    IQ within 1e-5 of the oracle, the same satellites visible, the same link-budget C/N0"""
+    cfg = gpu.preset_config(name)
+    n = cfg.total_samples()
+    sc = gpu.GnssScenario(cfg, noise=False)
+    got = sc.generate()
+    want = oracle.OracleScenario(cfg, noise=False).generate_range(0, n)
+    assert got.size == n and _relrms(got, want) <= TOL
+    st, ost = sc.satellite_status(), oracle.OracleScenario(cfg).status()
+    assert [s.prn for s in st] == [s.prn for s in ost] and [s.visible for s in st] == [bool(s.visible) for s in ost]
+    for a, b in zip(st, ost):
+        assert a.cn0_dbhz == pytest.approx(b.cn0_dbhz, abs=1e-6) and a.range_m == pytest.approx(b.range_m, rel=1e-12)
+    longer = cfg.copy()
+    longer.output.duration_s = 2.0
+    got = gpu.GnssScenario(longer, noise=False).generate_range(9_000_000, 30_000)
+    want = oracle.OracleScenario(longer, noise=False).generate_range(9_000_000, 30_000)
+    assert _relrms(got, want) <= TOL
