@@ -137,3 +137,28 @@ def test_gpu_tracking_single_channel_api_and_e1c(gpu, oracle):
     for k, c in enumerate(chans):
         want = oracle.OracleTrackingChannel(3, 4092, 5e6, 1.023e6, c["initial_code_phase"], -457.0).run(xe, e1c, n_per, 50)
         _assert_states_close(got[:, k], want, 4092.0)
+
+
+def _golden():
+    import os
+    from tests.conftest import GOLDEN_DIR
+    g = np.load(os.path.join(GOLDEN_DIR, "track_case.npz"))
+    return g["x"], g["code"], float(g["start"][0]), float(g["start"][1]), g["states"]
+
+
+def test_oracle_reproduces_golden_tracking_case(oracle):
+    """committed vectors (tools/make_golden_track.py): the restated tracking loop reproduces them bit for bit"""
+    x, code, cp0, dop0, want = _golden()
+    got = oracle.OracleTrackingChannel(11, 1023, 5e6, 1.023e6, cp0, dop0).with_dll_bandwidth(2.0).run(x, code, 5000, 20)
+    for f in want.dtype.names:
+        assert np.array_equal(got[f], want[f]), f
+
+
+@pytest.mark.gpu
+def test_gpu_tracking_golden_case(gpu):
+    """the CUDA channel against the committed oracle states (no oracle on this path)"""
+    x, code, cp0, dop0, want = _golden()
+    bank = gpu.TrackerBank([dict(prn=11, code_length=1023, sample_rate=5e6, chipping_rate=1.023e6, initial_code_phase=cp0,
+                                 initial_doppler=dop0, dll_bandwidth_hz=2.0)])
+    got = bank.process(x, code[None, :], 5000, 20)[:, 0]
+    _assert_states_close(got, want)
