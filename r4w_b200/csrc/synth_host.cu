@@ -367,16 +367,19 @@ void Scenario::render_to(uint64_t first, uint64_t n, void* dst, r4wb_mem where, 
     // host destination: render chunk by chunk into two device staging buffers; the copy of one chunk (side stream)
     // overlaps the rendering of the next
     ensure_side_stream();
-    uint64_t chunk_blocks = std::max<uint64_t>(1, (uint64_t)(16u << 20) / sc.B);   // ~16 Msamples per chunk
-    if (fmt == R4WB_FMT_CF32 && plan_periodic() && per_->L % sc.B == 0) {
-        const uint64_t bpp = per_->L / sc.B;                                      // chunk edges on primary-code periods:
-        chunk_blocks = std::max<uint64_t>(bpp, chunk_blocks / bpp * bpp);         // no partial periods inside the range
-    }
+    const uint64_t chunk_blocks = std::max<uint64_t>(1, (uint64_t)(16u << 20) / sc.B);   // ~16 Msamples per chunk
+    uint64_t bpp = 1;                                                              // blocks per primary-code period
+    if (fmt == R4WB_FMT_CF32 && plan_periodic() && per_->L % sc.B == 0) bpp = per_->L / sc.B;
+    ensure_side_stream();
     const size_t stage_bytes = (size_t)std::min<uint64_t>(n + sc.B, chunk_blocks * sc.B + sc.B) * bps;
     unsigned char* stage[2] = {d_stage_.reserve(stage_bytes), d_stage2_.reserve(stage_bytes)};
     uint32_t c = 0;
     for (uint64_t cb = b0, ce; cb <= b1; cb = ce, ++c) {
-        ce = std::min(b1 + 1, (cb / chunk_blocks + 1) * chunk_blocks);
+        // chunk edges on primary-code period boundaries (absolute multiples of bpp blocks), so that only the first and the
+        // last chunk of a range carry a partial period
+        ce = (cb + chunk_blocks) / bpp * bpp;
+        if (ce <= cb) ce = cb + chunk_blocks;
+        ce = std::min(b1 + 1, ce);
         const uint64_t f = std::max(first, cb * sc.B), l = std::min(first + n, ce * sc.B);
         const uint32_t k = c & 1u;
         if (c >= 2) R4WB_CUDA(cudaStreamWaitEvent(st, ev_copy_[k], 0));          // the buffer's previous copy is done
