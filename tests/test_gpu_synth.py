@@ -322,3 +322,24 @@ def test_presets_match_oracle(gpu, oracle, name):
     got = gpu.GnssScenario(longer, noise=False).generate_range(9_000_000, 30_000)
     want = oracle.OracleScenario(longer, noise=False).generate_range(9_000_000, 30_000)
     assert _relrms(got, want) <= TOL
+
+
+def test_600s_config_end_of_file_and_shards(gpu, oracle):
+    """BASELINE config 5 (e1c_8prn_600s_cn34_orbital, 3e9 samples, time-sharded over 8 GPUs in the scaling run): the last
+    10 ms of the file against the oracle (the carrier phase there is the scan of 600 000 per-block advances; the reference
+    accumulates it in f64 sample by sample, whose own rounding drift is ~5e-6 rad by then), and every shard boundary of an
+    8-way split rendered from either side equals one render across it"""
+    cfg = _cfg("e1c_8prn_600s_cn34_orbital")
+    sc = gpu.GnssScenario(cfg, noise=False)
+    n = sc.total_samples()
+    assert n == 3_000_000_000
+    got = sc.generate_range(n - 50_000, 50_000)
+    want = oracle.OracleScenario(cfg, noise=False, threads=8).generate_range(n - 50_000, 50_000)
+    assert _relrms(got, want) <= TOL
+    noisy = gpu.GnssScenario(cfg, noise=True)
+    for r in range(1, 8):
+        edge = r * (n // 8)
+        across = noisy.generate_range(edge - 6000, 12000)
+        left = gpu.GnssScenario(cfg, noise=True).generate_range(edge - 6000, 6000)       # tail of shard r-1 (fresh handle: own table)
+        right = gpu.GnssScenario(cfg, noise=True).generate_range(edge, 6000)             # head of shard r
+        assert np.array_equal(across[:6000], left) and np.array_equal(across[6000:], right)
