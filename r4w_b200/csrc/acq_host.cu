@@ -285,7 +285,8 @@ void Pcps::acquire_batch(const void* input, r4wb_fmt fmt, r4wb_mem where, uint64
     }
     if (!codes_copied && code_len) R4WB_CUDA(cudaMemcpyAsync(d_codes_.p, codes, (size_t)P * code_len, cudaMemcpyHostToDevice, st));
     const size_t pairs = (size_t)S * P;
-    d_pairpeaks_.reserve(pairs + 1);
+    const size_t guard_slots = 64;
+    d_pairpeaks_.reserve(pairs + guard_slots);
 
     for (int k = 0; k < 4; ++k) { prof_ms_[k] = 0.0; prof_n_[k] = 0; }
     run<float>(w32_, d_input, fmt, 0, S, stride, n_input, d_codes_.p, code_len, 0, P, d_pairpeaks_.p, nullptr);
@@ -294,22 +295,31 @@ void Pcps::acquire_batch(const void* input, r4wb_fmt fmt, r4wb_mem where, uint64
     R4WB_CUDA(cudaStreamSynchronize(st));
     prof_collect();
 
+    // Near-ties and near-threshold metrics: re-run those (snapshot, code) pairs through the f64 engine with the reference's
+    // literal wipe-off expression.  The reruns are queued back to back (they share the f64 work buffers in stream order) and
+    // read back once per batch.
     guard_count_ = 0;
+    std::vector<size_t> guards;
     for (size_t i = 0; i < pairs; ++i) {
-        const uint64_t s = i / P;
         const uint32_t c = (uint32_t)(i % P);
-        const uint8_t prn = prns ? prns[c] : 0;
-        finish(pk[i], prn, out[i]);
+        finish(pk[i], prns ? prns[c] : 0, out[i]);
         const bool near_tie = pk[i].best > 0.0 && (pk[i].best - pk[i].second) <= kNearTie * pk[i].best;
         const bool near_thr = threshold_ > 0.0 && std::fabs(out[i].peak_metric / threshold_ - 1.0) < kNearThreshold;
-        if (near_tie || near_thr) {
-            PairPeak* d_g = d_pairpeaks_.p + pairs;
-            run<double>(w64_, d_input, fmt, s, 1, stride, n_input, d_codes_.p, code_len, c, 1, d_g, nullptr);
-            PairPeak g;
-            R4WB_CUDA(cudaMemcpyAsync(&g, d_g, sizeof g, cudaMemcpyDeviceToHost, st));
-            R4WB_CUDA(cudaStreamSynchronize(st));
-            prof_collect();
-            finish(g, prn, out[i]);
+        if (near_tie || near_thr) guards.push_back(i);
+    }
+    std::vector<PairPeak> g(guard_slots);
+    for (size_t b = 0; b < guards.size(); b += guard_slots) {
+        const size_t nb = std::min(guard_slots, guards.size() - b);
+        for (size_t j = 0; j < nb; ++j) {
+            const size_t i = guards[b + j];
+            run<double>(w64_, d_input, fmt, i / P, 1, stride, n_input, d_codes_.p, code_len, (uint32_t)(i % P), 1, d_pairpeaks_.p + pairs + j, nullptr);
+        }
+        R4WB_CUDA(cudaMemcpyAsync(g.data(), d_pairpeaks_.p + pairs, nb * sizeof(PairPeak), cudaMemcpyDeviceToHost, st));
+        R4WB_CUDA(cudaStreamSynchronize(st));
+        prof_collect();
+        for (size_t j = 0; j < nb; ++j) {
+            const size_t i = guards[b + j];
+            finish(g[j], prns ? prns[(uint32_t)(i % P)] : 0, out[i]);
             ++guard_count_;
         }
     }
