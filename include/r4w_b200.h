@@ -217,6 +217,10 @@ r4wb_error r4wb_scenario_status(const r4wb_scenario* h, r4wb_sat_status* out, ui
 r4wb_error r4wb_e1_code(uint32_t channel, uint8_t prn, int8_t* out, uint64_t cap);
 /* GpsCaCodeGenerator::generate_code, gnss/prn.rs:34-162; PRN 1-32; out[1023] = +1/-1 */
 r4wb_error r4wb_gps_ca_code(uint8_t prn, int8_t* out, uint64_t cap);
+/* GpsL5CodeGenerator::new_i5, gnss/prn.rs:345-397 (the reference's simplified XA / XB pair); PRN 1-32; out[10230] = +1/-1 */
+r4wb_error r4wb_gps_l5_code(uint8_t prn, int8_t* out, uint64_t cap);
+/* GlonassCodeGenerator::generate_code, gnss/prn.rs:170-216: the 511-chip m-sequence shared by every satellite; out[511] */
+r4wb_error r4wb_glonass_code(int8_t* out, uint64_t cap);
 /* GalileoE1CodeGenerator::secondary_code, galileo_e1_codes.rs:29-31; out[25] */
 r4wb_error r4wb_e1c_secondary(int8_t* out, uint64_t cap);
 /* Sampled local replica code[floor(i*1.023e6/fs) mod 4092] * BOC(1,1) for i in [0, n) (no secondary code) —

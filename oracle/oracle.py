@@ -54,6 +54,8 @@ def lib():
         L.orc_e1_code.argtypes = [i32, i32, vp]; L.orc_e1_code.restype = i32
         L.orc_e1c_secondary.argtypes = [vp]
         L.orc_gps_ca_code.argtypes = [i32, vp]; L.orc_gps_ca_code.restype = i32
+        L.orc_glonass_code.argtypes = [i32, vp]; L.orc_glonass_code.restype = i32
+        L.orc_gps_l5_code.argtypes = [i32, i32, vp]; L.orc_gps_l5_code.restype = i32
         L.orc_e1c_replica.argtypes = [i32, dbl, vp, sz]
         L.orc_blackman_window.argtypes = [sz, vp]
         L.orc_lowpass_taps.argtypes = [dbl, dbl, sz, vp, sz]; L.orc_lowpass_taps.restype = sz
@@ -132,6 +134,20 @@ def gps_ca_code(prn: int) -> np.ndarray:
     out = np.zeros(1023, np.int8)
     if lib().orc_gps_ca_code(prn, _ptr(out)):
         raise ValueError("bad GPS PRN")
+    return out
+
+
+def glonass_code(frequency_channel: int = 0) -> np.ndarray:
+    out = np.zeros(511, np.int8)
+    if lib().orc_glonass_code(int(frequency_channel), _ptr(out)):
+        raise ValueError("GLONASS frequency channel must be -7 to +6")
+    return out
+
+
+def gps_l5_code(prn: int, q_channel: bool = False) -> np.ndarray:
+    out = np.zeros(10230, np.int8)
+    if lib().orc_gps_l5_code(int(prn), int(bool(q_channel)), _ptr(out)):
+        raise ValueError("GPS L5 PRN must be 1-32")
     return out
 
 

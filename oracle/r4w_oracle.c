@@ -70,6 +70,27 @@ int orc_gps_ca_code(int prn, int8_t* out)
     return 0;
 }
 
+/* GlonassCodeGenerator, gnss/prn.rs:170-216: 9-stage LFSR 1 + x^5 + x^9, all-ones start, the same 511 chips for every
+ * satellite; the constructor asserts the frequency channel -7..6 (the scenario passes `prn as i8`, so PRN 0..6) */
+int orc_glonass_code(int frequency_channel, int8_t* out)
+{
+    if (frequency_channel < -7 || frequency_channel > 6) return -1;
+    lfsr_t l = {0x1FF, 0x110, 9};
+    for (int i = 0; i < 511; ++i) out[i] = lfsr_clock(&l) == 0 ? 1 : -1;
+    return 0;
+}
+
+/* GpsL5CodeGenerator::generate_l5_code, gnss/prn.rs:376-397 (the reference's simplified XA / XB pair: no short cycle) */
+int orc_gps_l5_code(int prn, int q_channel, int8_t* out)
+{
+    if (prn < 1 || prn > 32) return -1;
+    uint32_t xb_init = ((uint32_t)prn * 0x2468u + (q_channel ? 0xACE0u : 0x1357u)) & 0x1FFFu;
+    if (xb_init < 1u) xb_init = 1u;
+    lfsr_t xa = {0x1FFF, 0x1E01, 13}, xb = {xb_init, q_channel ? 0x1B4Fu : 0x1AE3u, 13};
+    for (int i = 0; i < 10230; ++i) out[i] = ((lfsr_clock(&xa) ^ lfsr_clock(&xb)) == 0) ? 1 : -1;
+    return 0;
+}
+
 /* ------------------------------------------------------------------ signal constants, gnss/types.rs:62-127 */
 enum { SIG_GPS_L1CA = 0, SIG_GPS_L5 = 1, SIG_GLONASS_L1OF = 2, SIG_GAL_E1 = 3, SIG_GAL_E1C = 4, SIG_GAL_E1OS = 5 };
 
@@ -385,7 +406,9 @@ static int emitter_init(emitter_t* e, uint32_t signal, int prn, int plane, int s
     case SIG_GAL_E1: e->code_len = 4092; return orc_e1_code(0, prn, e->code);
     case SIG_GAL_E1C: e->code_len = 4092; return orc_e1_code(1, prn, e->code);
     case SIG_GAL_E1OS: e->code_len = 4092; if (orc_e1_code(0, prn, e->code)) return -1; return orc_e1_code(1, prn, e->code_e1c);
-    default: return -2; /* GPS L5 / GLONASS generators are outside the restated path */
+    case SIG_GPS_L5: e->code_len = 10230; return orc_gps_l5_code(prn, 0, e->code);                 /* new_i5, :369-372 */
+    case SIG_GLONASS_L1OF: e->code_len = 511; return orc_glonass_code((int)(int8_t)(uint8_t)prn, e->code);   /* new(prn as i8), :373-376 */
+    default: return -2;
     }
 }
 

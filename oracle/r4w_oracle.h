@@ -97,6 +97,8 @@ typedef struct orc_scenario orc_scenario;
 int orc_e1_code(int channel, int prn, int8_t* out4092);
 void orc_e1c_secondary(int8_t* out25);
 int orc_gps_ca_code(int prn, int8_t* out1023);
+int orc_glonass_code(int frequency_channel, int8_t* out511);          /* gnss/prn.rs:170-216 */
+int orc_gps_l5_code(int prn, int q_channel, int8_t* out10230);       /* gnss/prn.rs:376-397 */
 void orc_e1c_replica(int prn, double sample_rate, int8_t* out, size_t n);
 
 /* filters */

@@ -8,4 +8,4 @@ from ._lib import R4wB200Error, init, kernel_launches, device_count, version, bu
 from .scenario import GnssScenario, SatelliteStatus  # noqa: F401
 from .tracking import TrackingChannel, TrackerBank, TrackingState  # noqa: F401
 from .acquisition import (PcpsAcquisition, AcquisitionResult, AcquisitionGrid, e1_code, e1c_secondary,  # noqa: F401
-                          e1c_replica, gps_ca_code)
+                          e1c_replica, gps_ca_code, gps_l5_code, glonass_code)

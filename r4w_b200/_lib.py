@@ -64,6 +64,8 @@ SYMBOLS = {
     "r4wb_scenario_status": (_int, [_vp, C.POINTER(SatStatusPod), _u32, C.POINTER(_u32)]),
     "r4wb_e1_code": (_int, [_u32, _u8, _vp, _u64]),
     "r4wb_gps_ca_code": (_int, [_u8, _vp, _u64]),
+    "r4wb_gps_l5_code": (_int, [_u8, _vp, _u64]),
+    "r4wb_glonass_code": (_int, [_vp, _u64]),
     "r4wb_e1c_secondary": (_int, [_vp, _u64]),
     "r4wb_e1c_replica": (_int, [_u8, _dbl, _vp, _u64]),
     "r4wb_pcps_create": (_int, [_u64, _dbl, C.POINTER(_vp)]),

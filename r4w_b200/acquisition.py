@@ -197,3 +197,17 @@ def e1c_replica(prn: int, sample_rate: float, n: int) -> np.ndarray:
     out = np.zeros(int(n), np.int8)
     _lib.check(_lib.lib().r4wb_e1c_replica(int(prn), float(sample_rate), out.ctypes.data_as(C.c_void_p), out.size))
     return out
+
+
+def gps_l5_code(prn: int) -> np.ndarray:
+    """10230 chips (+1/-1) of the GPS L5 I5 code as the reference generates it (gnss/prn.rs:345-397), PRN 1-32"""
+    out = np.zeros(10230, np.int8)
+    _lib.check(_lib.lib().r4wb_gps_l5_code(int(prn), out.ctypes.data_as(C.c_void_p), out.size))
+    return out
+
+
+def glonass_code() -> np.ndarray:
+    """the 511-chip GLONASS L1OF ranging code (gnss/prn.rs:170-216)"""
+    out = np.zeros(511, np.int8)
+    _lib.check(_lib.lib().r4wb_glonass_code(out.ctypes.data_as(C.c_void_p), out.size))
+    return out

@@ -17,6 +17,8 @@ static thread_local std::string t_error;
 cudaStream_t current_stream() { return t_stream; }
 void e1_code_chips(uint32_t channel, uint32_t prn, int8_t* out);
 void gps_ca_code_chips(uint32_t prn, int8_t* out);
+void gps_l5_i5_code_chips(uint32_t prn, int8_t* out);
+void glonass_code_chips(int8_t* out);
 
 template <typename F>
 static r4wb_error guard(F&& body)
@@ -190,6 +192,21 @@ r4wb_error r4wb_gps_ca_code(uint8_t prn, int8_t* out, uint64_t cap)
     if (!out) { t_error = "out is NULL"; return R4WB_ERR_NULL_POINTER; }
     if (cap < 1023) { t_error = "code buffer needs 1023 entries"; return R4WB_ERR_INVALID_SIZE; }
     return guard([&] { gps_ca_code_chips(prn, out); });
+}
+
+r4wb_error r4wb_gps_l5_code(uint8_t prn, int8_t* out, uint64_t cap)
+{
+    if (!out) { t_error = "out is NULL"; return R4WB_ERR_NULL_POINTER; }
+    if (cap < 10230) { t_error = "code buffer needs 10230 entries"; return R4WB_ERR_INVALID_SIZE; }
+    return guard([&] { gps_l5_i5_code_chips(prn, out); });
+}
+
+r4wb_error r4wb_glonass_code(int8_t* out, uint64_t cap)
+{
+    if (!out) { t_error = "out is NULL"; return R4WB_ERR_NULL_POINTER; }
+    if (cap < 511) { t_error = "code buffer needs 511 entries"; return R4WB_ERR_INVALID_SIZE; }
+    glonass_code_chips(out);
+    return R4WB_OK;
 }
 
 r4wb_error r4wb_e1c_secondary(int8_t* out, uint64_t cap)

@@ -21,6 +21,7 @@ constexpr int kMaxYStride = 241;      // boundary-age classes per sign pattern: 
 constexpr int kPerBits = 2 * kCodeLen;   // half-chips of one Galileo E1 primary-code period (the longest supported)
 constexpr int kPerWords = 260;        // 8184 sign bits + 64 wrap-around bits, padded to a multiple of 4 words
 constexpr int kSynthThreads = 256;
+constexpr int kDirectWords = 320;     // packed chips of a "direct" satellite's primary code (GPS L5: 10 230 chips)
 
 // One piece of the reference's sequential f64 `phase += phase_inc` (gnss/scenario.rs:518-527) for a
 // constant-Doppler satellite: from visible-sample count i0 on, phase = x0 + (m - i0) * step EXACTLY
@@ -48,6 +49,9 @@ struct SatCode {
 // per-satellite constants (device copy lives in Scenario::d_sat)
 struct SatConst {
     SatCode code;
+    double chip_rate;            // 1.023e6 for the collapsed-FIR signals; 10.23e6 (GPS L5) / 0.511e6 (GLONASS) are "direct"
+    uint32_t direct;             // 1: rendered by k_synth_direct (literal 63-tap evaluation), skipped by k_synth
+    uint32_t pad0;
     double amp_scale;            // +1; the two halves of a GalileoE1OS satellite carry +-1/sqrt(2) (satellite_emitter.rs:316-321)
     Orbit orbit;
     double carrier_hz;
@@ -108,6 +112,13 @@ static_assert(sizeof(BlockSat) == 80, "BlockSat layout");
 
 struct BlockHdr { uint64_t first; uint32_t n; uint32_t pad; };
 
+// per-satellite constants of the direct path (k_synth_direct): signals whose chip rate is not 1.023 MHz
+struct DirectSat {
+    double spc;             // oversamples per chip = (8 fs) / chipping_rate, f64 like the reference (satellite_emitter.rs:245)
+    uint64_t epoch_bits;    // nav-bit sign per primary-code epoch (as SatCode)
+    uint32_t direct, code_len, epoch_period, pad;
+};
+
 // per-tile, per-satellite state (built by k_tile_params, read by k_synth)
 struct TileSat {
     uint64_t u0;        // half-chip position (18.46) at the newest oversample of the tile's first sample
@@ -148,6 +159,10 @@ struct SynthArgs {
     uint32_t n_sats;
     uint32_t nw64;             // 64-bit words of the per-satellite half-chip sign table
     uint32_t flags;
+    const DirectSat* dsat;     // [n_sats] (direct path)
+    const uint32_t* dcode;     // [n_sats][kDirectWords] packed chips, bit = 1 -> -1
+    uint32_t any_direct;       // some satellite is rendered by k_synth_direct
+    uint32_t max_block_n;      // longest block of the table (grid of k_synth_direct)
     uint32_t out_aligned16;    // out is aligned to two samples of the output format: sample pairs may be stored as one vector
     uint64_t delta46;
     uint32_t kmul;
@@ -171,6 +186,9 @@ struct ScenarioModel {
     std::vector<uint32_t> codebits;     // [n_sats][128] packed primary code (bit=1 -> chip -1)
     std::vector<uint32_t> perbits;      // [n_sats][kPerWords]
     std::vector<SatCode> satcode;       // [n_sats]
+    std::vector<DirectSat> dsat;        // [n_sats]
+    std::vector<uint32_t> dcodebits;    // [n_sats][kDirectWords]
+    bool any_direct = false;
     std::vector<uint32_t> cfg_index;    // virtual satellite -> index into cfg_sats (GalileoE1OS expands to two)
     float taps_f[64];
     float etab_f[64];
@@ -252,6 +270,8 @@ private:
     DevBuf<PhaseSegment> d_segments_;
     DevBuf<uint32_t> d_perbits_;
     DevBuf<SatCode> d_satcode_;
+    DevBuf<DirectSat> d_dsat_;
+    DevBuf<uint32_t> d_dcode_;
     DevBuf<float> d_taps_, d_etab_, d_ytab_;
     DevBuf<uint8_t> d_clslut_;
     DevBuf<BlockSat> d_tab_, d_seq_tab_;

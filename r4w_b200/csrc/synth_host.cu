@@ -13,6 +13,7 @@ namespace r4wb {
 // launchers (synth_kernels.cu)
 void launch_synth_kernel(const SynthArgs& a, int K, r4wb_fmt fmt, int grid, cudaStream_t st);
 int synth_max_blocks_per_sm(int K, r4wb_fmt fmt, size_t smem);
+void launch_synth_direct(const SynthArgs& a, r4wb_fmt fmt, cudaStream_t st);
 void launch_block_params(const ScenConst&, const SatConst*, const PhaseSegment*, uint64_t, uint32_t, BlockSat*, BlockHdr*, cudaStream_t);
 void launch_phase_scan(const SatConst*, uint32_t, uint32_t, BlockSat*, cudaStream_t);
 void launch_tile_params(const SynthArgs& a, uint32_t tb_begin, uint32_t tb_count, uint32_t tile_samples, TileRec* out, cudaStream_t st);
@@ -47,6 +48,8 @@ Scenario::Scenario(const r4wb_scenario_cfg& cfg) : md_(cfg)
     R4WB_CUDA(cudaMemcpyAsync(d_segments_.reserve(md_.segments.size()), md_.segments.data(), md_.segments.size() * sizeof(PhaseSegment), cudaMemcpyHostToDevice, st));
     R4WB_CUDA(cudaMemcpyAsync(d_perbits_.reserve(md_.perbits.size()), md_.perbits.data(), md_.perbits.size() * 4, cudaMemcpyHostToDevice, st));
     R4WB_CUDA(cudaMemcpyAsync(d_satcode_.reserve(md_.satcode.size()), md_.satcode.data(), md_.satcode.size() * sizeof(SatCode), cudaMemcpyHostToDevice, st));
+    R4WB_CUDA(cudaMemcpyAsync(d_dsat_.reserve(md_.dsat.size()), md_.dsat.data(), md_.dsat.size() * sizeof(DirectSat), cudaMemcpyHostToDevice, st));
+    R4WB_CUDA(cudaMemcpyAsync(d_dcode_.reserve(md_.dcodebits.size()), md_.dcodebits.data(), md_.dcodebits.size() * 4, cudaMemcpyHostToDevice, st));
     R4WB_CUDA(cudaMemcpyAsync(d_ytab_.reserve(md_.ytab.size()), md_.ytab.data(), md_.ytab.size() * 4, cudaMemcpyHostToDevice, st));
     R4WB_CUDA(cudaMemcpyAsync(d_taps_.reserve(64), md_.taps_f, sizeof md_.taps_f, cudaMemcpyHostToDevice, st));
     R4WB_CUDA(cudaMemcpyAsync(d_etab_.reserve(64), md_.etab_f, sizeof md_.etab_f, cudaMemcpyHostToDevice, st));
@@ -156,6 +159,7 @@ SynthArgs Scenario::base_args(const BlockSat* tab, const BlockHdr* hdr, uint64_t
     const ScenConst& sc = md_.sc;
     SynthArgs a{};
     a.tab = tab; a.hdr = hdr; a.perbits = d_perbits_.p; a.satcode = d_satcode_.p; a.taps = d_taps_.p; a.etab = d_etab_.p; a.ytab = d_ytab_.p; a.clslut = d_clslut_.p; a.lut_den = sc.lut_den; a.ystride = sc.ystride;
+    a.dsat = d_dsat_.p; a.dcode = d_dcode_.p; a.any_direct = md_.any_direct ? 1u : 0u; a.max_block_n = (uint32_t)max_block_n;
     const uint32_t tile = (uint32_t)synth_tile_samples(md_.tile_k);
     a.tiles_per_block = (uint32_t)((max_block_n + tile - 1) / tile);
     a.n_sats = sc.n_sats; a.nw64 = md_.nw64; a.flags = sc.flags;
@@ -202,6 +206,7 @@ void Scenario::launch_synth(const BlockSat* tab, const BlockHdr* hdr, const Tile
     prof_begin(0, st);
     launch_synth_kernel(a, tile_k, fmt, grid, st);
     prof_end(st);
+    if (md_.any_direct) launch_synth_direct(a, fmt, st);      // GPS L5 / GLONASS: added to what k_synth wrote
 }
 
 static bool periodic_enabled()
@@ -220,7 +225,7 @@ bool Scenario::plan_periodic()
     P.enabled = enabled;
     P.planned = true; P.ok = false; P.blk0 = tab_blk0_; P.blk1 = tab_blk1_; P.T_n = 0;
     const ScenConst& sc = md_.sc;
-    if (!enabled || sc.n_sats == 0 || md_.any_dynamic || md_.any_var_visibility) return false;
+    if (!enabled || sc.n_sats == 0 || md_.any_dynamic || md_.any_var_visibility || md_.any_direct) return false;
     P.ns = periodic_padded_sats(sc.n_sats);
     if (P.ns == 0) return false;
     // one primary-code period must be a whole number of output samples, the same for every satellite

@@ -280,6 +280,64 @@ __global__ void __launch_bounds__(kThreads, K <= 5 ? 3 : 2) k_synth(SynthArgs a)
 }
 
 // ----------------------------------------------------------------------------------------------
+// Direct path: satellites whose chip rate is not 1.023 MHz (GPS L5 at 10.23 Mchip/s: up to 17 chip boundaries inside one
+// 63-tap window; GLONASS L1OF at 0.511 Mchip/s: another sample lattice).  One thread per output sample evaluates the
+// reference's 63-tap sum literally per satellite (f64 chip index per tap, synth_math.cuh::direct_fir) and ADDS the rotated
+// contribution to the sample k_synth has already written (noise and the 1.023 MHz satellites).  Slow next to the collapsed
+// path (63 f64 divisions per satellite-sample) but the same arithmetic as the reference; float formats only.
+template <typename OutT>
+__global__ void __launch_bounds__(256) k_synth_direct(SynthArgs a)
+{
+    __shared__ double s_dp[8];
+    const uint32_t tb = a.tb_begin + blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+    const BlockHdr hd = a.hdr[tb];
+    const uint64_t m = hd.first + i;
+    double dp = 0.0;
+    if (i < hd.n && m >= a.out_first && m < a.out_first + a.out_n) {
+        const BlockSat* row = a.tab + (size_t)tb * a.n_sats;
+        float re = 0.0f, im = 0.0f;
+        bool any = false;
+        for (uint32_t s = 0; s < a.n_sats; ++s) {
+            const DirectSat d = a.dsat[s];
+            if (!d.direct || !(row[s].flags & 1u)) continue;
+            const float2 v = direct_sample(row[s], a.tab, a.dcode + (size_t)s * kDirectWords, a.taps, i, d);
+            re += v.x; im += v.y;
+            any = true;
+        }
+        if (any) {
+            OutT* o = reinterpret_cast<OutT*>(a.out) + (m - a.out_first);
+            const OutT old = *o;
+            OutT nw;
+            nw.x = old.x + re; nw.y = old.y + im;
+            *o = nw;
+            const float ox = (float)old.x, oy = (float)old.y, nx = (float)nw.x, ny = (float)nw.y;     // power of the cf32 sample, as k_synth
+            dp = ((double)nx * nx + (double)ny * ny) - ((double)ox * ox + (double)oy * oy);
+        }
+    }
+    if (a.power_sum) {
+        for (int off = 16; off > 0; off >>= 1) dp += __shfl_xor_sync(0xffffffffu, dp, off);
+        if ((threadIdx.x & 31u) == 0) s_dp[threadIdx.x >> 5] = dp;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double t = 0.0;
+            for (int w = 0; w < 8; ++w) t += s_dp[w];
+            if (t != 0.0) atomicAdd(a.power_sum, t);
+        }
+    }
+}
+
+void launch_synth_direct(const SynthArgs& a, r4wb_fmt fmt, cudaStream_t st)
+{
+    if (fmt != R4WB_FMT_CF32 && fmt != R4WB_FMT_CF64)
+        fail(R4WB_ERR_NOT_SUPPORTED, "GPS L5 / GLONASS satellites are rendered in the float formats only (cf32, cf64)");
+    if (a.tb_count == 0 || a.max_block_n == 0) return;
+    const dim3 grid((a.max_block_n + 255) / 256, a.tb_count);
+    if (fmt == R4WB_FMT_CF32) k_synth_direct<float2><<<grid, 256, 0, st>>>(a);
+    else k_synth_direct<double2><<<grid, 256, 0, st>>>(a);
+    R4WB_LAUNCH_CHECK();
+}
+
+// ----------------------------------------------------------------------------------------------
 // launchers (called from synth_host.cu)
 template <int K, int FMT>
 static void launch_synth_t(const SynthArgs& a, int grid, size_t smem, cudaStream_t st)

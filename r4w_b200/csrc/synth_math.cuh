@@ -197,14 +197,37 @@ R4WB_HD void fill_block_sat(const ScenConst& sc, const SatConst& st, const Phase
 
     // code phase of the block (satellite_emitter.rs:228-242)
     const double total_delay_s = add_rn(add_rn(div_rn(range_m, kC), iono_s), tropo_s);
-    const double chips_delay = mul_rn(total_delay_s, sc.chip_rate);
+    const double chips_delay = mul_rn(total_delay_s, st.chip_rate);
     const SatCode& cd = st.code;
     const double phase0 = fmod(chips_delay, (double)cd.code_len);
     const double eq = div_rn(chips_delay, (double)cd.code_len);
     const uint64_t e0 = eq > 0.0 ? (uint64_t)eq : 0ull;
 
-    // fixed-point half-chip position of the block's first oversample: exact rational part + f64 corrections
     const uint64_t G = first * (uint64_t)kOversample;
+    if (st.direct) {     // other chip rates: k_synth_direct evaluates the reference expression per tap from phase0 / e0 / G
+        uint64_t phi_d;
+        long long f_d, df_d;
+        if (st.static_phase) {
+            if (sc.flags & R4WB_FLAG_CLOSED_FORM_PHASE) {
+                f_d = (long long)llrint(ds / fs * kTwo64);
+                phi_d = (uint64_t)f_d * m_or_phi;
+            } else {
+                double x, step;
+                static_phase_at(segs + st.seg_begin, st.seg_count, m_or_phi, x, step);
+                f_d = (long long)llrint(step / (2.0 * kPi) * kTwo64);
+                phi_d = cycles_to_fixed(x / (2.0 * kPi));
+            }
+            df_d = 0;
+        } else {
+            f_d = (long long)llrint(ds / fs * kTwo64);
+            df_d = (long long)llrint((de - ds) / ((double)n * fs) * kTwo64);
+            phi_d = m_or_phi;
+        }
+        o.U = 0; o.phi = phi_d; o.f = f_d; o.df = df_d; o.phase0 = phase0; o.G = G; o.n = n; o.e0 = (uint32_t)e0;
+        o.amp = (float)(amp * st.amp_scale); o.flags = (visible ? 1u : 0u) | 32u; o.prev = -1; o.eps46 = 0; o.eps_t = 0; o.pad = 0;
+        return;
+    }
+    // fixed-point half-chip position of the block's first oversample: exact rational part + f64 corrections
     const unsigned __int128 n1 = (unsigned __int128)G * sc.ratB;
     const uint64_t ci = (uint64_t)(n1 / sc.ratA);
     const uint64_t cr = (uint64_t)(n1 % sc.ratA);
@@ -365,6 +388,7 @@ R4WB_HD TileSat tile_sat(const BlockSat& b, const BlockSat* __restrict__ tab, ui
     t.hb = h0 - (uint32_t)(kJ + 2);            // may go "negative": all uses are modulo differences
     t.phi = b.phi; t.f = b.f; t.df = b.df; t.amp = b.amp; t.eps_t = b.eps_t;
     uint32_t fl = b.flags & 3u;
+    if (b.flags & 32u) fl &= ~1u;                 // direct-path satellite: not rendered by k_synth
     // rotation over one step of 2*kSynthThreads samples, starting at sample i: phase(i + n) - phase(i) with
     // phase(i) = phi + (i+1) f + i(i+1)/2 df
     const uint64_t n = (uint64_t)(2 * kSynthThreads);
@@ -454,6 +478,53 @@ R4WB_HD_NOINLINE float fir_direct(const BlockSat& cur, const BlockSat* __restric
         acc += sgn ? -taps[k] : taps[k];
     }
     return acc;
+}
+
+// ---- direct path (chip rates other than 1.023 MHz: GPS L5, GLONASS L1OF) -------------------------------------------------
+// sign bit (1 <=> -1) of oversample q of block entry bs: the reference expression, literally (satellite_emitter.rs:264-292,
+// plain BPSK branch :334-336): chip = (cf % code_length) as usize, epoch = e0 + (cf / code_length) as usize, nav bit per epoch
+R4WB_HD uint32_t direct_sign(const BlockSat& bs, long long q, const uint32_t* __restrict__ code, const DirectSat& d)
+{
+    const double g = (double)(bs.G + (uint64_t)q);
+    const double cf = add_rn(bs.phase0, div_rn(g, d.spc));
+    const double cl = (double)d.code_len;
+    const double cm = fmod(cf, cl);
+    uint32_t c = cm > 0.0 ? (uint32_t)cm : 0u;
+    if (c > d.code_len - 1u) c = d.code_len - 1u;
+    const double eq = div_rn(cf, cl);
+    const uint64_t ep = (uint64_t)bs.e0 + (eq > 0.0 ? (uint64_t)eq : 0ull);
+    return ((code[c >> 5] >> (c & 31u)) ^ (uint32_t)(d.epoch_bits >> (uint32_t)(ep % d.epoch_period))) & 1u;
+}
+
+// the reference's 63-tap loop (fir.rs:392-409) for output sample i of block entry `cur`, FIR history from its predecessor
+R4WB_HD float direct_fir(const BlockSat& cur, const BlockSat* __restrict__ tab, const uint32_t* __restrict__ code,
+                         const float* __restrict__ taps, int i, const DirectSat& d)
+{
+    double acc = 0.0;
+    const long long g = (long long)kOversample * i;
+    for (int k = 0; k < kTaps; ++k) {
+        long long q = g - k;
+        const BlockSat* bs = &cur;
+        if (q < 0) {
+            if (cur.prev < 0) continue;                      // zero-initialised delay line
+            bs = &tab[cur.prev];
+            q += (long long)kOversample * bs->n;
+            if (q < 0) continue;                             // history older than one block: not modelled
+        }
+        acc += direct_sign(*bs, q, code, d) ? -(double)taps[k] : (double)taps[k];
+    }
+    return (float)acc;
+}
+
+// one direct-path satellite's contribution to output sample i of its block: amp * y * exp(j phase(i))
+R4WB_HD float2 direct_sample(const BlockSat& cur, const BlockSat* __restrict__ tab, const uint32_t* __restrict__ code,
+                             const float* __restrict__ taps, uint32_t i, const DirectSat& d)
+{
+    const float y = direct_fir(cur, tab, code, taps, (int)i, d);
+    const uint64_t ph = cur.phi + (uint64_t)(i + 1) * (uint64_t)cur.f + ((uint64_t)i * (i + 1) / 2) * (uint64_t)cur.df;
+    float sn, cs;
+    accurate_sincos_cycles(ph, &sn, &cs);
+    return make_float2(cur.amp * y * cs, cur.amp * y * sn);
 }
 
 // true when block `cur` continues its predecessor's code sequence exactly (same delay, adjacent in time): the

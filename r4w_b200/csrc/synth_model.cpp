@@ -48,6 +48,37 @@ void gps_ca_code_chips(uint32_t prn, int8_t* out /*[1023]*/)
     }
 }
 
+// Shift-register sequences in the product's own form (bit n of `taps` set <=> stage n+1 is fed back; the output is the last
+// stage; the register shifts toward the last stage) — what Lfsr::clock (core/spreading/lfsr.rs:58-72) computes.
+static uint32_t shift_register_step(uint32_t& state, uint32_t taps, int stages)
+{
+    const uint32_t out = (state >> (stages - 1)) & 1u;
+    uint32_t fb = state & taps;
+    fb ^= fb >> 16; fb ^= fb >> 8; fb ^= fb >> 4; fb ^= fb >> 2; fb ^= fb >> 1;
+    state = ((state << 1) | (fb & 1u)) & ((1u << stages) - 1u);
+    return out;
+}
+
+// GLONASS L1OF ranging code (gnss/prn.rs:170-216): 9 stages, 1 + x^5 + x^9, all ones; 511 chips, identical for every satellite
+void glonass_code_chips(int8_t* out /*[511]*/)
+{
+    uint32_t r = 0x1FFu;
+    for (int n = 0; n < 511; ++n) out[n] = shift_register_step(r, 0x110u, 9) ? -1 : 1;
+}
+
+// GPS L5 I5 code as the reference generates it (gnss/prn.rs:376-397): XA (x^13 + x^12 + x^10 + x^9 + 1, all ones) xor XB
+// (I5 taps 0x1AE3, start state derived from the PRN), 10 230 chips, no short cycle
+void gps_l5_i5_code_chips(uint32_t prn, int8_t* out /*[10230]*/)
+{
+    if (prn < 1 || prn > 32) fail(R4WB_ERR_INVALID_PARAMETER, "GPS L5 PRN must be 1-32, got %u", prn);
+    uint32_t xa = 0x1FFFu, xb = (prn * 0x2468u + 0x1357u) & 0x1FFFu;
+    if (xb == 0u) xb = 1u;
+    for (int n = 0; n < 10230; ++n) {
+        const uint32_t a = shift_register_step(xa, 0x1E01u, 13), b = shift_register_step(xb, 0x1AE3u, 13);
+        out[n] = (a ^ b) ? -1 : 1;
+    }
+}
+
 // 63-tap Blackman windowed-sinc low-pass, unity DC gain (core/filters/fir.rs:458-499, windows.rs:137-151)
 static void design_lowpass(double cutoff_hz, double rate_hz, double* h /*[63]*/)
 {
@@ -173,14 +204,17 @@ ScenarioModel::ScenarioModel(const r4wb_scenario_cfg& c_in) : cfg(c_in)
     const RxState rx0 = rx_at(rx, 0.0);
     // Virtual satellites: one per configured satellite, two for GalileoE1OS ((e1b - e1c) / sqrt 2 is a sum of two binary
     // sequences with the same delay and Doppler, and the FIR is linear; satellite_emitter.rs:307-321)
-    struct Virt { uint32_t cfg; uint32_t kind; double scale; };      // kind: 0 GPS C/A, 1 E1B, 2 E1C
+    struct Virt { uint32_t cfg; uint32_t kind; double scale; };      // kind: 0 GPS C/A, 1 E1B, 2 E1C, 3 GPS L5 (I5), 4 GLONASS L1OF
     std::vector<Virt> virt;
     for (uint32_t k = 0; k < cfg.n_sats; ++k) {
         const r4wb_sat_cfg& c = cfg_sats[k];
         const bool galileo = c.signal == R4WB_SIG_GALILEO_E1 || c.signal == R4WB_SIG_GALILEO_E1C || c.signal == R4WB_SIG_GALILEO_E1OS;
-        if (!galileo && c.signal != R4WB_SIG_GPS_L1CA)
-            fail(R4WB_ERR_NOT_SUPPORTED, "satellite %u: GPS L5 / GLONASS L1OF are not implemented on the GPU path", k);
-        if (galileo) {
+        if ((unsigned)c.signal > (unsigned)R4WB_SIG_GALILEO_E1OS) fail(R4WB_ERR_INVALID_PARAMETER, "satellite %u: unknown signal %u", k, (unsigned)c.signal);
+        if (c.signal == R4WB_SIG_GLONASS_L1OF) {
+            // the reference builds GlonassCodeGenerator::new(prn as i8), which asserts a frequency channel of -7..6 (prn.rs:181-183)
+            if (c.prn > 6) fail(R4WB_ERR_INVALID_PARAMETER, "GLONASS PRN (used as frequency channel) must be 0-6, got %u", c.prn);
+            if (c.plane >= 3 || c.slot >= 8) fail(R4WB_ERR_INVALID_PARAMETER, "GLONASS plane 0-2 / slot 0-7");
+        } else if (galileo) {
             if (c.prn < 1 || c.prn > 50) fail(R4WB_ERR_INVALID_PARAMETER, "Galileo PRN must be 1-50, got %u", c.prn);
             if (c.plane >= 3 || c.slot >= 10) fail(R4WB_ERR_INVALID_PARAMETER, "Galileo plane 0-2 / slot 0-9");
         } else {
@@ -188,6 +222,8 @@ ScenarioModel::ScenarioModel(const r4wb_scenario_cfg& c_in) : cfg(c_in)
             if (c.plane >= 6 || c.slot >= 6) fail(R4WB_ERR_INVALID_PARAMETER, "GPS plane 0-5 / slot 0-5");
         }
         if (c.signal == R4WB_SIG_GPS_L1CA) virt.push_back({k, 0u, 1.0});
+        else if (c.signal == R4WB_SIG_GPS_L5) virt.push_back({k, 3u, 1.0});
+        else if (c.signal == R4WB_SIG_GLONASS_L1OF) virt.push_back({k, 4u, 1.0});
         else if (c.signal == R4WB_SIG_GALILEO_E1) virt.push_back({k, 1u, 1.0});
         else if (c.signal == R4WB_SIG_GALILEO_E1C) virt.push_back({k, 2u, 1.0});
         else { const double sc2 = 1.0 / std::sqrt(2.0); virt.push_back({k, 1u, sc2}); virt.push_back({k, 2u, -sc2}); }
@@ -199,6 +235,9 @@ ScenarioModel::ScenarioModel(const r4wb_scenario_cfg& c_in) : cfg(c_in)
     cfg_index.assign(virt.size(), 0u);
     codebits.assign(std::max<size_t>(1, virt.size()) * 128, 0u);
     perbits.assign(std::max<size_t>(1, virt.size()) * kPerWords, 0u);
+    dsat.assign(std::max<size_t>(1, virt.size()), DirectSat{});
+    dcodebits.assign(std::max<size_t>(1, virt.size()) * kDirectWords, 0u);
+    const double os_rate_d = oc.sample_rate * (double)kOversample;
     for (uint32_t k = 0; k < (uint32_t)virt.size(); ++k) {
         const r4wb_sat_cfg& c = cfg_sats[virt[k].cfg];
         cfg_index[k] = virt[k].cfg;
@@ -206,7 +245,11 @@ ScenarioModel::ScenarioModel(const r4wb_scenario_cfg& c_in) : cfg(c_in)
         std::memset(&s, 0, sizeof s);
         s.amp_scale = virt[k].scale;
         s.orbit = nominal_orbit(c.signal, c.plane, c.slot);
-        s.carrier_hz = 1575420000.0;
+        // GnssSignal::carrier_frequency_hz / chipping_rate (gnss/types.rs:73-90)
+        s.carrier_hz = c.signal == R4WB_SIG_GPS_L5 ? 1176450000.0 : (c.signal == R4WB_SIG_GLONASS_L1OF ? 1602000000.0 : 1575420000.0);
+        s.chip_rate = virt[k].kind == 3 ? 10230000.0 : (virt[k].kind == 4 ? 511000.0 : sc.chip_rate);
+        s.direct = virt[k].kind >= 3 ? 1u : 0u;
+        if (s.direct) any_direct = true;
         s.has = c.has;
         s.orbital_dynamics = c.orbital_dynamics ? 1u : 0u;
         s.tx_power_dbw = c.tx_power_dbw;
@@ -241,21 +284,29 @@ ScenarioModel::ScenarioModel(const r4wb_scenario_cfg& c_in) : cfg(c_in)
 
         // code structure (satellite_emitter.rs:248-343)
         SatCode& cd = s.code;
-        int8_t chips[kCodeLen];
+        int8_t chips[10230];
         if (virt[k].kind == 0) { gps_ca_code_chips(c.prn, chips); cd.code_len = 1023; cd.has_boc = 0; }
+        else if (virt[k].kind == 3) { gps_l5_i5_code_chips(c.prn, chips); cd.code_len = 10230; cd.has_boc = 0; }
+        else if (virt[k].kind == 4) { glonass_code_chips(chips); cd.code_len = 511; cd.has_boc = 0; }
         else { e1_code_chips(virt[k].kind == 1 ? 0u : 1u, c.prn, chips); cd.code_len = (uint32_t)kCodeLen; cd.has_boc = 1; }
         cd.per_len = 2u * cd.code_len;
         cd.epoch_period = 1; cd.epoch_bits = 0;
         if (virt[k].kind == 2) {                              // E1C: 25-chip secondary code, one chip per 4 ms epoch
             cd.epoch_period = (uint32_t)kSecLen; cd.epoch_bits = kSecBits;
         } else if (c.nav_data) {                              // nav bit (bit_idx + prn) % 2, bit_idx = epoch / periods_per_bit (:286-292)
-            const uint32_t ppb = virt[k].kind == 0 ? 20u : 1u;   // 1 / (50 bps x 1 ms), 1 / (250 bps x 4 ms)
+            const uint32_t ppb = virt[k].kind == 1 ? 1u : 20u;   // 1 / (250 bps x 4 ms); 1 / (50 bps x 1 ms) for GPS L1 C/A, L5, GLONASS
             cd.epoch_period = 2u * ppb;
             for (uint32_t e = 0; e < cd.epoch_period; ++e)
                 if (((e / ppb) + c.prn) % 2u != 0u) cd.epoch_bits |= 1ull << e;
         }
         cd.hc_mod = cd.per_len * cd.epoch_period;
         satcode[k] = cd;
+        if (s.direct) {      // direct path: packed chips + the per-satellite samples_per_chip of satellite_emitter.rs:245
+            dsat[k] = DirectSat{os_rate_d / s.chip_rate, cd.epoch_bits, 1u, cd.code_len, cd.epoch_period, 0u};
+            for (uint32_t i = 0; i < cd.code_len; ++i)
+                dcodebits[(size_t)k * kDirectWords + (i >> 5)] |= (chips[i] < 0 ? 1u : 0u) << (i & 31);
+            continue;        // no half-chip tables: k_synth skips this satellite
+        }
         for (uint32_t i = 0; i < cd.code_len; ++i)
             codebits[(size_t)k * 128 + (i >> 5)] |= (chips[i] < 0 ? 1u : 0u) << (i & 31);
         // half-chip signs of one primary-code period (with BOC(1,1): second half of every chip inverted), followed by a
@@ -356,7 +407,7 @@ void ScenarioModel::status(uint64_t current, r4wb_sat_status* out, uint32_t cap,
         const r4wb_sat_cfg& c = cfg_sats[k];
         Vec3 sp, sv;
         orbit_state(nominal_orbit(c.signal, c.plane, c.slot), t, sp, sv);
-        const double carrier_hz = 1575420000.0;
+        const double carrier_hz = c.signal == R4WB_SIG_GPS_L5 ? 1176450000.0 : (c.signal == R4WB_SIG_GLONASS_L1OF ? 1602000000.0 : 1575420000.0);
         const Look la = look_from(rx_pos, rx_lla, sp);
         r4wb_sat_status& o = out[k];
         std::memset(&o, 0, sizeof o);

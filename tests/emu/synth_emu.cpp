@@ -144,6 +144,27 @@ struct Emu {
     {
         if (md.tile_k == 5) render_t<5>(tb_tab, tb_hdr, tb_begin, tb_count, out_first, out_n, out, max_block_n, only_sat, n_ambiguous);
         else render_t<10>(tb_tab, tb_hdr, tb_begin, tb_count, out_first, out_n, out, max_block_n, only_sat, n_ambiguous);
+        if (!md.any_direct) return;
+        // k_synth_direct, thread loop flattened: GPS L5 / GLONASS satellites added to what the main pass wrote
+        const uint32_t ns = md.sc.n_sats;
+        for (uint32_t tb = tb_begin; tb < tb_begin + tb_count; ++tb) {
+            const BlockHdr hd = tb_hdr[tb];
+            const BlockSat* row = tb_tab + (size_t)tb * ns;
+            for (uint32_t i = 0; i < hd.n; ++i) {
+                const uint64_t m = hd.first + i;
+                if (m < out_first || m >= out_first + out_n) continue;
+                float re = 0.0f, im = 0.0f;
+                for (uint32_t s = 0; s < ns; ++s) {
+                    if (only_sat >= 0 && (int)s != only_sat) continue;
+                    const DirectSat d = md.dsat[s];
+                    if (!d.direct || !(row[s].flags & 1u)) continue;
+                    const float2 v = direct_sample(row[s], tb_tab, md.dcodebits.data() + (size_t)s * kDirectWords, md.taps_f, i, d);
+                    re += v.x; im += v.y;
+                }
+                out[2 * (m - out_first)] += re;
+                out[2 * (m - out_first) + 1] += im;
+            }
+        }
     }
 };
 

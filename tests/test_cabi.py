@@ -106,3 +106,23 @@ def test_gps_ca_codes_match_oracle(L, oracle):
         assert np.array_equal(R.gps_ca_code(prn), oracle.gps_ca_code(prn))
     with pytest.raises(R.R4wB200Error):
         R.gps_ca_code(33)
+
+
+def test_gps_l5_and_glonass_codes_match_oracle(L, oracle):
+    """the product's own shift-register generators against the oracle's restatement of GpsL5CodeGenerator / GlonassCodeGenerator
+    (gnss/prn.rs:170-216, 345-397); reference KATs: test_glonass_code_length (511), test_gps_l5_code_length (10230),
+    test_gps_l5_iq_different; plus the m-sequence property of the GLONASS code (autocorrelation -1 off the peak)"""
+    import r4w_b200 as R
+    g = R.glonass_code()
+    assert g.size == 511 and np.array_equal(g, oracle.glonass_code(0)) and np.array_equal(g, oracle.glonass_code(6))
+    gi = g.astype(np.int64)
+    assert int(gi @ gi) == 511 and all(int(gi @ np.roll(gi, k)) == -1 for k in (1, 7, 255, 510))
+    for prn in (1, 7, 32):
+        c = R.gps_l5_code(prn)
+        assert c.size == 10230 and np.array_equal(c, oracle.gps_l5_code(prn))
+    assert not np.array_equal(oracle.gps_l5_code(1), oracle.gps_l5_code(1, q_channel=True))
+    assert not np.array_equal(R.gps_l5_code(1), R.gps_l5_code(2))
+    with pytest.raises(R.R4wB200Error):
+        R.gps_l5_code(33)
+    with pytest.raises(ValueError):
+        oracle.glonass_code(7)

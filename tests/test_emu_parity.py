@@ -195,8 +195,10 @@ def _signal_variant(signals):
     cfg.satellites = cfg.satellites[: len(signals)]
     for s, (sig, prn, nav) in zip(cfg.satellites, signals):
         s.signal, s.prn, s.nav_data = sig, prn, nav
-        if sig == "GpsL1Ca":
+        if sig in ("GpsL1Ca", "GpsL5"):
             s.plane, s.slot = min(s.plane, 5), min(s.slot, 5)
+        if sig == "GlonassL1of":
+            s.plane, s.slot = min(s.plane, 2), min(s.slot, 7)
     return cfg
 
 
@@ -205,6 +207,10 @@ SIGNAL_CASES = {
     "galileo_e1b": [("GalileoE1", 3, True), ("GalileoE1", 25, False)],                       # BOC(1,1), nav bit per 4 ms epoch
     "galileo_e1os": [("GalileoE1OS", 8, True), ("GalileoE1OS", 2, False), ("GalileoE1C", 5, False)],   # (e1b - e1c) / sqrt 2
     "mixed": [("GpsL1Ca", 5, True), ("GalileoE1", 11, True), ("GalileoE1C", 12, False), ("GalileoE1OS", 13, True)],
+    # chip rates other than 1.023 MHz: the direct path (k_synth_direct)
+    "glonass": [("GlonassL1of", 3, True), ("GlonassL1of", 0, False)],                       # 0.511 Mchip/s, 511 chips, PRN = frequency channel
+    "gps_l5": [("GpsL5", 7, True), ("GpsL5", 32, False)],                                   # 10.23 Mchip/s, 10 230 chips (aliased at 5 MHz)
+    "all_signals": [("GlonassL1of", 3, True), ("GpsL5", 7, True), ("GpsL1Ca", 9, True), ("GalileoE1C", 12, False), ("GalileoE1OS", 2, True)],
 }
 
 

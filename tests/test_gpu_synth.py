@@ -207,10 +207,14 @@ def test_device_prologue_rounds_like_host(gpu, emu):
 
 def test_unsupported_inputs_fail_loudly(gpu):
     cfg = _cfg("e1c_prn3_20s_withdoppler")
-    bad = cfg.copy(); bad.satellites[0].signal = "GpsL5"
+    bad = cfg.copy(); bad.satellites[0].signal = "GlonassL1of"; bad.satellites[0].prn = 9      # frequency channel must be -7..6 (prn.rs:181-183)
     with pytest.raises(gpu.R4wB200Error) as e:
         gpu.GnssScenario(bad)
-    assert e.value.code == 7                    # NotSupported, never a silent CPU path
+    assert e.value.code == 5
+    l5 = cfg.copy(); l5.satellites[0].signal = "GpsL5"; l5.satellites[0].plane = 1; l5.satellites[0].slot = 1
+    with pytest.raises(gpu.R4wB200Error) as e:          # direct-path satellites: float sink formats only, never a silent CPU path
+        gpu.GnssScenario(l5).generate_range_format(0, 5000, "ci8")
+    assert e.value.code == 7
     bad = cfg.copy(); bad.satellites[0].prn = 51
     with pytest.raises(gpu.R4wB200Error):
         gpu.GnssScenario(bad)
@@ -271,9 +275,10 @@ def test_integer_sink_formats_match_oracle(gpu, oracle, fmt, lsb):
             assert np.abs(true.astype(np.int64)).max() < (32767 if fmt == "ci16" else 127 if fmt == "ci8" else 255)
 
 
-@pytest.mark.parametrize("case", ["gps_l1ca", "galileo_e1b", "galileo_e1os", "mixed"])
+@pytest.mark.parametrize("case", ["gps_l1ca", "galileo_e1b", "galileo_e1os", "mixed", "glonass", "gps_l5", "all_signals"])
 def test_other_signals_match_oracle(gpu, oracle, case):
-    """GPS L1 C/A, Galileo E1B and the E1OS composite (satellite_emitter.rs:248-343) on the GPU path"""
+    """GPS L1 C/A, Galileo E1B, the E1OS composite (satellite_emitter.rs:248-343) and, through the direct path,
+    GPS L5 and GLONASS L1OF on the GPU"""
     from tests.test_emu_parity import SIGNAL_CASES, _signal_variant
     cfg = _signal_variant(SIGNAL_CASES[case])
     for first, n in ((0, 20000), (49_990_000, 15000)):
