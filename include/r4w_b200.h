@@ -286,6 +286,24 @@ r4wb_error r4wb_track_state_get(const r4wb_tracker* h, r4wb_track_state* out, ui
 /* TrackingChannel::nav_bits :339-342: *n = bits detected so far, the first min(cap, *n) copied to out */
 r4wb_error r4wb_track_nav_bits(const r4wb_tracker* h, uint32_t channel, int8_t* out, uint64_t cap, uint64_t* n);
 
+/* ---- r4w-sim generic scenario engine: the per-sample loops of ScenarioEngine::generate_block,
+ * crates/r4w-sim/src/scenario/engine.rs:61-137.  The emitters are caller objects (trait Emitter) and the per-block geometry
+ * (:68-101) is the caller's f64 work; the composer owns ScenarioEngine::carrier_phases and the noise stream. ---- */
+typedef struct r4wb_composer r4wb_composer;
+/* noise_std = sqrt(ScenarioConfig::noise_power_linear() / 2) (engine.rs:126-127), seed = ScenarioConfig::seed */
+r4wb_error r4wb_composer_create(uint32_t n_emitters, double sample_rate, double noise_std, uint64_t seed, r4wb_composer** out);
+void r4wb_composer_destroy(r4wb_composer* h);
+/* ScenarioEngine::reset, engine.rs:149-153 */
+r4wb_error r4wb_composer_reset(r4wb_composer* h);
+/* One block: baseband is [n_emitters][n] (Emitter::generate_iq of every emitter; rows of inactive emitters are ignored),
+ * doppler_hz / amplitude / active are per emitter (active may be NULL = all active).  out[n] = sum of the Doppler-rotated,
+ * scaled emitters + receiver noise; the carrier phases advance as engine.rs:108-113. */
+r4wb_error r4wb_composer_block(r4wb_composer* h, const void* baseband, r4wb_fmt in_fmt, r4wb_mem in_where, uint64_t n,
+                               const double* doppler_hz, const double* amplitude, const uint8_t* active, void* out,
+                               r4wb_fmt out_fmt, r4wb_mem out_where);
+/* ScenarioEngine::carrier_phases (radians) after the last block */
+r4wb_error r4wb_composer_phases(const r4wb_composer* h, double* out, uint32_t cap);
+
 #ifdef __cplusplus
 }
 #endif

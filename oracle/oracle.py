@@ -22,6 +22,7 @@ def build(force: bool = False) -> str:
     src = os.path.join(_HERE, "r4w_oracle.c")
     stale = (not os.path.exists(_SO)) or os.path.getmtime(_SO) < max(
         os.path.getmtime(src), os.path.getmtime(os.path.join(_HERE, "r4w_oracle_track.c")),
+        os.path.getmtime(os.path.join(_HERE, "r4w_oracle_sim.c")),
         os.path.getmtime(os.path.join(_HERE, "r4w_oracle.h")))
     if force or stale:
         subprocess.check_call(["make", "-C", _HERE, "-B", "libr4w_oracle.so"], stdout=subprocess.DEVNULL)
@@ -98,6 +99,11 @@ def lib():
         L.orc_saastamoinen_zenith_m.restype = d
         L.orc_to_int_format.argtypes = [vp, sz, C.c_int, vp]
         L.orc_to_int_format.restype = C.c_int
+        L.orc_sim_compose_emitter.argtypes = [vp, sz, d, d, d, vp, vp]
+        L.orc_sim_link.argtypes = [vp, vp, vp, vp, d, d, vp]
+        L.orc_sim_noise_power.argtypes = [d, d]; L.orc_sim_noise_power.restype = d
+        L.orc_sim_trajectory.argtypes = [i32, vp, d, vp]
+        L.orc_sim_waypoints.argtypes = [vp, sz, d, vp]
         L.orc_track_new.argtypes = [C.c_uint8, sz, d, d, d, d]; L.orc_track_new.restype = vp
         L.orc_track_free.argtypes = [vp]
         L.orc_track_set_dll_bandwidth.argtypes = [vp, d]
@@ -423,3 +429,48 @@ def dll_s_curve(el_spacing: float, num_points: int):
     e = np.zeros(num_points); d = np.zeros(num_points)
     lib().orc_dll_s_curve(float(el_spacing), int(num_points), _ptr(e), _ptr(d))
     return e, d
+
+
+# ---- r4w-sim generic scenario engine (r4w_oracle_sim.c; crates/r4w-sim/src/scenario/) -----------------------------------
+def sim_trajectory(kind: str, params, t: float) -> np.ndarray:
+    """Trajectory::state_at -> [x, y, z, vx, vy, vz] (ECEF).  kind: Static (lat, lon, alt), Linear (+ ve, vn, vu),
+    Circular (+ radius_m, omega_rad_s, initial_bearing_deg), Waypoints (rows of t, lat, lon, alt)"""
+    out = np.zeros(6)
+    if kind == "Waypoints":
+        p = np.ascontiguousarray(params, np.float64).reshape(-1, 4)
+        lib().orc_sim_waypoints(_ptr(p), p.shape[0], float(t), _ptr(out))
+    else:
+        p = np.zeros(6); q = np.asarray(params, np.float64).ravel(); p[:q.size] = q
+        lib().orc_sim_trajectory({"Static": 0, "Linear": 1, "Circular": 3}[kind], _ptr(p), float(t), _ptr(out))
+    return out
+
+
+def sim_link(rx6, em6, carrier_hz: float, power_dbm: float):
+    """engine.rs:82-98 -> (range_m, doppler_hz, path_loss_db, rx_amplitude)"""
+    rx = np.ascontiguousarray(rx6, np.float64); em = np.ascontiguousarray(em6, np.float64)
+    out = np.zeros(4)
+    lib().orc_sim_link(_ptr(rx[:3].copy()), _ptr(rx[3:].copy()), _ptr(em[:3].copy()), _ptr(em[3:].copy()), float(carrier_hz), float(power_dbm), _ptr(out))
+    return tuple(float(v) for v in out)
+
+
+def sim_noise_power(noise_floor_dbw_hz: float, sample_rate: float) -> float:
+    return float(lib().orc_sim_noise_power(float(noise_floor_dbw_hz), float(sample_rate)))
+
+
+class OracleComposer:
+    """the Doppler / amplitude / sum loops of ScenarioEngine::generate_block (engine.rs:105-122), noise-free"""
+
+    def __init__(self, n_emitters: int, sample_rate: float):
+        self.fs = float(sample_rate)
+        self.phases = np.zeros(n_emitters)
+
+    def block(self, baseband: np.ndarray, doppler_hz, amplitude, active=None) -> np.ndarray:
+        bb = np.ascontiguousarray(baseband, np.complex128)
+        out = np.zeros(bb.shape[1], np.complex128)
+        for e in range(bb.shape[0]):
+            if active is not None and not active[e]:
+                continue
+            ph = C.c_double(self.phases[e])
+            lib().orc_sim_compose_emitter(_ptr(bb[e]), bb.shape[1], float(doppler_hz[e]), self.fs, float(amplitude[e]), C.byref(ph), _ptr(out))
+            self.phases[e] = ph.value
+        return out

@@ -190,6 +190,15 @@ double orc_loop_filter_2nd_run(double bw, double T, double disc, size_t n_update
 double orc_loop_filter_3rd_run(double bw, double T, double disc, size_t n_updates);
 void orc_dll_s_curve(double el_spacing, size_t num_points, double* err, double* disc);
 
+/* ---- r4w-sim generic scenario engine, r4w_oracle_sim.c: crates/r4w-sim/src/scenario/ ---- */
+void orc_sim_compose_emitter(const orc_c64* baseband, size_t n, double doppler_hz, double sample_rate, double rx_amplitude,
+                             double* carrier_phase, orc_c64* composite);
+void orc_sim_link(const double* rx_pos, const double* rx_vel, const double* em_pos, const double* em_vel, double carrier_hz,
+                  double power_dbm, double* out4);
+double orc_sim_noise_power(double noise_floor_dbw_hz, double sample_rate);
+void orc_sim_trajectory(int kind, const double* p, double t, double* out6);
+void orc_sim_waypoints(const double* points, size_t n, double t, double* out6);
+
 #ifdef __cplusplus
 }
 #endif

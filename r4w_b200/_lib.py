@@ -79,6 +79,11 @@ SYMBOLS = {
     "r4wb_pcps_acquire_batch": (_int, [_vp, _vp, _int, _int, _u64, _u64, _u64, _vp, _u64, _vp, _u32, _vp]),
     "r4wb_pcps_acquire_grid": (_int, [_vp, _vp, _int, _u64, _vp, _u64, _vp, _u64]),
     "r4wb_pcps_guard_count": (_u64, [_vp]),
+    "r4wb_composer_create": (_int, [_u32, _dbl, _dbl, _u64, C.POINTER(_vp)]),
+    "r4wb_composer_destroy": (None, [_vp]),
+    "r4wb_composer_reset": (_int, [_vp]),
+    "r4wb_composer_block": (_int, [_vp, _vp, _int, _int, _u64, _vp, _vp, _vp, _vp, _int, _int]),
+    "r4wb_composer_phases": (_int, [_vp, _vp, _u32]),
     "r4wb_track_create": (_int, [_vp, _u32, C.POINTER(_vp)]),
     "r4wb_track_destroy": (None, [_vp]),
     "r4wb_track_process": (_int, [_vp, _vp, _int, _int, _u64, _u64, _u64, _vp, _u64, _vp]),

@@ -5,6 +5,7 @@
 #include <new>
 
 #include "acq.cuh"
+#include "compose.cuh"
 #include "synth.cuh"
 #include "track.cuh"
 
@@ -56,6 +57,7 @@ using namespace r4wb;
 
 struct r4wb_scenario { Scenario impl; explicit r4wb_scenario(const r4wb_scenario_cfg& c) : impl(c) {} };
 struct r4wb_pcps { Pcps impl; r4wb_pcps(uint64_t n, double fs) : impl(n, fs) {} };
+struct r4wb_composer { Composer impl; r4wb_composer(uint32_t n, double fs, double sd, uint64_t seed) : impl(n, fs, sd, seed) {} };
 struct r4wb_tracker { TrackerBank impl; r4wb_tracker(const r4wb_track_cfg* c, uint32_t n) : impl(c, n) {} };
 
 extern "C" {
@@ -341,6 +343,42 @@ r4wb_error r4wb_track_nav_bits(const r4wb_tracker* h, uint32_t channel, int8_t* 
 {
     if (!h || !n) { t_error = "handle/n is NULL"; return R4WB_ERR_NULL_POINTER; }
     return guard([&] { *n = h->impl.nav_bits(channel, out, cap); });
+}
+
+
+// ---- r4w-sim composer
+r4wb_error r4wb_composer_create(uint32_t n_emitters, double sample_rate, double noise_std, uint64_t seed, r4wb_composer** out)
+{
+    if (!out) { t_error = "out is NULL"; return R4WB_ERR_NULL_POINTER; }
+    *out = nullptr;
+    return guard([&] {
+        require_device();
+        *out = new r4wb_composer(n_emitters, sample_rate, noise_std, seed);
+    });
+}
+
+void r4wb_composer_destroy(r4wb_composer* h) { delete h; }
+
+r4wb_error r4wb_composer_reset(r4wb_composer* h)
+{
+    if (!h) { t_error = "handle is NULL"; return R4WB_ERR_NULL_POINTER; }
+    h->impl.reset();
+    return R4WB_OK;
+}
+
+r4wb_error r4wb_composer_block(r4wb_composer* h, const void* baseband, r4wb_fmt in_fmt, r4wb_mem in_where, uint64_t n, const double* doppler_hz,
+                               const double* amplitude, const uint8_t* active, void* out, r4wb_fmt out_fmt, r4wb_mem out_where)
+{
+    if (!h) { t_error = "handle is NULL"; return R4WB_ERR_NULL_POINTER; }
+    return guard([&] { h->impl.block(baseband, in_fmt, in_where, n, doppler_hz, amplitude, active, out, out_fmt, out_where); });
+}
+
+r4wb_error r4wb_composer_phases(const r4wb_composer* h, double* out, uint32_t cap)
+{
+    if (!h || !out) { t_error = "handle/out is NULL"; return R4WB_ERR_NULL_POINTER; }
+    const std::vector<double>& p = h->impl.phases();
+    for (uint32_t k = 0; k < cap && k < p.size(); ++k) out[k] = p[k];
+    return R4WB_OK;
 }
 
 }  // extern "C"
