@@ -5,11 +5,12 @@
 //   process (E/P/L correlators, discriminators, loop filters, NCO updates, C/N0, lock, nav bits)   :177-313
 //   estimate_cn0 :316-337, LoopFilter2nd :365-397, LoopFilter3rd :399-437
 // The reference runs one channel at a time, one code period per call; the loop feedback makes the periods of a channel
-// sequential, the channels are independent.  k_track: one CTA per channel walks its periods in order; inside a period
-// the 512 threads split the samples (carrier wipe-off + the three code look-ups in f64 with the reference's own
+// sequential, the channels are independent.  k_track: one thread-block cluster (1-8 CTAs) per channel walks its periods in
+// order; inside a period the cluster's threads split the samples (carrier wipe-off + the three code look-ups in f64 with the reference's own
 // expressions, never contracted into FMAs, so the chip indices are the reference's), a fixed-order tree reduces the six
 // correlator sums, thread 0 runs the loop update exactly as :219-313 and publishes the state for the next period.
 // Only the summation order differs from the reference (pairwise instead of sequential): states agree to ~1e-12.
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -17,6 +18,8 @@
 #include <vector>
 
 #include "track.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace r4wb {
 
@@ -62,10 +65,17 @@ __global__ void __launch_bounds__(kTrackThreads) k_track(TrackChan* __restrict__
                                                           uint64_t code_stride, r4wb_track_state* __restrict__ out, uint32_t n_channels,
                                                           int8_t* __restrict__ nav_out, uint32_t nav_cap, uint32_t* __restrict__ nav_n)
 {
+    // A channel is one thread-block CLUSTER (1, 2, 4 or 8 CTAs, chosen by the host from the bank size): the CTAs split the
+    // period's samples, leave their six partial sums in their own shared memory, and after one cluster barrier every CTA
+    // reads all partials through distributed shared memory in rank order and runs the (identical) loop update itself, so
+    // nothing has to be broadcast back.  The partial slots are double-buffered: one cluster barrier per period.
+    cg::cluster_group cluster = cg::this_cluster();
+    const uint32_t cs = cluster.num_blocks(), rank = cluster.block_rank();
     extern __shared__ int8_t s_code[];
     __shared__ double s_red[kTrackThreads / 32][6];
+    __shared__ double s_part[2][6];
     __shared__ TrackChan s_c;
-    const uint32_t ch = blockIdx.x, tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const uint32_t ch = blockIdx.x / cs, tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     if (tid == 0) s_c = chans[ch];
     __syncthreads();
     const uint32_t code_length = s_c.code_length;
@@ -80,14 +90,14 @@ __global__ void __launch_bounds__(kTrackThreads) k_track(TrackChan* __restrict__
         const double cf = s_c.carrier_freq, cph = s_c.carrier_phase, cp = s_c.code_phase, half = s_c.el_spacing / 2.0;
         double ei = 0.0, eq = 0.0, pi = 0.0, pq = 0.0, li = 0.0, lq = 0.0;
         const SampleT* xp = x + p * n_per_period;
-        for (uint64_t i = tid; i < n_per_period; i += kTrackThreads) {           // :186-217
+        for (uint64_t i = (uint64_t)rank * kTrackThreads + tid; i < n_per_period; i += (uint64_t)kTrackThreads * cs) {   // :186-217
             const double t = (double)i / fs;
             const double arg = __dmul_rn(__dmul_rn(-2.0, 3.14159265358979323846), __dadd_rn(__dmul_rn(cf, t), cph));
-            double sn, cs;
-            sincos(arg, &sn, &cs);
+            double sn, cs_;
+            sincos(arg, &sn, &cs_);
             const double re = (double)xp[i].x, im = (double)xp[i].y;
-            const double sre = __dadd_rn(__dmul_rn(re, cs), -__dmul_rn(im, sn));
-            const double sim = __dadd_rn(__dmul_rn(re, sn), __dmul_rn(im, cs));
+            const double sre = __dadd_rn(__dmul_rn(re, cs_), -__dmul_rn(im, sn));
+            const double sim = __dadd_rn(__dmul_rn(re, sn), __dmul_rn(im, cs_));
             const double chip = __dadd_rn(cp, (double)i / spc);
             const double ec = (double)s_code[as_index(rem_euclid_d(__dadd_rn(chip, -half), cl), code_length)];
             const double pc = (double)s_code[as_index(rem_euclid_d(chip, cl), code_length)];
@@ -103,13 +113,25 @@ __global__ void __launch_bounds__(kTrackThreads) k_track(TrackChan* __restrict__
             if (lane == 0) s_red[warp][j] = v[j];
         }
         __syncthreads();
+        if (cs > 1) {
+            if (tid < 6) {
+                double a = 0.0;
+                for (int w = 0; w < kTrackThreads / 32; ++w) a += s_red[w][tid];
+                s_part[p & 1][tid] = a;
+            }
+            cluster.sync();                           // every CTA's partial sums of this period are in place
+        }
         if (tid == 0) {
             TrackChan& c = s_c;
-            double s[6];
-            for (int j = 0; j < 6; ++j) {
-                double a = 0.0;
-                for (int w = 0; w < kTrackThreads / 32; ++w) a += s_red[w][j];
-                s[j] = a;
+            double s[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+            if (cs > 1) {
+                for (uint32_t r = 0; r < cs; ++r) {   // rank order: the same totals in every CTA
+                    const double* part = cluster.map_shared_rank(&s_part[p & 1][0], r);
+                    for (int j = 0; j < 6; ++j) s[j] += part[j];
+                }
+            } else {
+                for (int j = 0; j < 6; ++j)
+                    for (int w = 0; w < kTrackThreads / 32; ++w) s[j] += s_red[w][j];
             }
             c.p_i = s[2]; c.p_q = s[3];
             const double early_power = sqrt(__dadd_rn(__dmul_rn(s[0], s[0]), __dmul_rn(s[1], s[1])));
@@ -150,7 +172,7 @@ __global__ void __launch_bounds__(kTrackThreads) k_track(TrackChan* __restrict__
             if (c.prev_sign != 0 && sign != c.prev_sign && !c.bit_sync && c.ms_count > 20ull) c.bit_sync = 1u;
             c.prev_sign = sign;
             if (c.nav_bit_count >= 20u) {
-                if (nav_count < nav_cap) nav_out[(size_t)ch * nav_cap + nav_count] = c.nav_acc >= 0.0 ? 1 : -1;
+                if (rank == 0 && nav_count < nav_cap) nav_out[(size_t)ch * nav_cap + nav_count] = c.nav_acc >= 0.0 ? 1 : -1;
                 ++nav_count;
                 c.nav_acc = 0.0;
                 c.nav_bit_count = 0u;
@@ -162,11 +184,12 @@ __global__ void __launch_bounds__(kTrackThreads) k_track(TrackChan* __restrict__
             o.prompt_i = c.p_i; o.prompt_q = c.p_q; o.cn0_dbhz = cn0; o.ms_count = c.ms_count;
             o.prn = (uint8_t)c.prn; o.carrier_lock = (uint8_t)c.carrier_lock; o.code_lock = (uint8_t)c.code_lock; o.bit_sync = (uint8_t)c.bit_sync;
             o.pad[0] = o.pad[1] = o.pad[2] = o.pad[3] = 0;
-            out[p * n_channels + ch] = o;
+            if (rank == 0) out[p * n_channels + ch] = o;
         }
         __syncthreads();
     }
-    if (tid == 0) {
+    if (cs > 1) cluster.sync();                       // no CTA leaves while another may still read its partial sums
+    if (tid == 0 && rank == 0) {
         chans[ch] = s_c;
         nav_n[ch] = nav_count;
     }
@@ -239,12 +262,34 @@ void TrackerBank::process(const void* samples, r4wb_fmt fmt, r4wb_mem where, uin
     d_nav_.reserve((size_t)n * nav_cap);
     d_nav_n_.reserve(n);
     const size_t smem = (max_cl + 15u) & ~15u;
-    if (fmt == R4WB_FMT_CF32)
-        k_track<float2><<<n, kTrackThreads, smem, st>>>(d_chan_.p, (const float2*)d_x, n_per_period, n_periods, channel_stride, d_codes_.p, code_stride,
-                                                        d_out_.p, n, d_nav_.p, nav_cap, d_nav_n_.p);
+    // cluster size: as many CTAs per channel as keep the whole bank resident (148 SMs), up to the portable maximum of 8
+    static int sm_count = 0;
+    if (!sm_count) {
+        int dev = 0;
+        R4WB_CUDA(cudaGetDevice(&dev));
+        R4WB_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+    }
+    unsigned cs = 1;
+    while (cs < 8 && (uint64_t)n * cs * 2 <= (uint64_t)sm_count && (uint64_t)kTrackThreads * cs * 2 <= n_per_period) cs *= 2;
+    cudaLaunchConfig_t lc{};
+    lc.gridDim = dim3(n * cs); lc.blockDim = dim3(kTrackThreads); lc.dynamicSmemBytes = smem; lc.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    lc.attrs = attr; lc.numAttrs = 1;
+    const uint32_t nch = n;
+    if (cs == 1 && fmt == R4WB_FMT_CF32)             // plain launch: a cluster attribute of 1 costs occupancy on a full bank
+        k_track<float2><<<n, kTrackThreads, smem, st>>>(d_chan_.p, (const float2*)d_x, n_per_period, n_periods, channel_stride, d_codes_.p,
+                                                        code_stride, d_out_.p, nch, d_nav_.p, nav_cap, d_nav_n_.p);
+    else if (cs == 1)
+        k_track<double2><<<n, kTrackThreads, smem, st>>>(d_chan_.p, (const double2*)d_x, n_per_period, n_periods, channel_stride, d_codes_.p,
+                                                         code_stride, d_out_.p, nch, d_nav_.p, nav_cap, d_nav_n_.p);
+    else if (fmt == R4WB_FMT_CF32)
+        R4WB_CUDA(cudaLaunchKernelEx(&lc, k_track<float2>, d_chan_.p, (const float2*)d_x, n_per_period, n_periods, channel_stride,
+                                     (const int8_t*)d_codes_.p, code_stride, d_out_.p, nch, d_nav_.p, nav_cap, d_nav_n_.p));
     else
-        k_track<double2><<<n, kTrackThreads, smem, st>>>(d_chan_.p, (const double2*)d_x, n_per_period, n_periods, channel_stride, d_codes_.p, code_stride,
-                                                         d_out_.p, n, d_nav_.p, nav_cap, d_nav_n_.p);
+        R4WB_CUDA(cudaLaunchKernelEx(&lc, k_track<double2>, d_chan_.p, (const double2*)d_x, n_per_period, n_periods, channel_stride,
+                                     (const int8_t*)d_codes_.p, code_stride, d_out_.p, nch, d_nav_.p, nav_cap, d_nav_n_.p));
     R4WB_LAUNCH_CHECK();
     std::vector<int8_t> nav((size_t)n * nav_cap);
     std::vector<uint32_t> nav_n(n);
