@@ -273,7 +273,8 @@ def run_b200(args):
     e2e_steps = max(1, min(args.steps, 3))
     _lib.set_stream(torch.cuda.current_stream().cuda_stream)
     scen.generate_range_into(first, n, host.value)              # warm-up (staging buffers, page faults)
-    acq.acquire_batch_raw(host_np, min(n_snap, 64), CODE_LENGTH, CODE_LENGTH, codes, prns)
+    acq.acquire_batch_raw(host_np, n_snap, CODE_LENGTH, CODE_LENGTH, codes, prns)      # warm-up at full size: the library's device input
+    #                                                                                   buffer (0.8 GB) and event pool are allocated here
     barrier()
     ts = time.perf_counter()
     for _ in range(e2e_steps):
