@@ -196,7 +196,7 @@ def run_b200(args):
     import torch.distributed as dist
     import r4w_b200 as R
     from r4w_b200 import _lib
-    from r4w_b200.dist import all_gather_table, results_to_table, segment_for_rank
+    from r4w_b200.dist import all_gather_table, all_reduce_power, results_to_table, segment_for_rank
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -264,6 +264,21 @@ def run_b200(args):
     prof = rec[-1][3]
     sprof = {k: (float(np.mean([r[5][k][0] for r in rec])), rec[-1][5][k][1]) for k in rec[-1][5]}
     guards = int(np.sum([r[4] for r in rec]))
+
+    # the CLI's average-power line (main.rs:4494-4509) over all ranks' segments: one all-reduce of {sum |s|^2, count}
+    scen.generate_device(first, n, iq)
+    torch.cuda.synchronize()
+    pw_sum, pw_cnt = all_reduce_power(scen.last_power_sum(), n)
+    # the reference's default Doppler grid (+-5 kHz / 500 Hz = 21 bins, acquisition.rs:63-74) on a 296-snapshot sample
+    acq21 = R.PcpsAcquisition(CODE_LENGTH, 5e6)
+    ns21 = min(n_snap, 296)
+    acq21.acquire_batch_raw(iq, ns21, CODE_LENGTH, CODE_LENGTH, codes, prns)
+    torch.cuda.synchronize()
+    ts = time.perf_counter()
+    acq21.acquire_batch_raw(iq, ns21, CODE_LENGTH, CODE_LENGTH, codes, prns)
+    torch.cuda.synchronize()
+    ms_acq21 = (time.perf_counter() - ts) * 1e3
+    cells21 = ns21 * len(prns) * acq21.num_doppler_bins() * CODE_LENGTH
 
     # ---- e2e: the same step through the C-ABI with HOST buffers (pinned), copies inside the timed region
     import ctypes as C
@@ -364,10 +379,13 @@ def run_b200(args):
         cores = os.cpu_count() or 1
         th_s = max(1, min(len(prns), cores))
         v_s, n_s, dt_s = cpu_synth(cfg, 3.0, th_s)                    # 3 s of the scenario: ~10-15 s of host work
+        v_1, n_1, dt_1 = cpu_synth(cfg, 0.3, 1)                       # the reference's default build is single-threaded
         ns_c = max(1, min(n_snap, 8 * cores))                         # ~10 s of host work on all cores
         v_a, c_a, dt_a = cpu_acq(host_np, codes, prns, ns_c, cores)
         cpu = ({"value": v_s, "unit": "Msamples/s", "cores": th_s, "kind": "port",
-                "sample": f"3 s of {WORKLOAD} ({n_s} samples, {dt_s:.1f} s wall), oracle port, one thread per satellite"},
+                "sample": f"3 s of {WORKLOAD} ({n_s} samples, {dt_s:.1f} s wall), oracle port, one thread per satellite",
+                "single_thread": {"value": v_1, "unit": "Msamples/s", "cores": 1,
+                                  "sample": f"0.3 s of {WORKLOAD} ({n_1} samples, {dt_1:.1f} s wall), oracle port, 1 thread"}},
                {"value": v_a, "unit": "cells/s", "cores": cores, "kind": "port",
                 "sample": f"{ns_c} snapshot(s) x {len(prns)} PRNs x {bins} bins ({c_a} cells, {dt_a:.1f} s wall), oracle port, {cores} threads"})
     _lib.check(_lib.lib().r4wb_host_free(host))
@@ -404,7 +422,10 @@ def run_b200(args):
                     "e2e": {"value": cells / (ms_acq_e2e * 1e-3), "unit": "cells/s", "h2d_bytes_per_step": n_snap * CODE_LENGTH * 8,
                             "d2h_bytes_per_step": n_snap * len(prns) * 32,
                             "api": "r4wb_pcps_acquire_batch(..., R4WB_MEM_HOST) from pinned host memory"},
-                    "first_snapshot": [[int(table[0, c, 2]), float(table[0, c, 3])] for c in range(len(prns))]},
+                    "first_snapshot": [[int(table[0, c, 2]), float(table[0, c, 3])] for c in range(len(prns))],
+                    "default_grid_rank0": {"bins": acq21.num_doppler_bins(), "snapshots": ns21, "cells_per_s": cells21 / (ms_acq21 * 1e-3),
+                                           "note": "reference default +-5 kHz / 500 Hz, device-resident input, wall clock of one call"}},
+            "avg_power": {"value": pw_sum / max(pw_cnt, 1), "samples": pw_cnt, "note": "sum |s|^2 / count all-reduced over the ranks (the CLI's avg-power line)"},
             "gpu_launches": int(launches),
             "clocks": clk,
         }

@@ -59,6 +59,19 @@ def all_gather_table(local: np.ndarray, counts: List[int] = None) -> np.ndarray:
     return out.cpu().numpy()
 
 
+def all_reduce_power(power_sum: float, n_samples: int) -> Tuple[float, int]:
+    """The CLI's average-power line over a time-sharded render (crates/r4w-cli/src/main.rs:4494-4509: sum |s|^2 / count):
+    one all-reduce of {sum |s|^2, count} over the ranks.  Returns (total sum, total count)."""
+    import torch
+    import torch.distributed as dist
+    if not dist.is_available() or not dist.is_initialized() or dist.get_world_size() == 1:
+        return float(power_sum), int(n_samples)
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+    t = torch.tensor([float(power_sum), float(n_samples)], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t[0].item()), int(round(float(t[1].item())))
+
+
 ACQ_DTYPE = np.dtype([("prn", "u1"), ("detected", "u1"), ("has_cn0", "u1"), ("_pad", "u1", (5,)), ("code_phase", "f8"),
                       ("doppler_hz", "f8"), ("peak_metric", "f8"), ("threshold", "f8"), ("cn0_estimate", "f8")])
 

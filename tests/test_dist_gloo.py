@@ -16,7 +16,7 @@ def _free_port():
 
 def _worker(rank, world, port, q):
     import torch.distributed as dist
-    from r4w_b200.dist import all_gather_table, segment_for_rank
+    from r4w_b200.dist import all_gather_table, all_reduce_power, segment_for_rank
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -30,7 +30,8 @@ def _worker(rank, world, port, q):
             local[s, :, 0] = [3, 25, 8]
             local[s, :, 2] = (s0 + s) * 100 + np.arange(3)
         full = all_gather_table(local)
-        q.put((rank, first, n, full))
+        psum, cnt = all_reduce_power(1000.0 * (rank + 1), n)          # avg-power line of a time-sharded render
+        q.put((rank, first, n, full, psum, cnt))
     finally:
         dist.destroy_process_group()
 
@@ -46,7 +47,8 @@ def test_all_gather_peak_table_world2():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    (r0, f0, n0, t0), (r1, f1, n1, t1) = out
+    (r0, f0, n0, t0, p0, c0), (r1, f1, n1, t1, p1, c1) = out
+    assert p0 == p1 == 3000.0 and c0 == c1 == 7 * 20000 + 123
     assert f0 == 0 and f0 + n0 == f1 and f1 + n1 == 7 * 20000 + 123
     assert n0 == 4 * 20000 and n1 == 3 * 20000 + 123
     assert t0.shape == (7, 3, 6) and np.array_equal(t0, t1)
@@ -57,3 +59,5 @@ def test_all_gather_single_process_is_identity():
     from r4w_b200.dist import all_gather_table
     a = np.arange(24, dtype=np.float64).reshape(2, 2, 6)
     assert np.array_equal(all_gather_table(a), a)
+    from r4w_b200.dist import all_reduce_power
+    assert all_reduce_power(12.5, 100) == (12.5, 100)
