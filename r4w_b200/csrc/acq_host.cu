@@ -199,6 +199,24 @@ void Pcps::run(AcqWork<T>& w, const void* d_input, r4wb_fmt fmt, uint64_t s0, ui
     uint64_t chunk = std::max<uint64_t>(1, chunk_bytes / (row_bytes * std::max(1u, g.D)));
     chunk = std::min<uint64_t>(chunk, std::max<uint64_t>(1, 0x3fffffffull / ((uint64_t)std::max(1u, g.D) * nc * F)));
     chunk = std::min(chunk, ns);
+    if (fast && rf_use_tmem() && chunk < ns && chunk > 8) {
+        // one CTA per (snapshot, Doppler) row and one resident CTA per SM: pick the chunk (within 25 % of the byte budget)
+        // whose row count fills whole waves of the SMs best (195 snapshots x 41 rows = 54.02 waves of 148 -> 148 x 41 = 41.00)
+        static int sm_count = 0;
+        if (!sm_count) {
+            int dev = 0;
+            R4WB_CUDA(cudaGetDevice(&dev));
+            R4WB_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+        }
+        uint64_t best = chunk;
+        double best_eff = 0.0;
+        for (uint64_t c = chunk; c >= chunk - chunk / 4 && c >= 1; --c) {
+            const uint64_t rows = c * g.D, waves = (rows + sm_count - 1) / sm_count;
+            const double eff = (double)rows / (double)(waves * sm_count);
+            if (eff > best_eff + 1e-9) { best_eff = eff; best = c; }
+        }
+        chunk = best;
+    }
     w.x.reserve((size_t)chunk * g.D * g.N);
     d_rowpeaks_.reserve((size_t)chunk * g.D * nc * Fr);
     const size_t bps = fmt == R4WB_FMT_CF64 ? 16 : 8;
