@@ -1,7 +1,7 @@
 """First-contact GPU check: synthesis and acquisition against the oracle + quick timings.  Diagnostic, not a test."""
 import os, sys, time
 import numpy as np
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import torch
 import r4w_b200 as R
