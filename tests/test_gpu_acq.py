@@ -61,7 +61,9 @@ def test_scenario_kat_gps_2046(gpu, oracle):
     assert int(r.code_phase) == 321 and r.doppler_hz == 1500.0      # corr[k] = sum x[n+k] c[n] peaks at the roll amount
 
 
-@pytest.mark.parametrize("name", ["e1c_8prn_20s_clean", "e1c_prn3_20s_withdoppler", "e1c_60s_all_prns", "e1c_8prn_60s_cn34_orbital"])
+@pytest.mark.parametrize("name", ["e1c_8prn_20s_clean", "e1c_prn3_20s_withdoppler", "e1c_60s_all_prns", "e1c_8prn_60s_cn34_orbital",
+                                  "e1c_8prn_600s_cn34_orbital", "e1c_60s_clean", "e1c_60s_cn34", "e1c_60s_cn34_effects",
+                                  "e1c_8prn_20s_cn34_orbital", "e1c_8prn_60s_mach3_ftwayne_berne", "e1c_prn3_20s_30ms_delay"])
 def test_e1c_indices_match_oracle_all_prns(gpu, oracle, name):
     """every PRN 1-50 (present, absent, and the wrap-around-lag cases) on oracle-generated noisy input: (lag, bin) identical"""
     cfg = _cfg(name)
