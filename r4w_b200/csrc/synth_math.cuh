@@ -496,22 +496,54 @@ R4WB_HD uint32_t direct_sign(const BlockSat& bs, long long q, const uint32_t* __
     return ((code[c >> 5] >> (c & 31u)) ^ (uint32_t)(d.epoch_bits >> (uint32_t)(ep % d.epoch_period))) & 1u;
 }
 
-// the reference's 63-tap loop (fir.rs:392-409) for output sample i of block entry `cur`, FIR history from its predecessor
+// the reference's 63-tap loop (fir.rs:392-409) for output sample i of block entry `cur`, FIR history from its predecessor.
+// The chip index and the primary-code epoch are carried from tap to tap (consecutive taps are 1 / spc < 1 chips apart, so
+// the chip index steps down by 0 or 1); one 64-bit division per block entry touched.  The fast position phase0 + (G + q) *
+// (1 / spc) is within ~5e-8 chips of the reference's f64 value (cf < 2^28 chips): when its fraction keeps 1e-6 clear of a
+// chip boundary its floor IS the reference's floor; an oversample closer than that takes direct_sign (the literal
+// expression, also for the epoch), so the result is the reference's for every tap.
 R4WB_HD float direct_fir(const BlockSat& cur, const BlockSat* __restrict__ tab, const uint32_t* __restrict__ code,
                          const float* __restrict__ taps, int i, const DirectSat& d)
 {
     double acc = 0.0;
     const long long g = (long long)kOversample * i;
+    const double inv_spc = 1.0 / d.spc;
+    const BlockSat* bs = &cur;
+    long long shift = 0;                 // q (relative to bs) = g - k + shift
+    bool primed = false;
+    double c_prev = 0.0;
+    uint32_t chip = 0, ep = 0;
     for (int k = 0; k < kTaps; ++k) {
-        long long q = g - k;
-        const BlockSat* bs = &cur;
+        long long q = g - k + shift;
         if (q < 0) {
-            if (cur.prev < 0) continue;                      // zero-initialised delay line
+            if (bs != &cur || cur.prev < 0) break;           // zero-initialised delay line / history older than one block: not modelled
             bs = &tab[cur.prev];
-            q += (long long)kOversample * bs->n;
-            if (q < 0) continue;                             // history older than one block: not modelled
+            shift = (long long)kOversample * bs->n;
+            q += shift;
+            if (q < 0) break;
+            primed = false;
         }
-        acc += direct_sign(*bs, q, code, d) ? -(double)taps[k] : (double)taps[k];
+        const double gq = (double)(bs->G + (uint64_t)q);
+        const double cf = fma(gq, inv_spc, bs->phase0);
+        const double fl = floor(cf), fr = cf - fl;
+        uint32_t sgn;
+        if (!(fr > 1e-6 && fr < 1.0 - 1e-6)) {               // too close to a chip boundary for the fast form: literal expression
+            sgn = direct_sign(*bs, q, code, d);
+            primed = false;
+        } else {
+            if (!primed) {
+                const uint64_t c = (uint64_t)fl;
+                chip = (uint32_t)(c % d.code_len);
+                ep = (uint32_t)(((uint64_t)bs->e0 + c / d.code_len) % d.epoch_period);
+                primed = true;
+            } else if (fl != c_prev) {                        // one chip back
+                if (chip == 0u) { chip = d.code_len - 1u; ep = ep == 0u ? d.epoch_period - 1u : ep - 1u; }
+                else --chip;
+            }
+            c_prev = fl;
+            sgn = ((code[chip >> 5] >> (chip & 31u)) ^ (uint32_t)(d.epoch_bits >> ep)) & 1u;
+        }
+        acc += sgn ? -(double)taps[k] : (double)taps[k];
     }
     return (float)acc;
 }
