@@ -193,8 +193,8 @@ void Scenario::launch_synth(const BlockSat* tab, const BlockHdr* hdr, const Tile
     }
     const int tile_k = md_.tile_k;
     const size_t smem = synth_smem_bytes(a.n_sats, a.nw64, a.lut_den, a.ystride);
-    static int per_sm_cache[2][5] = {};                      // [tile_k == 5][fmt], for the smem size of the first query
-    static size_t per_sm_smem[2][5] = {};
+    thread_local int per_sm_cache[2][5] = {};                    // [tile_k == 5][fmt], for the smem size of the first query
+    thread_local size_t per_sm_smem[2][5] = {};
     int& cached = per_sm_cache[tile_k == 5][(int)fmt];
     if (!cached || per_sm_smem[tile_k == 5][(int)fmt] != smem) {
         cached = std::max(1, synth_max_blocks_per_sm(tile_k, fmt, smem));
