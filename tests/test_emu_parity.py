@@ -257,3 +257,16 @@ def test_presets_replay_matches_oracle(oracle, emu, name):
     got = emu.EmuScenario(longer, noise=False).generate_range(2_400_000, 7000)
     want = oracle.OracleScenario(longer, noise=False).generate_range(2_400_000, 7000)
     assert _relrms(got, want) <= TOL
+
+
+@pytest.mark.parametrize("rate", [0.3, 40.0, 5000.0, -20000.0])
+def test_doppler_rate_replay_matches_oracle(oracle, emu, rate):
+    """`doppler_rate_hz_per_s` (scenario.rs:416-421): Doppler ramps linearly inside and across blocks; small rates take the
+    linearised phasor recurrence, large ones the per-sample sincos path"""
+    cfg = _cfg("e1c_8prn_20s_clean").copy()
+    for k, s in enumerate(cfg.satellites):
+        s.doppler_rate_hz_per_s = rate * (1 + 0.1 * k) * (1 if k % 2 == 0 else -1)
+    for first, n in ((0, 11000), (49_995_000, 12000)):
+        got = emu.EmuScenario(cfg, noise=False).generate_range(first, n)
+        want = oracle.OracleScenario(cfg, noise=False).generate_range(first, n)
+        assert _relrms(got, want) <= TOL

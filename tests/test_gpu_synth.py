@@ -348,3 +348,19 @@ def test_600s_config_end_of_file_and_shards(gpu, oracle):
         left = gpu.GnssScenario(cfg, noise=True).generate_range(edge - 6000, 6000)       # tail of shard r-1 (fresh handle: own table)
         right = gpu.GnssScenario(cfg, noise=True).generate_range(edge, 6000)             # head of shard r
         assert np.array_equal(across[:6000], left) and np.array_equal(across[6000:], right)
+
+
+@pytest.mark.parametrize("rate", [0.3, 40.0, 5000.0, -20000.0])
+def test_doppler_rate_matches_oracle(gpu, oracle, rate):
+    """`doppler_rate_hz_per_s` (scenario.rs:416-421) on the GPU: linearised phasor recurrence for small rates,
+    per-sample sincos for large ones; a long range so the phase scan over blocks is exercised"""
+    cfg = _cfg("e1c_8prn_20s_clean").copy()
+    for k, s in enumerate(cfg.satellites):
+        s.doppler_rate_hz_per_s = rate * (1 + 0.1 * k) * (1 if k % 2 == 0 else -1)
+    sc = gpu.GnssScenario(cfg, noise=False)
+    x = sc.generate_range(49_000_000, 1_000_000)
+    assert sc.last_path() == 0                         # Doppler is not constant: general kernel
+    want = oracle.OracleScenario(cfg, noise=False, threads=8).generate_range(49_990_000, 10_000)
+    assert _relrms(x[990_000:], want) <= TOL
+    want = oracle.OracleScenario(cfg, noise=False, threads=8).generate_range(0, 10_000)
+    assert _relrms(gpu.GnssScenario(cfg, noise=False).generate_range(0, 10_000), want) <= TOL
