@@ -270,3 +270,15 @@ def test_doppler_rate_replay_matches_oracle(oracle, emu, rate):
         got = emu.EmuScenario(cfg, noise=False).generate_range(first, n)
         want = oracle.OracleScenario(cfg, noise=False).generate_range(first, n)
         assert _relrms(got, want) <= TOL
+
+
+@pytest.mark.parametrize("kind", ["Isotropic", "Hemispherical", "Patch", "ChokeRing"])
+def test_antenna_patterns_replay_matches_oracle(oracle, emu, kind):
+    """AntennaPattern::gain_dbi (gnss/environment/antenna.rs:35-62) inside the link budget of satellites without a cn0 override"""
+    from r4w_b200.config import preset_config, AntennaPattern
+    cfg = preset_config("MultiConstellation")
+    cfg.receiver.antenna = AntennaPattern(kind, 4.0, 120.0)
+    cfg.output.duration_s = 0.004
+    got = emu.EmuScenario(cfg, noise=False).generate_range(0, 20000)
+    want = oracle.OracleScenario(cfg, noise=False).generate_range(0, 20000)
+    assert _relrms(got, want) <= TOL

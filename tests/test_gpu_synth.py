@@ -364,3 +364,17 @@ def test_doppler_rate_matches_oracle(gpu, oracle, rate):
     assert _relrms(x[990_000:], want) <= TOL
     want = oracle.OracleScenario(cfg, noise=False, threads=8).generate_range(0, 10_000)
     assert _relrms(gpu.GnssScenario(cfg, noise=False).generate_range(0, 10_000), want) <= TOL
+
+
+@pytest.mark.parametrize("kind", ["Isotropic", "Hemispherical", "Patch", "ChokeRing"])
+def test_antenna_patterns_match_oracle(gpu, oracle, kind):
+    """AntennaPattern::gain_dbi (gnss/environment/antenna.rs:35-62) in the device-side link budget: IQ and reported C/N0"""
+    from r4w_b200.config import AntennaPattern
+    cfg = gpu.preset_config("MultiConstellation")
+    cfg.receiver.antenna = AntennaPattern(kind, 4.0, 120.0)
+    cfg.output.duration_s = 0.02
+    sc = gpu.GnssScenario(cfg, noise=False)
+    want = oracle.OracleScenario(cfg, noise=False).generate_range(0, 100_000)
+    assert _relrms(sc.generate(), want) <= TOL
+    for a, b in zip(sc.satellite_status(), oracle.OracleScenario(cfg).status()):
+        assert a.antenna_gain_dbi == pytest.approx(b.antenna_gain_dbi, abs=1e-9) and a.cn0_dbhz == pytest.approx(b.cn0_dbhz, abs=1e-6)
