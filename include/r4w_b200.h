@@ -197,6 +197,14 @@ r4wb_error r4wb_scenario_generate_block(r4wb_scenario* h, uint64_t n, void* dst,
  * throughput entry point (time-sharding across GPUs = disjoint [first, first+n) ranges). */
 r4wb_error r4wb_scenario_generate(r4wb_scenario* h, uint64_t first, uint64_t n, void* dst,
                                   r4wb_mem where, r4wb_fmt fmt);
+/* The CLI's file sink (`r4w gnss scenario --output`, crates/r4w-cli/src/main.rs:4483-4509: BufWriter + IqFormat::
+ * write_samples per block, core/io/format.rs:191-227): renders the whole scenario [0, total_samples) in `fmt` and streams
+ * it into `path` (created/truncated) — device staging -> pinned host buffers -> a writer thread, all three overlapped.
+ * *samples / *bytes = what was written, *power_sum = sum |s|^2 of the pre-conversion samples (the avg-power line);
+ * any of the three may be NULL.  Leaves the handle done (is_done() = 1) as the CLI loop does.  InvalidParameter when the
+ * file cannot be created, BufferFull on a short write. */
+r4wb_error r4wb_scenario_write_file(r4wb_scenario* h, const char* path, r4wb_fmt fmt, uint64_t* samples, uint64_t* bytes,
+                                    double* power_sum);
 /* Sum of |s|^2 over the last generate / generate_block call (the CLI's avg-power line, main.rs:4494-4509) */
 r4wb_error r4wb_scenario_last_power_sum(const r4wb_scenario* h, double* power_sum);
 /* Which synthesis kernels rendered the bulk of the last generate call: 0 = k_synth (general), 1 = the period-resident

@@ -57,6 +57,7 @@ SYMBOLS = {
     "r4wb_scenario_current_sample": (_u64, [_vp]),
     "r4wb_scenario_generate_block": (_int, [_vp, _u64, _vp, _int, _int, C.POINTER(_u64)]),
     "r4wb_scenario_generate": (_int, [_vp, _u64, _u64, _vp, _int, _int]),
+    "r4wb_scenario_write_file": (_int, [_vp, C.c_char_p, _int, C.POINTER(_u64), C.POINTER(_u64), C.POINTER(_dbl)]),
     "r4wb_scenario_last_power_sum": (_int, [_vp, C.POINTER(_dbl)]),
     "r4wb_scenario_last_path": (C.c_uint32, [_vp]),
     "r4wb_scenario_set_profiling": (_int, [_vp, _int]),

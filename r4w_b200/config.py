@@ -457,3 +457,129 @@ def preset_config(name: str) -> GnssScenarioConfig:
         gal = [galileo_e1(p, s) for p, s in ((0, 7), (1, 5), (0, 0), (1, 6), (1, 4), (0, 6))]
         return GnssScenarioConfig(gps(5) + gal)
     raise ValueError(f"unknown preset {name!r}; one of {PRESETS}")
+
+
+# ---- serde_yaml-shaped export (the CLI's companion `<output>.yaml`, crates/r4w-cli/src/main.rs:4511-4531, and --export-preset) ----
+def _ryu(x: float) -> str:
+    """f64 the way serde_yaml 0.9 prints it (ryu shortest round-trip; `.inf`/`.nan` spellings)"""
+    x = float(x)
+    if x != x:
+        return ".nan"
+    if x in (float("inf"), float("-inf")):
+        return ".inf" if x > 0 else "-.inf"
+    r = repr(x)
+    if "e" in r:
+        mant, exp = r.split("e")
+        e = int(exp)
+        if e == -5:                                       # ryu stays positional down to 1e-5; Python switches at 1e-5
+            return f"{x:.{len(mant.replace('.', '').replace('-', '')) + 4}f}".rstrip("0")
+        return f"{mant}e{e}"
+    return r
+
+
+def _yaml_str(s: str) -> str:
+    plain = bool(s) and s[0] not in "{}[]&*!|>'\"%@`#,?:- " and ": " not in s and " #" not in s and not s.endswith((" ", ":")) \
+        and s.lower() not in ("null", "true", "false", "~", "yes", "no", "on", "off")
+    if plain:
+        try:
+            float(s)
+            plain = False
+        except ValueError:
+            pass
+    return s if plain else "'" + s.replace("'", "''") + "'"
+
+
+def _scalar(v) -> str:
+    if v is None:
+        return "null"
+    if isinstance(v, bool):
+        return "true" if v else "false"
+    if isinstance(v, int):
+        return str(v)
+    if isinstance(v, float):
+        return _ryu(v)
+    return _yaml_str(str(v))
+
+
+class _Tagged:
+    """externally tagged enum with a struct body: `key: !Variant` + the body's fields one level in"""
+    def __init__(self, tag, body):
+        self.tag, self.body = tag, body
+
+
+def _emit(node, ind: int, out: list):
+    pad = "  " * ind
+    if isinstance(node, dict):
+        for k, v in node.items():
+            if isinstance(v, _Tagged):
+                out.append(f"{pad}{k}: !{v.tag}")
+                _emit(v.body, ind + 1, out)
+            elif isinstance(v, dict) and v:
+                out.append(f"{pad}{k}:")
+                _emit(v, ind + 1, out)
+            elif isinstance(v, (list, tuple)) and len(v):
+                out.append(f"{pad}{k}:")
+                _emit(list(v), ind, out)                  # libyaml: a sequence sits at its key's own indent
+            elif isinstance(v, (dict, list, tuple)):
+                out.append(f"{pad}{k}: " + ("{}" if isinstance(v, dict) else "[]"))
+            else:
+                out.append(f"{pad}{k}: {_scalar(v)}")
+    elif isinstance(node, list):
+        for item in node:
+            if isinstance(item, dict) and item:
+                sub: list = []
+                _emit(item, ind + 1, sub)
+                out.append(f"{pad}- {sub[0][2 * (ind + 1):]}")
+                out.extend(sub[1:])
+            else:
+                out.append(f"{pad}- {_scalar(item)}")
+
+
+def config_to_dict(cfg: GnssScenarioConfig) -> dict:
+    """Field order and `skip_serializing_if = Option::is_none` as the reference's derive(Serialize) (scenario_config.rs:137-191,
+    304-315, 383-401, 417-437, 455-487)"""
+    lla = lambda p: {"lat_deg": float(p.lat_deg), "lon_deg": float(p.lon_deg), "alt_m": float(p.alt_m)}       # noqa: E731
+    sats = []
+    for s in cfg.satellites:
+        d = {"signal": s.signal, "prn": int(s.prn), "plane": int(s.plane), "slot": int(s.slot),
+             "tx_power_dbw": float(s.tx_power_dbw), "nav_data": bool(s.nav_data)}
+        for key in ("elevation_deg", "azimuth_deg", "range_m", "range_rate_mps", "doppler_hz", "doppler_rate_hz_per_s"):
+            if getattr(s, key) is not None:
+                d[key] = float(getattr(s, key))
+        d["orbital_dynamics"] = bool(s.orbital_dynamics)
+        for key in ("cn0_dbhz", "iono_delay_m", "tropo_delay_m"):
+            if getattr(s, key) is not None:
+                d[key] = float(getattr(s, key))
+        sats.append(d)
+    r, a = cfg.receiver, cfg.receiver.antenna
+    if a.kind == "Isotropic":
+        antenna = "Isotropic"
+    elif a.kind == "Patch":
+        antenna = _Tagged("Patch", {"peak_gain_dbi": float(a.peak_gain_dbi), "beamwidth_deg": float(a.beamwidth_deg)})
+    else:
+        antenna = _Tagged(a.kind, {"peak_gain_dbi": float(a.peak_gain_dbi)})
+    recv = {"position": lla(r.position), "antenna": antenna, "elevation_mask_deg": float(r.elevation_mask_deg),
+            "noise_figure_db": float(r.noise_figure_db), "bandwidth_hz": float(r.bandwidth_hz)}
+    if r.trajectory is not None:
+        t = r.trajectory
+        recv["trajectory"] = {"start": lla(t.start), "end": lla(t.end),
+                              "speed_mps": None if t.speed_mps is None else float(t.speed_mps), "description": t.description}
+    e = cfg.environment
+    fl = lambda m: None if m is None else {k: ([float(x) for x in v] if isinstance(v, (list, tuple)) else float(v)) for k, v in m.items()}  # noqa: E731
+    env = {"ionosphere_enabled": bool(e.ionosphere_enabled), "ionosphere_model": fl(e.ionosphere_model),
+           "ionosphere_source": {"type": e.ionosphere_source}, "troposphere_enabled": bool(e.troposphere_enabled),
+           "troposphere_model": fl(e.troposphere_model), "multipath_preset": e.multipath_preset,
+           "multipath_enabled": bool(e.multipath_enabled), "ephemeris_source": {"type": e.ephemeris_source}}
+    o = cfg.output
+    outp = {"sample_rate": float(o.sample_rate), "duration_s": float(o.duration_s), "block_size": int(o.block_size),
+            "seed": int(o.seed), "start_time_gps_s": float(o.start_time_gps_s), "format": o.format,
+            "lpf_cutoff_hz": float(o.lpf_cutoff_hz), "output_path": o.output_path}
+    return {"satellites": sats, "receiver": recv, "environment": env, "output": outp}
+
+
+def dumps_config(cfg: GnssScenarioConfig) -> str:
+    """`serde_yaml::to_string(&config)`: the text of the effective-config companion file / `--export-preset`.  Round-trips
+    through loads_config."""
+    out: list = []
+    _emit(config_to_dict(cfg), 0, out)
+    return "\n".join(out) + "\n"

@@ -145,6 +145,16 @@ r4wb_error r4wb_scenario_generate(r4wb_scenario* h, uint64_t first, uint64_t n, 
     return guard([&] { h->impl.generate(first, n, dst, where, fmt); });
 }
 
+r4wb_error r4wb_scenario_write_file(r4wb_scenario* h, const char* path, r4wb_fmt fmt, uint64_t* samples, uint64_t* bytes,
+                                    double* power_sum)
+{
+    if (!h || !path) { t_error = "handle/path is NULL"; return R4WB_ERR_NULL_POINTER; }
+    return guard([&] {
+        const double p = h->impl.write_file(path, fmt, samples, bytes);
+        if (power_sum) *power_sum = p;
+    });
+}
+
 r4wb_error r4wb_scenario_last_power_sum(const r4wb_scenario* h, double* power_sum)
 {
     if (!h || !power_sum) { t_error = "handle/power_sum is NULL"; return R4WB_ERR_NULL_POINTER; }

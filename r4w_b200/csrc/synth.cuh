@@ -241,6 +241,8 @@ public:
     void generate(uint64_t first, uint64_t n, void* dst, r4wb_mem where, r4wb_fmt fmt);
     // one reference block of min(n, remaining) samples at current_sample
     uint64_t generate_block(uint64_t n, void* dst, r4wb_mem where, r4wb_fmt fmt);
+    // the CLI's file sink (main.rs:4483-4509): the whole scenario, in `fmt`, streamed into `path`; returns sum |s|^2
+    double write_file(const char* path, r4wb_fmt fmt, uint64_t* samples, uint64_t* bytes);
     double last_power_sum();
     uint32_t last_path() const { return last_path_; }
     void set_profiling(bool on) { profiling_ = on; }

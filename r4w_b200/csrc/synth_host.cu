@@ -4,6 +4,12 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
+#include <cerrno>
+#include <fcntl.h>
+#include <unistd.h>
+#include <mutex>
+#include <thread>
 
 #include "synth_math.cuh"
 #include "synth_periodic.cuh"
@@ -438,6 +444,101 @@ uint64_t Scenario::generate_block(uint64_t n_req, void* dst, r4wb_mem where, r4w
     seq_.advance(md_, tab, (uint32_t)n);
     current_ += n;
     return n;
+}
+
+// File sink: segments of ~16 Msamples are rendered into two pinned host buffers (render_to's own double-buffered D2H); a
+// writer drains one buffer into the file (kSinkWriters threads, one pwrite range each) while the next segment renders and
+// copies into the other.
+namespace {
+constexpr int kSinkWriters = 4;
+
+bool pwrite_all(int fd, const unsigned char* p, size_t n, off_t at)
+{
+    while (n > 0) {
+        const ssize_t w = ::pwrite(fd, p, std::min<size_t>(n, (size_t)64 << 20), at);
+        if (w < 0) { if (errno == EINTR) continue; return false; }
+        if (w == 0) return false;
+        p += w; n -= (size_t)w; at += w;
+    }
+    return true;
+}
+}  // namespace
+
+double Scenario::write_file(const char* path, r4wb_fmt fmt, uint64_t* samples, uint64_t* bytes)
+{
+    const ScenConst& sc = md_.sc;
+    if ((unsigned)fmt > (unsigned)R4WB_FMT_CU8) fail(R4WB_ERR_INVALID_PARAMETER, "unknown sample format %d", (int)fmt);
+    const int fd = ::open(path, O_WRONLY | O_CREAT | O_TRUNC, 0644);
+    if (fd < 0) fail(R4WB_ERR_INVALID_PARAMETER, "cannot create '%s': %s", path, std::strerror(errno));
+    const size_t bps = fmt_bytes(fmt);
+    uint64_t unit = sc.B;                                                          // segment edges on period boundaries
+    if (fmt == R4WB_FMT_CF32 && plan_periodic() && per_->L % sc.B == 0) unit = per_->L;
+    const uint64_t seg = std::max<uint64_t>(1, (uint64_t)(16u << 20) / unit) * unit;
+    const uint64_t cap = std::min<uint64_t>(seg, std::max<uint64_t>(sc.total, 1));
+    unsigned char* pin[2] = {nullptr, nullptr};
+    struct Job { const unsigned char* p; size_t n; off_t at; };
+    std::mutex mu;
+    std::condition_variable cv;
+    Job job{nullptr, 0, 0};
+    bool busy = false, quit = false, io_failed = false;
+    std::thread writer([&] {
+        for (;;) {
+            std::unique_lock<std::mutex> lk(mu);
+            cv.wait(lk, [&] { return busy || quit; });
+            if (!busy) return;
+            const Job j = job;
+            lk.unlock();
+            bool ok[kSinkWriters];
+            std::thread part[kSinkWriters];
+            const size_t each = ((j.n + kSinkWriters - 1) / kSinkWriters + 4095) / 4096 * 4096;
+            for (int t = 0; t < kSinkWriters; ++t) {
+                const size_t lo = std::min(j.n, each * t), hi = std::min(j.n, each * (t + 1));
+                ok[t] = true;
+                part[t] = std::thread([&, t, lo, hi] { if (hi > lo) ok[t] = pwrite_all(fd, j.p + lo, hi - lo, j.at + (off_t)lo); });
+            }
+            bool all = true;
+            for (int t = 0; t < kSinkWriters; ++t) { part[t].join(); all = all && ok[t]; }
+            lk.lock();
+            if (!all) io_failed = true;
+            busy = false;
+            cv.notify_all();
+        }
+    });
+    auto drain = [&] { std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&] { return !busy; }); };
+    auto finish = [&] {
+        drain();
+        { std::lock_guard<std::mutex> lk(mu); quit = true; }
+        cv.notify_all();
+        writer.join();
+        for (auto*& p : pin) if (p) { cudaFreeHost(p); p = nullptr; }
+    };
+    double power = 0.0;
+    uint64_t done = 0;
+    try {
+        for (auto*& p : pin) R4WB_CUDA(cudaMallocHost((void**)&p, (size_t)cap * bps));
+        for (uint32_t c = 0; done < sc.total; ++c) {
+            const uint64_t n = std::min(seg, sc.total - done);
+            unsigned char* dst = pin[c & 1u];
+            render_to(done, n, dst, R4WB_MEM_HOST, fmt);                           // the other buffer may still be draining
+            power += last_power_sum();
+            drain();
+            if (io_failed) break;
+            { std::lock_guard<std::mutex> lk(mu); job = Job{dst, (size_t)n * bps, (off_t)(done * bps)}; busy = true; }
+            cv.notify_all();
+            done += n;
+        }
+    } catch (...) {
+        finish();
+        ::close(fd);
+        throw;
+    }
+    finish();
+    const bool closed = ::close(fd) == 0;
+    if (io_failed || !closed) fail(R4WB_ERR_BUFFER_FULL, "short write to '%s'", path);
+    current_ = sc.total;                                                           // the CLI loop leaves the scenario done
+    if (samples) *samples = done;
+    if (bytes) *bytes = done * bps;
+    return power;
 }
 
 double Scenario::last_power_sum()

@@ -159,6 +159,13 @@ class GnssScenario:
         _lib.set_stream(torch.cuda.current_stream(out.device).cuda_stream)
         _lib.check(_lib.lib().r4wb_scenario_generate(self._h, int(first), int(n), C.c_void_p(ptr), _lib.MEM_DEVICE, fmt))
 
+    def write_file(self, path, fmt: int = _lib.FMT_CF32):
+        """The CLI's file sink (main.rs:4483-4509): the whole scenario streamed into `path` in `fmt` -> (samples written,
+        bytes written, sum |s|^2 of the pre-conversion samples).  Leaves the scenario done."""
+        n, b, p = C.c_uint64(0), C.c_uint64(0), C.c_double(0.0)
+        _lib.check(_lib.lib().r4wb_scenario_write_file(self._h, str(path).encode(), int(fmt), C.byref(n), C.byref(b), C.byref(p)))
+        return int(n.value), int(b.value), float(p.value)
+
     def last_power_sum(self) -> float:
         """Sum |s|^2 over the last generate call (the CLI's avg-power line, main.rs:4494-4509)."""
         v = C.c_double(0.0)
