@@ -160,6 +160,12 @@ typedef struct r4wb_acq_result {
 typedef struct r4wb_scenario r4wb_scenario;   /* opaque: GnssScenario, gnss/scenario.rs:51-74 */
 typedef struct r4wb_pcps r4wb_pcps;           /* opaque: PcpsAcquisition, gnss/acquisition.rs:40-55 */
 
+/* Threading.  A scenario, tracker or composer handle mirrors a `&mut self` object: one host thread at a time.  A pcps
+ * handle mirrors `PcpsAcquisition::acquire(&self)` (re-entrant in the reference): after configuration it may be shared
+ * between threads; searches on one handle take turns on its device scratch.  Every call returns with its results complete
+ * (the calling thread's stream is synchronised before a host result is handed back).  Errors never unwind through the
+ * boundary: a code is returned and the text is kept per thread (r4wb_last_error). */
+
 /* ---- library ---- */
 const char* r4wb_version(void);                 /* static NUL-terminated, like r4w_version (r4w-ffi/src/lib.rs:119-123) */
 const char* r4wb_last_error(void);              /* thread-local text of the last failure */

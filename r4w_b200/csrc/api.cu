@@ -2,6 +2,7 @@
 // Every entry point converts internal failures into r4wb_error + a thread-local message; nothing unwinds.
 #include <cmath>
 #include <cstring>
+#include <mutex>
 #include <new>
 
 #include "acq.cuh"
@@ -42,6 +43,12 @@ static r4wb_error guard(F&& body)
     }
 }
 
+template <typename H, typename F>
+static r4wb_error guard_on(const H* h, F&& body)
+{
+    return guard([&] { R4WB_CUDA(cudaSetDevice(h->device)); body(); });
+}
+
 static void require_device()
 {
     int n = 0;
@@ -55,10 +62,15 @@ static void require_device()
 
 using namespace r4wb;
 
-struct r4wb_scenario { Scenario impl; explicit r4wb_scenario(const r4wb_scenario_cfg& c) : impl(c) {} };
-struct r4wb_pcps { Pcps impl; r4wb_pcps(uint64_t n, double fs) : impl(n, fs) {} };
-struct r4wb_composer { Composer impl; r4wb_composer(uint32_t n, double fs, double sd, uint64_t seed) : impl(n, fs, sd, seed) {} };
-struct r4wb_tracker { TrackerBank impl; r4wb_tracker(const r4wb_track_cfg* c, uint32_t n) : impl(c, n) {} };
+// A handle lives on the device that was current when it was created; every call that touches the device re-selects it, so a
+// handle can be used from a host thread whose current device is another one (new threads start on device 0).
+static int device_now() { int d = 0; cudaGetDevice(&d); return d; }
+struct r4wb_scenario { int device = device_now(); Scenario impl; explicit r4wb_scenario(const r4wb_scenario_cfg& c) : impl(c) {} };
+// `PcpsAcquisition::acquire(&self)` is re-entrant in the reference; here a handle owns device scratch, so concurrent calls on
+// one handle take turns (`mu`)
+struct r4wb_pcps { int device = device_now(); Pcps impl; std::mutex mu; r4wb_pcps(uint64_t n, double fs) : impl(n, fs) {} };
+struct r4wb_composer { int device = device_now(); Composer impl; r4wb_composer(uint32_t n, double fs, double sd, uint64_t seed) : impl(n, fs, sd, seed) {} };
+struct r4wb_tracker { int device = device_now(); TrackerBank impl; r4wb_tracker(const r4wb_track_cfg* c, uint32_t n) : impl(c, n) {} };
 
 extern "C" {
 
@@ -128,7 +140,7 @@ uint64_t r4wb_scenario_current_sample(const r4wb_scenario* h) { return h ? h->im
 r4wb_error r4wb_scenario_reset(r4wb_scenario* h)
 {
     if (!h) { t_error = "handle is NULL"; return R4WB_ERR_NULL_POINTER; }
-    return guard([&] { h->impl.reset(); });
+    return guard_on(h, [&] { h->impl.reset(); });
 }
 
 r4wb_error r4wb_scenario_generate_block(r4wb_scenario* h, uint64_t n, void* dst, r4wb_mem where, r4wb_fmt fmt,
@@ -136,20 +148,20 @@ r4wb_error r4wb_scenario_generate_block(r4wb_scenario* h, uint64_t n, void* dst,
 {
     if (!h || !written) { t_error = "handle/written is NULL"; return R4WB_ERR_NULL_POINTER; }
     *written = 0;
-    return guard([&] { *written = h->impl.generate_block(n, dst, where, fmt); });
+    return guard_on(h, [&] { *written = h->impl.generate_block(n, dst, where, fmt); });
 }
 
 r4wb_error r4wb_scenario_generate(r4wb_scenario* h, uint64_t first, uint64_t n, void* dst, r4wb_mem where, r4wb_fmt fmt)
 {
     if (!h) { t_error = "handle is NULL"; return R4WB_ERR_NULL_POINTER; }
-    return guard([&] { h->impl.generate(first, n, dst, where, fmt); });
+    return guard_on(h, [&] { h->impl.generate(first, n, dst, where, fmt); });
 }
 
 r4wb_error r4wb_scenario_write_file(r4wb_scenario* h, const char* path, r4wb_fmt fmt, uint64_t* samples, uint64_t* bytes,
                                     double* power_sum)
 {
     if (!h || !path) { t_error = "handle/path is NULL"; return R4WB_ERR_NULL_POINTER; }
-    return guard([&] {
+    return guard_on(h, [&] {
         const double p = h->impl.write_file(path, fmt, samples, bytes);
         if (power_sum) *power_sum = p;
     });
@@ -158,7 +170,7 @@ r4wb_error r4wb_scenario_write_file(r4wb_scenario* h, const char* path, r4wb_fmt
 r4wb_error r4wb_scenario_last_power_sum(const r4wb_scenario* h, double* power_sum)
 {
     if (!h || !power_sum) { t_error = "handle/power_sum is NULL"; return R4WB_ERR_NULL_POINTER; }
-    return guard([&] { *power_sum = const_cast<r4wb_scenario*>(h)->impl.last_power_sum(); });
+    return guard_on(h, [&] { *power_sum = const_cast<r4wb_scenario*>(h)->impl.last_power_sum(); });
 }
 
 r4wb_error r4wb_scenario_set_profiling(r4wb_scenario* h, int enabled)
@@ -171,7 +183,7 @@ r4wb_error r4wb_scenario_set_profiling(r4wb_scenario* h, int enabled)
 r4wb_error r4wb_scenario_last_profile(r4wb_scenario* h, double* ms, uint64_t* launches)
 {
     if (!h || !ms || !launches) { t_error = "handle/ms/launches is NULL"; return R4WB_ERR_NULL_POINTER; }
-    return guard([&] { h->impl.last_profile(ms, launches); });
+    return guard_on(h, [&] { h->impl.last_profile(ms, launches); });
 }
 
 uint32_t r4wb_scenario_last_path(const r4wb_scenario* h) { return h ? h->impl.last_path() : 0u; }
@@ -179,14 +191,14 @@ uint32_t r4wb_scenario_last_path(const r4wb_scenario* h) { return h ? h->impl.la
 r4wb_error r4wb_scenario_status(const r4wb_scenario* h, r4wb_sat_status* out, uint32_t cap, uint32_t* n)
 {
     if (!h || !out) { t_error = "handle/out is NULL"; return R4WB_ERR_NULL_POINTER; }
-    return guard([&] { h->impl.status(out, cap, n); });
+    return guard_on(h, [&] { h->impl.status(out, cap, n); });
 }
 
 /* test hook (not part of the drop-in surface): prologue entry of a canonical block */
 r4wb_error r4wb_debug_block_params(r4wb_scenario* h, uint64_t block, uint32_t sat, double* out12)
 {
     if (!h || !out12) { t_error = "handle/out is NULL"; return R4WB_ERR_NULL_POINTER; }
-    return guard([&] { h->impl.debug_block(block, sat, out12); });
+    return guard_on(h, [&] { h->impl.debug_block(block, sat, out12); });
 }
 
 /* ---------------------------------------------------------------- codes */
@@ -265,7 +277,7 @@ void r4wb_pcps_destroy(r4wb_pcps* h) { delete h; }
 r4wb_error r4wb_pcps_set_doppler_range(r4wb_pcps* h, double max_hz, double step_hz)
 {
     if (!h) { t_error = "handle is NULL"; return R4WB_ERR_NULL_POINTER; }
-    return guard([&] { h->impl.set_doppler_range(max_hz, step_hz); });
+    return guard_on(h, [&] { h->impl.set_doppler_range(max_hz, step_hz); });
 }
 
 r4wb_error r4wb_pcps_set_threshold(r4wb_pcps* h, double threshold)
@@ -296,15 +308,15 @@ r4wb_error r4wb_pcps_set_profiling(r4wb_pcps* h, int enabled)
 r4wb_error r4wb_pcps_last_profile(const r4wb_pcps* h, double* ms, uint64_t* launches)
 {
     if (!h || !ms || !launches) { t_error = "NULL argument"; return R4WB_ERR_NULL_POINTER; }
-    h->impl.last_profile(ms, launches);
-    return R4WB_OK;
+    return guard_on(h, [&] { h->impl.last_profile(ms, launches); });
 }
 
 r4wb_error r4wb_pcps_acquire(r4wb_pcps* h, const void* input, r4wb_fmt fmt, uint64_t n_input, const int8_t* code,
                              uint64_t code_len, uint8_t prn, r4wb_acq_result* out)
 {
     if (!h || !input || !code || !out) { t_error = "NULL argument"; return R4WB_ERR_NULL_POINTER; }
-    return guard([&] { h->impl.acquire_batch(input, fmt, R4WB_MEM_HOST, 1, 0, n_input, code, code_len, &prn, 1, out); });
+    std::lock_guard<std::mutex> lk(h->mu);
+    return guard_on(h, [&] { h->impl.acquire_batch(input, fmt, R4WB_MEM_HOST, 1, 0, n_input, code, code_len, &prn, 1, out); });
 }
 
 r4wb_error r4wb_pcps_acquire_batch(r4wb_pcps* h, const void* input, r4wb_fmt fmt, r4wb_mem where, uint64_t n_snapshots,
@@ -312,14 +324,16 @@ r4wb_error r4wb_pcps_acquire_batch(r4wb_pcps* h, const void* input, r4wb_fmt fmt
                                    const uint8_t* prns, uint32_t n_codes, r4wb_acq_result* out)
 {
     if (!h || !input || !codes || !out) { t_error = "NULL argument"; return R4WB_ERR_NULL_POINTER; }
-    return guard([&] { h->impl.acquire_batch(input, fmt, where, n_snapshots, snapshot_stride, n_input, codes, code_len, prns, n_codes, out); });
+    std::lock_guard<std::mutex> lk(h->mu);
+    return guard_on(h, [&] { h->impl.acquire_batch(input, fmt, where, n_snapshots, snapshot_stride, n_input, codes, code_len, prns, n_codes, out); });
 }
 
 r4wb_error r4wb_pcps_acquire_grid(r4wb_pcps* h, const void* input, r4wb_fmt fmt, uint64_t n_input, const int8_t* code,
                                   uint64_t code_len, double* power_out, uint64_t cap)
 {
     if (!h || !input || !code || !power_out) { t_error = "NULL argument"; return R4WB_ERR_NULL_POINTER; }
-    return guard([&] { h->impl.acquire_grid(input, fmt, n_input, code, code_len, power_out, cap); });
+    std::lock_guard<std::mutex> lk(h->mu);
+    return guard_on(h, [&] { h->impl.acquire_grid(input, fmt, n_input, code, code_len, power_out, cap); });
 }
 
 
@@ -340,19 +354,19 @@ r4wb_error r4wb_track_process(r4wb_tracker* h, const void* samples, r4wb_fmt fmt
                               uint64_t channel_stride, const int8_t* codes, uint64_t code_stride, r4wb_track_state* out)
 {
     if (!h) { t_error = "handle is NULL"; return R4WB_ERR_NULL_POINTER; }
-    return guard([&] { h->impl.process(samples, fmt, where, n_per_period, n_periods, channel_stride, codes, code_stride, out); });
+    return guard_on(h, [&] { h->impl.process(samples, fmt, where, n_per_period, n_periods, channel_stride, codes, code_stride, out); });
 }
 
 r4wb_error r4wb_track_state_get(const r4wb_tracker* h, r4wb_track_state* out, uint32_t cap)
 {
     if (!h || !out) { t_error = "handle/out is NULL"; return R4WB_ERR_NULL_POINTER; }
-    return guard([&] { h->impl.state(out, cap); });
+    return guard_on(h, [&] { h->impl.state(out, cap); });
 }
 
 r4wb_error r4wb_track_nav_bits(const r4wb_tracker* h, uint32_t channel, int8_t* out, uint64_t cap, uint64_t* n)
 {
     if (!h || !n) { t_error = "handle/n is NULL"; return R4WB_ERR_NULL_POINTER; }
-    return guard([&] { *n = h->impl.nav_bits(channel, out, cap); });
+    return guard_on(h, [&] { *n = h->impl.nav_bits(channel, out, cap); });
 }
 
 
@@ -380,7 +394,7 @@ r4wb_error r4wb_composer_block(r4wb_composer* h, const void* baseband, r4wb_fmt 
                                const double* amplitude, const uint8_t* active, void* out, r4wb_fmt out_fmt, r4wb_mem out_where)
 {
     if (!h) { t_error = "handle is NULL"; return R4WB_ERR_NULL_POINTER; }
-    return guard([&] { h->impl.block(baseband, in_fmt, in_where, n, doppler_hz, amplitude, active, out, out_fmt, out_where); });
+    return guard_on(h, [&] { h->impl.block(baseband, in_fmt, in_where, n, doppler_hz, amplitude, active, out, out_fmt, out_where); });
 }
 
 r4wb_error r4wb_composer_phases(const r4wb_composer* h, double* out, uint32_t cap)

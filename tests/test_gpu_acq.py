@@ -250,3 +250,33 @@ def test_register_engine_equals_shared_memory_engine(gpu):
 
     a, b = run({}), run({"R4WB_ACQ_ENGINE": "smem"})
     assert a == b and a.count(";") == 6 * 16 - 1
+
+
+def test_shared_handle_from_several_threads():
+    """`acquire(&self)` is re-entrant in the reference: one handle searched from four host threads at once (ctypes drops the
+    GIL during the call) gives each thread the sequential answer"""
+    import threading
+    import r4w_b200 as gpu
+    cfg = _cfg("e1c_8prn_20s_clean")
+    x = gpu.GnssScenario(cfg, noise=False).generate_range(0, 20000)
+    acq = gpu.PcpsAcquisition(20000, 5e6).with_doppler_range(5000.0, 250.0)
+    prns = [3, 25, 8, 2, 13, 15, 1, 7]
+    codes = {p: gpu.e1c_replica(p, 5e6, 20000) for p in prns}
+    want = {p: acq.acquire(x, codes[p], p) for p in prns}
+    got, errs = {}, []
+
+    def work(mine):
+        try:
+            for _ in range(3):
+                for p in mine:
+                    got[p] = acq.acquire(x, codes[p], p)
+        except Exception as e:          # noqa: BLE001
+            errs.append(e)
+
+    ts = [threading.Thread(target=work, args=(prns[k::4],)) for k in range(4)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert not errs
+    for p in prns:
+        assert (got[p].code_phase, got[p].doppler_hz, got[p].detected) == (want[p].code_phase, want[p].doppler_hz, want[p].detected)
+        assert abs(got[p].peak_metric - want[p].peak_metric) <= 1e-9 * want[p].peak_metric
