@@ -11,6 +11,8 @@ collective; one all-gather of the peak table).  `value` is synthesis throughput 
 the `acq` object carries the cells/s half with its own roofline / e2e / cpu_baseline.
 
   python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path
+  python bench.py --workload e1c_8prn_60s_cn34_orbital.yaml      # another BASELINE.json config as the segment (weak: one per GPU)
+  python bench.py --workload e1c_8prn_600s_cn34_orbital.yaml --strong --acq-snapshots 5000   # config 5: 600 s split over the ranks
   python bench.py --impl reference [...]                         # the reference algorithm on the host cores
 """
 from __future__ import annotations
@@ -33,6 +35,7 @@ WORKLOAD = "e1c_8prn_20s_clean.yaml"
 SEGMENT_S = 20.0
 CODE_LENGTH = 20000            # samples per E1C primary-code period at 5 MHz
 DOPPLER_MAX, DOPPLER_STEP = 5000.0, 250.0
+E2E_MAX_SAMPLES = 300_000_000  # the host-buffer (e2e) legs cover at most this many samples of a rank's segment
 FLOP_PER_CELL = 264.6          # reference-equivalent flop per (PRN, Doppler, lag) cell
 FP32_PEAK_TFLOPS = 74.4        # 148 SM x 128 lanes x 2 x 1.965 GHz (nominal; MEASURED_PEAKS.json has no FP32 figure)
 HBM_FALLBACK_GBS = 6650.0      # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
@@ -100,9 +103,17 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def load_workload(n_ranks: int):
+def load_workload(n_ranks: int, args=None):
+    """The scenario all ranks share.  Default: the 20 s bench workload, weak-scaled (N x 20 s).  `--workload X.yaml` names
+    another of BASELINE.json's configs: weak scaling repeats its duration per GPU, `--strong` keeps the config's own
+    duration and splits it over the ranks (config 5: the 600 s file time-sharded across 2/4/8 GPUs)."""
+    global WORKLOAD, SEGMENT_S
     from r4w_b200.config import load_config
+    if args is not None and args.workload:
+        WORKLOAD = os.path.basename(args.workload)
     cfg = load_config(os.path.join(ROOT, "configs", WORKLOAD), cli_elevation_mask_deg=5.0)   # the CLI's default mask
+    if args is not None and args.workload:
+        SEGMENT_S = cfg.output.duration_s / n_ranks if args.strong else cfg.output.duration_s
     cfg.output.duration_s = SEGMENT_S * n_ranks
     return cfg
 
@@ -154,7 +165,7 @@ def run_reference(args):
     from oracle import oracle as O
     O.build()
     cores = os.cpu_count() or 1
-    cfg = load_workload(max(1, args.gpus))
+    cfg = load_workload(max(1, args.gpus), args)
     n_sats = len(cfg.satellites)
     th_s = max(1, min(n_sats, cores))
     prns = [s.prn for s in cfg.satellites]
@@ -210,7 +221,7 @@ def run_b200(args):
     R.init(local)
     dev = torch.device("cuda", local)
 
-    cfg = load_workload(world)
+    cfg = load_workload(world, args)
     prns = [s.prn for s in cfg.satellites]
     codes = np.stack([R.e1c_replica(p, 5e6, CODE_LENGTH) for p in prns])
     scen = R.GnssScenario(cfg, noise=True)
@@ -283,6 +294,9 @@ def run_b200(args):
     # ---- e2e: the same step through the C-ABI with HOST buffers (pinned), copies inside the timed region
     import ctypes as C
     host = C.c_void_p()
+    n_full, n_snap_full = n, n_snap
+    n = min(n, E2E_MAX_SAMPLES)                                  # host-buffer legs: at most 60 s of samples (2.4 GB pinned)
+    n_snap = min(n_snap, n // CODE_LENGTH)
     _lib.check(_lib.lib().r4wb_host_alloc(C.byref(host), n * 8))
     host_np = np.ctypeslib.as_array(C.cast(host, C.POINTER(C.c_float)), shape=(2 * n,)).view(np.complex64)
     e2e_steps = max(1, min(args.steps, 3))
@@ -313,6 +327,7 @@ def run_b200(args):
         tab2 = results_to_table(pods, n_snap, len(prns))
     torch.cuda.synchronize()
     ms_acq_e2e = (time.perf_counter() - ts) * 1e3 / e2e_steps
+    n_e2e, n_snap_e2e, n, n_snap = n, n_snap, n_full, n_snap_full
 
     # ---- tracking channels, rank 0, outside the timed step: one E1C channel per satellite of the scenario over
     # the first second of the rendered stream (250 code periods of 20 000 samples), device-resident input
@@ -396,11 +411,11 @@ def run_b200(args):
         line = {
             "metric": "gnss_iq_synth_msamples_per_s", "value": total_samples / (ms_syn * 1e-3) / 1e6, "unit": "Msamples/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_syn, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{WORKLOAD} x {world} GPU(s): {SEGMENT_S:.0f} s segment per GPU (time-sharded), 8 Galileo E1C PRNs, "
-                                   f"5 MS/s, noise on, cf32 into HBM; then PCPS over {n_snap} snapshots/GPU x 8 PRNs x {bins} Doppler bins x "
+            "scaling": "strong" if args.strong else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{WORKLOAD} x {world} GPU(s): {SEGMENT_S:g} s segment per GPU (time-sharded), {len(prns)} Galileo E1C PRNs, "
+                                   f"5 MS/s, noise on, cf32 into HBM; then PCPS over {n_snap} snapshots/GPU x {len(prns)} PRNs x {bins} Doppler bins x "
                                    f"{CODE_LENGTH} lags", "samples_per_gpu": n, "snapshots_per_gpu": n_snap, "prns": prns,
-                       "l2": "per-step output 0.8 GB and spectra working set exceed the 126 MB L2 (no explicit flush)",
+                       "l2": f"per-step output {n * 8 / 1e9:.1f} GB and spectra working set exceed the 126 MB L2 (no explicit flush)",
                        "step": "synth then acquire; ms_per_step/value cover the synthesis half, acq.* the acquisition half, ms_step_total both"},
             "ms_step_total": ms_total,
             "roofline": {"bound": "hbm", "kernel": syn_kernel, "achieved": synth_gbs, "peak": peak, "unit": "GB/s", "frac": synth_gbs / peak,
@@ -409,8 +424,8 @@ def run_b200(args):
                          "note": "8 B per output sample (one cf32 store) x the samples this kernel wrote / its CUDA-event time on the launching "
                                  "stream; `value` is over the whole generate call (all kernels + launch gaps)"},
             "synth_kernel_ms": {k: v[0] for k, v in sprof.items()}, "synth_kernel_launches": {k: v[1] for k, v in sprof.items()},
-            "e2e": {"value": total_samples / (ms_syn_e2e * 1e-3) / 1e6, "unit": "Msamples/s", "h2d_bytes_per_step": 0,
-                    "d2h_bytes_per_step": n * 8, "api": "r4wb_scenario_generate(..., R4WB_MEM_HOST, CF32) into pinned host memory",
+            "e2e": {"value": n_e2e * world / (ms_syn_e2e * 1e-3) / 1e6, "unit": "Msamples/s", "h2d_bytes_per_step": 0,
+                    "d2h_bytes_per_step": n_e2e * 8, "samples_per_gpu": n_e2e, "api": "r4wb_scenario_generate(..., R4WB_MEM_HOST, CF32) into pinned host memory",
                     "other_formats_rank0": fmt_e2e},
             "acq": {"metric": "pcps_acq_cells_per_s", "value": cells / (ms_acq * 1e-3), "unit": "cells/s", "ms_per_step": ms_acq,
                     "cells_per_step": cells, "f64_guard_reruns": guards,
@@ -419,8 +434,9 @@ def run_b200(args):
                                  "unit": "TFLOP/s", "frac": (acq_tflops / FP32_PEAK_TFLOPS) if acq_tflops else None, "traffic": ncu_traffic("k_rf_inv_peak_tm"),
                                  "peak_source": "nominal FP32 FMA peak (148 SM x 128 lanes x 2 x 1.965 GHz)",
                                  "note": f"{FLOP_PER_CELL} reference-equivalent flop per cell / summed CUDA-event time of the forward and inverse FFT kernels"},
-                    "e2e": {"value": cells / (ms_acq_e2e * 1e-3), "unit": "cells/s", "h2d_bytes_per_step": n_snap * CODE_LENGTH * 8,
-                            "d2h_bytes_per_step": n_snap * len(prns) * 32,
+                    "e2e": {"value": n_snap_e2e * len(prns) * bins * CODE_LENGTH * world / (ms_acq_e2e * 1e-3), "unit": "cells/s",
+                            "h2d_bytes_per_step": n_snap_e2e * CODE_LENGTH * 8, "d2h_bytes_per_step": n_snap_e2e * len(prns) * 32,
+                            "snapshots_per_gpu": n_snap_e2e,
                             "api": "r4wb_pcps_acquire_batch(..., R4WB_MEM_HOST) from pinned host memory"},
                     "first_snapshot": [[int(table[0, c, 2]), float(table[0, c, 3])] for c in range(len(prns))],
                     "default_grid_rank0": {"bins": acq21.num_doppler_bins(), "snapshots": ns21, "cells_per_s": cells21 / (ms_acq21 * 1e-3),
@@ -446,6 +462,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--acq-snapshots", type=int, default=0, help="snapshots per GPU per step (0 = the whole segment)")
+    ap.add_argument("--workload", default="", help="another config of BASELINE.json (file name under configs/); default " + WORKLOAD)
+    ap.add_argument("--strong", action="store_true", help="with --workload: split the config's own duration over the ranks")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-track", action="store_true", help="skip the tracking-channel leg (SURVEY.md section 8 f2)")
     args = ap.parse_args()
