@@ -198,7 +198,7 @@ def run_reference(args):
                 "e2e": {"value": a, "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------- GPU arm
@@ -242,13 +242,15 @@ def run_b200(args):
     def step(record):
         e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
         e0.record()
+        th = time.perf_counter()
         scen.generate_device(first, n, iq)
+        th = time.perf_counter() - th
         e1.record()
         pods = acq.acquire_batch_raw(iq, n_snap, CODE_LENGTH, CODE_LENGTH, codes, prns)
         table = all_gather_table(results_to_table(pods, n_snap, len(prns)))
         e2.record()
         if record is not None:
-            record.append((e0, e1, e2, acq.last_profile(), acq.guard_count(), scen.last_profile()))
+            record.append((e0, e1, e2, acq.last_profile(), acq.guard_count(), scen.last_profile(), th))
         return table
 
     for _ in range(max(args.warmup, 0)):
@@ -275,6 +277,9 @@ def run_b200(args):
     prof = rec[-1][3]
     sprof = {k: (float(np.mean([r[5][k][0] for r in rec])), rec[-1][5][k][1]) for k in rec[-1][5]}
     guards = int(np.sum([r[4] for r in rec]))
+    if os.environ.get("R4WB_BENCH_DEBUG"):
+        print(f"[rank {rank}] synth e0->e1 {ms_syn:.3f} ms, kernels {dict((k, round(v[0], 3)) for k, v in sprof.items())}, "
+              f"host enqueue {np.mean([r[6] for r in rec]) * 1e3:.3f} ms, first {first}, n {n}", file=sys.stderr, flush=True)
 
     # the CLI's average-power line (main.rs:4494-4509) over all ranks' segments: one all-reduce of {sum |s|^2, count}
     scen.generate_device(first, n, iq)
@@ -450,9 +455,29 @@ def run_b200(args):
         if cpu is not None:
             line["cpu_baseline"] = cpu[0]
             line["acq"]["cpu_baseline"] = cpu[1]
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Everything a library prints on fd 1 from here on (NCCL's version banner at communicator creation, for one) goes to
+    stderr; `emit` writes the ONE JSON line of the contract on the real stdout."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
 
 
 def main():
@@ -467,6 +492,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-track", action="store_true", help="skip the tracking-channel leg (SURVEY.md section 8 f2)")
     args = ap.parse_args()
+    quiet_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -436,13 +436,14 @@ R4WB_HD_NOINLINE uint32_t chip_sign_exact(const BlockSat& bs, long long q, const
 {
     const double g = (double)(bs.G + (uint64_t)q);
     const double cf = add_rn(bs.phase0, div_rn(g, spc));                       // satellite_emitter.rs:268
-    const double cm = fmod(cf, (double)cd.code_len);
-    uint32_t c = cm > 0.0 ? (uint32_t)cm : 0u;                                   // :269
-    if (c > cd.code_len - 1u) c = cd.code_len - 1u;                              // :281
-    const double cp = cf - floor(cf);                                            // :270
+    // `cf % code_length` (:269, Rust % = fmod) is exact for 0 <= cf < 2^53: floor(cf) mod code_length + frac(cf), so the chip
+    // index `(..) as usize` is an integer remainder (always <= code_length - 1, the clamp of :281 never binds)
+    const double fl = floor(cf);
+    const uint32_t c = cf > 0.0 ? (uint32_t)((uint64_t)fl % cd.code_len) : 0u;
+    const double cp = cf - fl;                                                   // :270
     const double eq = div_rn(cf, (double)cd.code_len);
-    const uint64_t ep = (uint64_t)bs.e0 + (eq > 0.0 ? (uint64_t)eq : 0ull);      // :278
-    const uint32_t boc = (cd.has_boc && !(fmod(mul_rn(cp, 2.0), 2.0) < 1.0)) ? 1u : 0u;   // :303-305
+    const uint64_t ep = (uint64_t)bs.e0 + (eq > 0.0 ? (uint64_t)eq : 0ull);      // :278 (the f64 quotient, literally: it may round up to an integer)
+    const uint32_t boc = (cd.has_boc && !(cp < 0.5)) ? 1u : 0u;                  // :303-305: (cp * 2) % 2 < 1 with cp in [0, 1) <=> cp < 0.5, exactly
     return code_bit(per, c) ^ boc ^ ((uint32_t)(cd.epoch_bits >> (uint32_t)(ep % cd.epoch_period)) & 1u);
 }
 
@@ -456,6 +457,20 @@ R4WB_HD uint32_t chip_sign(const BlockSat& bs, long long q, const uint32_t* __re
     return halfchip_sign(per, h, cd);
 }
 
+// sign of tap k of the window whose newest oversample is g (relative to the start of `cur`): 0 <=> +1, 1 <=> -1, -1 <=> the
+// tap reaches into the zero-initialised delay line (or history older than one block: not modelled) and contributes nothing
+R4WB_HD int tap_sign(const BlockSat& cur, const BlockSat* __restrict__ tab, const uint32_t* __restrict__ per, long long g, int k,
+                     uint64_t delta46, double spc, const SatCode& cd)
+{
+    long long q = g - k;
+    if (q >= 0) return (int)chip_sign(cur, q, per, delta46, spc, cd);
+    if (cur.prev < 0) return -1;
+    const BlockSat& pb = tab[cur.prev];
+    q += (long long)kOversample * pb.n;
+    if (q < 0) return -1;
+    return (int)chip_sign(pb, q, per, delta46, spc, cd);
+}
+
 // direct 63-tap evaluation of output sample i of block entry `cur` (history from `prev`): the reference's own loop
 // (fir.rs:392-409 over satellite_emitter.rs:264-330), used for samples whose window touches an ambiguous boundary.
 R4WB_HD_NOINLINE float fir_direct(const BlockSat& cur, const BlockSat* __restrict__ tab, const uint32_t* __restrict__ per,
@@ -464,21 +479,68 @@ R4WB_HD_NOINLINE float fir_direct(const BlockSat& cur, const BlockSat* __restric
     float acc = 0.0f;
     const long long g = (long long)kOversample * i;
     for (int k = 0; k < kTaps; ++k) {
-        long long q = g - k;
-        uint32_t sgn;
-        if (q >= 0) {
-            sgn = chip_sign(cur, q, per, delta46, spc, cd);
-        } else {
-            if (cur.prev < 0) continue;                      // zero-initialised delay line
-            const BlockSat& pb = tab[cur.prev];
-            q += (long long)kOversample * pb.n;
-            if (q < 0) continue;                             // history older than one block: not modelled
-            sgn = chip_sign(pb, q, per, delta46, spc, cd);
-        }
+        const int sgn = tap_sign(cur, tab, per, g, k, delta46, spc, cd);
+        if (sgn < 0) continue;
         acc += sgn ? -taps[k] : taps[k];
     }
     return acc;
 }
+
+#ifdef __CUDACC__
+// fir_direct for the lanes of a warp that need it, evaluated by the WHOLE warp.  A lane owns the adjacent samples i and i + 1
+// (`need_a`, `need_b`).  The lanes that meet an ambiguous boundary own consecutive samples (the boundary stays inside the
+// 63-tap window for eight samples), so their windows overlap: requesters whose windows fit into one span of 128 oversamples
+// form a group, lane l resolves the signs of oversamples l, l + 32, l + 64, l + 96 of the span (the expensive part: the
+// reference's literal f64 chip index for the one oversample inside the rounding band — once per group, not once per requester
+// and tap), eight ballots publish them, and every requester adds its 63 taps in the reference's order: the same f32 sum as
+// fir_direct, bit for bit.  Every lane of the warp must call this (converged); lane order = sample order.
+static __device__ __noinline__ float2 fir_direct_warp(bool need_a, bool need_b, int i, float2 y, const BlockSat& cur,
+                                                      const BlockSat* __restrict__ tab, const uint32_t* __restrict__ per,
+                                                      const float* __restrict__ taps, uint64_t delta46, double spc, const SatCode& cd)
+{
+    unsigned m = __ballot_sync(0xffffffffu, need_a || need_b);
+    const int lane = (int)(threadIdx.x & 31u);
+    const long long g_lo = (long long)kOversample * (need_a ? i : i + 1), g_hi = (long long)kOversample * (need_b ? i + 1 : i);
+    while (m) {
+        const int src = __ffs((int)m) - 1;
+        const long long g0 = __shfl_sync(0xffffffffu, g_lo, src);              // the group's oldest window
+        const bool mine = ((m >> lane) & 1u) && g_lo >= g0 && g_hi - g0 <= 128 - kTaps;
+        const unsigned grp = __ballot_sync(0xffffffffu, mine);                  // contains src
+        const long long base = g0 - (kTaps - 1);                                // span = oversamples [base, base + 128)
+        unsigned neg[4], val[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int sgn = tap_sign(cur, tab, per, base + lane + 32 * r, 0, delta46, spc, cd);
+            neg[r] = __ballot_sync(0xffffffffu, sgn == 1);
+            val[r] = __ballot_sync(0xffffffffu, sgn >= 0);
+        }
+        if (mine) {
+            const unsigned long long negA = neg[0] | ((unsigned long long)neg[1] << 32), negB = neg[2] | ((unsigned long long)neg[3] << 32);
+            const unsigned long long valA = val[0] | ((unsigned long long)val[1] << 32), valB = val[2] | ((unsigned long long)val[3] << 32);
+#pragma unroll 1
+            for (int h = 0; h < 2; ++h) {
+                if (!(h ? need_b : need_a)) continue;
+                // the window's 63 signs as one word: bit j <-> span index lo + j <-> tap 62 - j
+                const int lo = (int)((long long)kOversample * (i + h) - g0);    // 0 .. 128 - kTaps
+                unsigned long long wn, wv;
+                if (lo == 0) { wn = negA; wv = valA; }
+                else if (lo < 64) { wn = (negA >> lo) | (negB << (64 - lo)); wv = (valA >> lo) | (valB << (64 - lo)); }
+                else { wn = negB >> (lo - 64); wv = valB >> (lo - 64); }
+                float acc = 0.0f;
+#pragma unroll
+                for (int k = 0; k < kTaps; ++k) {                               // the reference's order; an absent tap adds +0 (exact)
+                    const int j = kTaps - 1 - k;
+                    const float t = taps[k];
+                    acc += ((wv >> j) & 1ull) ? (((wn >> j) & 1ull) ? -t : t) : 0.0f;
+                }
+                if (h) y.y = acc; else y.x = acc;
+            }
+        }
+        m &= ~grp;
+    }
+    return y;
+}
+#endif
 
 // ---- direct path (chip rates other than 1.023 MHz: GPS L5, GLONASS L1OF) -------------------------------------------------
 // sign bit (1 <=> -1) of oversample q of block entry bs: the reference expression, literally (satellite_emitter.rs:264-292,
@@ -703,6 +765,12 @@ R4WB_HD void sat_accumulate_t(const TileSat& ts, const SynthK& K, const uint2* _
             const bool amb_a = ((ta0 + e) & m) < 2 * e || ((ta1 + e) & m) < 2 * e || ((ta2 + e) & m) < 2 * e || ((ta3 + e) & m) < 2 * e;
             const bool amb_b = ((tb0 + e) & m) < 2 * e || ((tb1 + e) & m) < 2 * e || ((tb2 + e) & m) < 2 * e || ((tb3 + e) & m) < 2 * e;
             const uint32_t ia = ia0 + 2u * (uint32_t)kSynthThreads * (uint32_t)k;
+#ifdef __CUDA_ARCH__
+            // device: the warp shares the literal evaluation (all lanes are here: `check` and k are uniform)
+            const bool need_a = amb_a && ia < i_end, need_b = amb_b && ia + 1 < i_end;
+            if (__any_sync(0xffffffffu, need_a || need_b))
+                y = fir_direct_warp(need_a, need_b, (int)ia, y, *slow.cur, slow.tab, slow.per, slow.taps, K.delta46, K.spc, *slow.code);
+#else
             if (amb_a && ia < i_end) {
                 y.x = fir_direct(*slow.cur, slow.tab, slow.per, slow.taps, (int)ia, K.delta46, K.spc, *slow.code);
                 if (n_ambiguous) ++*n_ambiguous;
@@ -711,6 +779,7 @@ R4WB_HD void sat_accumulate_t(const TileSat& ts, const SynthK& K, const uint2* _
                 y.y = fir_direct(*slow.cur, slow.tab, slow.per, slow.taps, (int)ia + 1, K.delta46, K.spc, *slow.code);
                 if (n_ambiguous) ++*n_ambiguous;
             }
+#endif
         }
         if (k == 0 && (ts.flags & 8u) && tid < 4u) y = make_float2(yfix[2u * tid], yfix[2u * tid + 1u]);
         if (exact_rot) {
