@@ -20,7 +20,8 @@ namespace r4wb {
 void launch_synth_kernel(const SynthArgs& a, int K, r4wb_fmt fmt, int grid, cudaStream_t st);
 int synth_max_blocks_per_sm(int K, r4wb_fmt fmt, size_t smem);
 void launch_synth_direct(const SynthArgs& a, r4wb_fmt fmt, cudaStream_t st);
-void launch_block_params(const ScenConst&, const SatConst*, const PhaseSegment*, uint64_t, uint32_t, BlockSat*, BlockHdr*, cudaStream_t);
+void launch_block_params(const ScenConst&, const SatConst*, const PhaseSegment*, uint64_t, uint32_t, BlockSat*, BlockHdr*, double*, double*, cudaStream_t);
+void launch_phase_exact(const ScenConst&, const SatConst*, uint32_t, BlockSat*, const double*, const double*, double*, PhaseQ*, cudaStream_t);
 void launch_phase_scan(const SatConst*, uint32_t, uint32_t, BlockSat*, cudaStream_t);
 void launch_tile_params(const SynthArgs& a, uint32_t tb_begin, uint32_t tb_count, uint32_t tile_samples, TileRec* out, cudaStream_t st);
 // launchers (synth_periodic.cu)
@@ -138,7 +139,16 @@ void Scenario::build_canonical_table(uint64_t blk_begin, uint64_t blk_end)
     if (per_) per_->planned = false;
     d_tab_.reserve(std::max<size_t>(1, (size_t)nblk * sc.n_sats));
     d_hdr_.reserve(std::max<size_t>(1, nblk));
-    launch_block_params(sc, d_sat_.p, d_segments_.p, blk_begin, (uint32_t)nblk, d_tab_.p, d_hdr_.p, st);
+    // dynamic satellites: the reference's sequentially accumulated f64 carrier phase, reproduced exactly (synth_math.cuh:
+    // block_phase_q / phase_after_block) unless the caller asked for the closed form; needs the table to start at block 0
+    const bool exact_phase = md_.any_dynamic && !(sc.flags & R4WB_FLAG_CLOSED_FORM_PHASE) && blk_begin == 0 && sc.n_sats > 0;
+    DevBuf<double> dop, papprox, pstart;            // scratch of this build only
+    DevBuf<PhaseQ> pq;
+    if (exact_phase) {
+        const size_t ne = (size_t)nblk * sc.n_sats;
+        dop.reserve(2 * ne); papprox.reserve(ne); pstart.reserve(ne); pq.reserve(ne);
+    }
+    launch_block_params(sc, d_sat_.p, d_segments_.p, blk_begin, (uint32_t)nblk, d_tab_.p, d_hdr_.p, dop.p, papprox.p, st);
     if (sc.n_sats == 0) {   // headers still needed
         std::vector<BlockHdr> h(nblk);
         for (uint64_t b = 0; b < nblk; ++b) {
@@ -149,6 +159,10 @@ void Scenario::build_canonical_table(uint64_t blk_begin, uint64_t blk_end)
         R4WB_CUDA(cudaStreamSynchronize(st));
     }
     if (md_.any_dynamic || md_.any_var_visibility) launch_phase_scan(d_sat_.p, sc.n_sats, (uint32_t)nblk, d_tab_.p, st);
+    if (exact_phase) {
+        launch_phase_exact(sc, d_sat_.p, (uint32_t)nblk, d_tab_.p, dop.p, papprox.p, pstart.p, pq.p, st);
+        R4WB_CUDA(cudaStreamSynchronize(st));       // the scratch buffers are freed on return
+    }
     tab_blk0_ = blk_begin;
     tab_blk1_ = blk_end;
     tab_valid_ = true;

@@ -131,7 +131,7 @@ R4WB_HD uint64_t cycles_to_fixed(double cycles)
 // satellite_emitter.rs:228-242, plus the fixed-point NCO start values the kernel needs.
 // m_or_phi: visible-sample count (static-phase satellites) or phase in cycles 0.64 (dynamic, explicit mode).
 R4WB_HD void fill_block_sat(const ScenConst& sc, const SatConst& st, const PhaseSegment* segs, uint64_t first,
-                            uint32_t n, uint64_t m_or_phi, BlockSat& o)
+                            uint32_t n, uint64_t m_or_phi, BlockSat& o, double* dop_out = nullptr /* [2]: doppler_start_hz, doppler_end_hz */)
 {
     const double fs = sc.fs;
     const double elapsed = (double)first / fs;
@@ -178,6 +178,7 @@ R4WB_HD void fill_block_sat(const ScenConst& sc, const SatConst& st, const Phase
     } else if (st.has & R4WB_HAS_RANGE_RATE) {
         ds = de = -st.range_rate_mps * st.carrier_hz / kC;
     } else { ds = dop_s; de = dop_e; }
+    if (dop_out) { dop_out[0] = ds; dop_out[1] = de; }
 
     // scenario.rs:430-439: the override, else SatelliteEmitter::status_at(t_start) (satellite_emitter.rs:165-178): the models see
     // the ORBIT's look angle (not the YAML elevation) and GPS seconds of week; 0 m when the model is disabled
@@ -294,6 +295,82 @@ R4WB_HD uint64_t block_advance(const BlockSat& b)
 {
     const uint64_t n = b.n;
     return n * (uint64_t)b.f + (uint64_t)b.df * (n * (n - 1) / 2);
+}
+
+// ---- the reference's carrier phase of a satellite whose Doppler changes (gnss/scenario.rs:516-527), exactly --------------
+// The reference keeps ONE f64 per satellite and adds a freshly computed increment per sample for the whole run; by 600 s the
+// rounding of those 3e9 additions has drifted ~2e-5 rad away from the real sum.  The drift is reproducible without walking
+// the samples in order: while |phase| stays inside one binade [2^k, 2^(k+1)) it is a multiple of u = 2^(k-52), and
+// fl(phase + inc) = phase + rint(inc / u) u (unless inc / u is an exact tie, when the parity of the running value decides).
+// So a block's advance is the INTEGER sum of its rounded increments (block_phase_q, one thread per block and satellite), and
+// only blocks that cross a binade, hold a tie, or start near zero are walked sample by sample (phase_walk).
+
+// the per-sample increment, literally: frac = i / n; doppler = ds + frac (de - ds); inc = 2.0 * PI * doppler / fs
+R4WB_HD double ref_phase_inc(double ds, double de, uint32_t i, double n_f64, double fs)
+{
+    const double frac = div_rn((double)i, n_f64);
+    const double dop = add_rn(ds, mul_rn(frac, add_rn(de, -ds)));
+    return div_rn(mul_rn(6.283185307179586, dop), fs);
+}
+
+struct PhaseQ {
+    long long Q;        // sum over the block of rint(inc_i / 2^(k-52))
+    double approx;      // real-number sum of the block's increments (0 when the satellite is not visible)
+    double span;        // bound of |partial sums| inside the block
+    int k;              // binade the sum was formed for
+    uint32_t ok;        // 1: Q usable when the phase stays in binade k over the block; 0: walk the samples
+};
+
+// approximate (real-number) advance of a block and a bound on the excursion of the partial sums
+R4WB_HD void block_phase_approx(double ds, double de, uint32_t n, double fs, double* approx, double* span)
+{
+    const double w = 6.283185307179586 / fs;
+    *approx = w * ((double)n * ds + (de - ds) * ((double)n - 1.0) * 0.5);
+    const double m = fmax(fabs(ds), fabs(de));
+    *span = ((ds < 0.0) != (de < 0.0)) ? w * m * (double)n : fabs(*approx);
+}
+
+R4WB_HD void block_phase_q(double ds, double de, uint32_t n, double fs, int k, long long* Q, bool* tie)
+{
+    long long q = 0;
+    bool t = false;
+    const double nf = (double)n;
+    for (uint32_t i = 0; i < n; ++i) {
+        const double x = scalbn(ref_phase_inc(ds, de, i, nf, fs), 52 - k);     // exact (power of two)
+        const double fl = floor(x), r = x - fl;                                 // exact
+        if (r == 0.5) t = true;
+        q += (long long)fl + (r > 0.5 ? 1 : 0);
+    }
+    *Q = q; *tie = t;
+}
+
+// true when a phase that starts the block at `ph` provably stays inside binade k for every sample of the block
+R4WB_HD bool phase_stays_in_binade(double ph, const PhaseQ& r)
+{
+    if (!r.ok || ph == 0.0 || ilogb(ph) != r.k) return false;
+    const double a = fabs(ph), lo = scalbn(1.0, r.k), hi = scalbn(1.0, r.k + 1);
+    const double margin = 1e-3 + 1e-9 * a;
+    // partial sums lie between ph and ph + approx (same-sign Doppler) or within +-span of ph
+    const double e = (ph < 0.0) ? -r.approx : r.approx;                          // advance of |phase|
+    const double amin = fmin(a, a + e), amax = fmax(a, a + e);
+    const bool mono = r.span == fabs(r.approx);
+    const double l = mono ? amin : a - r.span, h = mono ? amax : a + r.span;
+    return l - margin > lo && h + margin < hi;
+}
+
+// the block's samples one by one (the reference's own loop)
+R4WB_HD double phase_walk(double ph, double ds, double de, uint32_t n, double fs)
+{
+    const double nf = (double)n;
+    for (uint32_t i = 0; i < n; ++i) ph = add_rn(ph, ref_phase_inc(ds, de, i, nf, fs));
+    return ph;
+}
+
+// phase at the end of a block that starts at ph
+R4WB_HD double phase_after_block(double ph, const PhaseQ& r, double ds, double de, uint32_t n, double fs)
+{
+    if (phase_stays_in_binade(ph, r)) return add_rn(ph, scalbn((double)r.Q, r.k - 52));   // both multiples of u, sum inside the binade: exact
+    return phase_walk(ph, ds, de, n, fs);
 }
 
 // ----------------------------------------------------------------------------------------------

@@ -37,6 +37,7 @@ def lib():
         L.emu_scenario_generate.argtypes = [vp, u64, u64, vp, C.c_int, C.POINTER(u64)]
         L.emu_scenario_generate_block.argtypes = [vp, u64, vp, C.POINTER(u64)]
         L.emu_block_params.argtypes = [vp, u64, C.c_uint32, vp]
+        L.emu_phase_model_check.argtypes = [C.c_double, C.c_double, C.c_double, u64, vp]; L.emu_phase_model_check.restype = None
         L.emu_fft.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]
         L.emu_pcps.argtypes = [C.c_int, u64, C.c_double, C.c_double, C.c_double, vp, C.c_int, u64, vp, u64, vp, vp]
         _lib = L
@@ -111,3 +112,11 @@ def pcps(code_length: int, fs: float, dmax: float, dstep: float, x: np.ndarray, 
                    grid.ctypes.data_as(C.c_void_p) if want_grid else None)
     res = (out[0], out[1], out[2], int(out[3]))
     return res + (grid,) if want_grid else res
+
+
+def phase_model_check(d0: float, rate: float, jerk: float, blocks: int):
+    """-> (blocks where the integer-sum phase model differs from the literal accumulation, blocks walked sample by sample,
+    final phase, final phase - real-number sum)"""
+    out = np.zeros(4, np.float64)
+    lib().emu_phase_model_check(d0, rate, jerk, blocks, out.ctypes.data_as(C.c_void_p))
+    return int(out[0]), int(out[1]), float(out[2]), float(out[3])

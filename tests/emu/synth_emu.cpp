@@ -34,6 +34,9 @@ struct Emu {
         const uint64_t nblk = blk_end - blk_begin;
         tab.assign((size_t)nblk * std::max(1u, ns), BlockSat{});
         hdr.assign(nblk, BlockHdr{});
+        // k_phase_prefix / k_phase_q / k_phase_exact: the reference's sequential f64 carrier phase of dynamic satellites
+        const bool exact_phase = md.any_dynamic && !(sc.flags & R4WB_FLAG_CLOSED_FORM_PHASE) && blk_begin == 0 && ns > 0;
+        std::vector<double> dop(exact_phase ? 2 * (size_t)nblk * ns : 0);
         for (uint64_t tb = 0; tb < nblk; ++tb) {
             const uint64_t first = (blk_begin + tb) * sc.B;
             const uint64_t rem = sc.total - first;
@@ -41,10 +44,12 @@ struct Emu {
             hdr[tb] = BlockHdr{first, n, 0};
             for (uint32_t s = 0; s < ns; ++s) {
                 BlockSat o;
-                fill_block_sat(sc, md.sats[s], md.segments.data(), first, n, first, o);
+                double d2[2];
+                fill_block_sat(sc, md.sats[s], md.segments.data(), first, n, first, o, d2);
                 o.prev = tb > 0 ? (int32_t)((tb - 1) * ns + s) : -1;
                 if (!md.sats[s].static_phase) o.phi = (o.flags & 1u) ? block_advance(o) : 0ull;
                 tab[tb * ns + s] = o;
+                if (exact_phase) { dop[2 * (tb * ns + s)] = d2[0]; dop[2 * (tb * ns + s) + 1] = d2[1]; }
             }
         }
         if (md.any_dynamic || md.any_var_visibility) {
@@ -58,6 +63,42 @@ struct Emu {
                     if (dynamic) { e.phi = run; run += adv; }
                     e.prev = prev >= 0 ? (int32_t)((uint32_t)prev * ns + s) : -1;
                     if (e.flags & 1u) prev = (int)b;
+                }
+            }
+        }
+        if (exact_phase) {
+            std::vector<PhaseQ> pq((size_t)nblk * ns);
+            for (uint32_t s = 0; s < ns; ++s) {
+                if (md.sats[s].static_phase) continue;
+                double run = 0.0;                                        // k_phase_prefix
+                std::vector<double> start(nblk);
+                for (uint64_t b = 0; b < nblk; ++b) {
+                    const BlockSat& e = tab[b * ns + s];
+                    PhaseQ& r = pq[b * ns + s];
+                    r = PhaseQ{};
+                    start[b] = run;
+                    if (e.flags & 1u) block_phase_approx(dop[2 * (b * ns + s)], dop[2 * (b * ns + s) + 1], e.n, sc.fs, &r.approx, &r.span);
+                    run += r.approx;
+                }
+#pragma omp parallel for schedule(dynamic, 256)
+                for (long long b = 0; b < (long long)nblk; ++b) {        // k_phase_q
+                    const BlockSat& e = tab[b * ns + s];
+                    PhaseQ& r = pq[b * ns + s];
+                    if (!(e.flags & 1u) || start[b] == 0.0) continue;
+                    r.k = ilogb(start[b]);
+                    if (r.k < 8) continue;
+                    bool tie;
+                    block_phase_q(dop[2 * (b * ns + s)], dop[2 * (b * ns + s) + 1], e.n, sc.fs, r.k, &r.Q, &tie);
+                    r.ok = tie ? 0u : 1u;
+                }
+                double ph = 0.0;                                         // k_phase_exact
+                for (uint64_t b = 0; b < nblk; ++b) {
+                    BlockSat& e = tab[b * ns + s];
+                    e.phi = cycles_to_fixed(ph / (2.0 * kPi));
+                    if (!(e.flags & 1u)) continue;
+                    const size_t k = b * ns + s;
+                    if (phase_stays_in_binade(ph, pq[k])) ph = ph + scalbn((double)pq[k].Q, pq[k].k - 52);
+                    else ph = phase_walk(ph, dop[2 * k], dop[2 * k + 1], e.n, sc.fs);
                 }
             }
         }
@@ -183,6 +224,35 @@ int guard(F&& f)
 extern "C" {
 
 const char* emu_last_error(void) { return g_err.c_str(); }
+
+// The binade / integer-sum model of the reference's sequential f64 carrier phase (synth_math.cuh: block_phase_q,
+// phase_after_block) against the literal per-sample accumulation, for a Doppler d0 + rate t + jerk t^2 over `blocks` blocks of
+// 5000 samples at 5 MHz.  The binade is predicted from the approximate prefix exactly as k_phase_prefix / k_phase_q do.
+// out[0] = blocks where the two differ (must be 0), out[1] = blocks walked sample by sample, out[2] = final phase (rad),
+// out[3] = final phase - real-number sum (the reference's rounding drift).
+void emu_phase_model_check(double d0, double rate, double jerk, uint64_t blocks, double* out)
+{
+    const double fs = 5e6;
+    const uint32_t n = 5000;
+    double ph_ref = 0.0, ph = 0.0, approx_sum = 0.0;
+    uint64_t walked = 0, mism = 0;
+    for (uint64_t b = 0; b < blocks; ++b) {
+        const double t0 = (double)b * 1e-3, t1 = t0 + 1e-3;
+        const double ds = d0 + rate * t0 + jerk * t0 * t0, de = d0 + rate * t1 + jerk * t1 * t1;
+        ph_ref = phase_walk(ph_ref, ds, de, n, fs);
+        PhaseQ r{};
+        block_phase_approx(ds, de, n, fs, &r.approx, &r.span);
+        if (approx_sum != 0.0) {
+            r.k = ilogb(approx_sum);
+            if (r.k >= 8) { bool tie; block_phase_q(ds, de, n, fs, r.k, &r.Q, &tie); r.ok = tie ? 0u : 1u; }
+        }
+        if (!phase_stays_in_binade(ph, r)) ++walked;
+        ph = phase_after_block(ph, r, ds, de, n, fs);
+        approx_sum += r.approx;
+        if (ph != ph_ref) { ++mism; ph = ph_ref; }
+    }
+    out[0] = (double)mism; out[1] = (double)walked; out[2] = ph_ref; out[3] = ph_ref - approx_sum;
+}
 
 int emu_scenario_create(const r4wb_scenario_cfg* cfg, void** out)
 {

@@ -282,3 +282,17 @@ def test_antenna_patterns_replay_matches_oracle(oracle, emu, kind):
     got = emu.EmuScenario(cfg, noise=False).generate_range(0, 20000)
     want = oracle.OracleScenario(cfg, noise=False).generate_range(0, 20000)
     assert _relrms(got, want) <= TOL
+
+
+@pytest.mark.parametrize("d0,rate,jerk,blocks", [(2779.31, -0.42, 0.0, 20000), (-2831.7, 0.35, 0.0, 20000), (35.0, -0.9, 0.0, 60000),
+                                                 (-457.3938, 0.0, 1e-4, 20000), (0.0, 0.0, 0.0, 50)])
+def test_exact_phase_model_equals_sequential_accumulation(emu, d0, rate, jerk, blocks):
+    """the reference adds one f64 increment per sample for the whole run (scenario.rs:516-527); the product reproduces that sum
+    block by block from integer sums of the increments rounded to the binade's ulp, walking only the blocks that cross a binade
+    (or hold a tie): both must give the same f64 at EVERY block boundary — positive and negative phase, a Doppler zero crossing
+    (phase turns around), a curved Doppler, and zero Doppler"""
+    mism, walked, final, drift = emu.phase_model_check(d0, rate, jerk, blocks)
+    assert mism == 0
+    if d0 != 0.0:
+        assert walked < blocks // 10          # almost every block takes the integer-sum path
+        assert drift != 0.0                   # the reference's sum is not the real-number sum: that drift is what is reproduced
