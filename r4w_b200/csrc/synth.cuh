@@ -207,12 +207,14 @@ struct ScenarioModel {
 // sequential-API state (generate_block with caller-chosen block sizes)
 struct SeqState {
     std::vector<uint64_t> m;            // visible samples so far (static-phase satellites)
-    std::vector<uint64_t> phi;          // carrier phase, cycles 0.64 (dynamic satellites)
+    std::vector<uint64_t> phi;          // carrier phase, cycles 0.64 (dynamic satellites, closed-form scan)
+    std::vector<double> ph;             // the reference's own f64 phase accumulator (dynamic satellites; scenario.rs:516-527)
+    std::vector<double> dop;            // [2 n_sats] Doppler at the start / end of the block make_table built last
     std::vector<BlockSat> prev;         // last visible block per satellite
     std::vector<uint8_t> has_prev;
     void reset(size_t n_sats);
     // two-row table (row 0 = each satellite's last visible block, row 1 = the block [first, first+n))
-    void make_table(const ScenarioModel& md, uint64_t first, uint32_t n, std::vector<BlockSat>& tab, BlockHdr hdr[2]) const;
+    void make_table(const ScenarioModel& md, uint64_t first, uint32_t n, std::vector<BlockSat>& tab, BlockHdr hdr[2]);
     void advance(const ScenarioModel& md, const std::vector<BlockSat>& tab, uint32_t n);
 };
 

@@ -441,17 +441,23 @@ void SeqState::reset(size_t n_sats)
 {
     m.assign(n_sats, 0);
     phi.assign(n_sats, 0);
+    ph.assign(n_sats, 0.0);
+    dop.assign(2 * n_sats, 0.0);
     prev.assign(n_sats, BlockSat{});
     has_prev.assign(n_sats, 0);
 }
 
-void SeqState::make_table(const ScenarioModel& md, uint64_t first, uint32_t n, std::vector<BlockSat>& tab, BlockHdr hdr[2]) const
+void SeqState::make_table(const ScenarioModel& md, uint64_t first, uint32_t n, std::vector<BlockSat>& tab, BlockHdr hdr[2])
 {
     const uint32_t ns = md.sc.n_sats;
+    // dynamic satellites start the block at the reference's own f64 phase (walked sample by sample in advance()) unless the
+    // caller asked for the closed form
+    const bool exact = !(md.sc.flags & R4WB_FLAG_CLOSED_FORM_PHASE);
     tab.assign((size_t)2 * std::max(1u, ns), BlockSat{});
     for (uint32_t s = 0; s < ns; ++s) {
         BlockSat cur;
-        fill_block_sat(md.sc, md.sats[s], md.segments.data(), first, n, md.sats[s].static_phase ? m[s] : phi[s], cur);
+        const uint64_t dyn_phi = exact ? cycles_to_fixed(ph[s] / (2.0 * kPi)) : phi[s];
+        fill_block_sat(md.sc, md.sats[s], md.segments.data(), first, n, md.sats[s].static_phase ? m[s] : dyn_phi, cur, &dop[2 * s]);
         cur.prev = has_prev[s] ? (int32_t)s : -1;
         tab[s] = prev[s];
         tab[ns + s] = cur;
@@ -467,7 +473,10 @@ void SeqState::advance(const ScenarioModel& md, const std::vector<BlockSat>& tab
         const BlockSat& cur = tab[ns + s];
         if (!(cur.flags & 1u)) continue;
         m[s] += n;
-        if (!md.sats[s].static_phase) phi[s] += block_advance(cur);
+        if (!md.sats[s].static_phase) {
+            phi[s] += block_advance(cur);
+            if (!(md.sc.flags & R4WB_FLAG_CLOSED_FORM_PHASE)) ph[s] = phase_walk(ph[s], dop[2 * s], dop[2 * s + 1], n, md.sc.fs);   // scenario.rs:520-523
+        }
         prev[s] = cur;
         prev[s].prev = -1;
         has_prev[s] = 1;

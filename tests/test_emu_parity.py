@@ -296,3 +296,14 @@ def test_exact_phase_model_equals_sequential_accumulation(emu, d0, rate, jerk, b
     if d0 != 0.0:
         assert walked < blocks // 10          # almost every block takes the integer-sum path
         assert drift != 0.0                   # the reference's sum is not the real-number sum: that drift is what is reproduced
+
+
+def test_sequential_blocks_equal_random_access_dynamic(emu):
+    """dynamic satellites: the sequential API walks the reference's f64 phase sample by sample on the host (SeqState::advance),
+    the random-access path rebuilds it from integer sums per block (k_phase_q / k_phase_exact) — the two must hand the kernel
+    the same start phase for every block, so canonical blocks rendered one by one equal one render of the range bit for bit"""
+    cfg = _cfg("e1c_8prn_60s_cn34_orbital")
+    a = emu.EmuScenario(cfg, noise=False)
+    seq = np.concatenate([a.generate_block(5000) for _ in range(24)])
+    rnd = emu.EmuScenario(cfg, noise=False).generate_range(0, 120000)
+    assert np.array_equal(seq, rnd)

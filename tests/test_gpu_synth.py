@@ -407,7 +407,7 @@ def test_600s_config_mid_file_equals_host_replay(gpu, emu):
     sc = gpu.GnssScenario(cfg, noise=False)
     t = time.perf_counter()
     sc.generate_range(2_999_990_000, 10_000)                       # builds the whole 600 000-block table
-    assert time.perf_counter() - t < 20.0                          # one-time prologue incl. the exact phase pass (~1 s measured)
+    assert time.perf_counter() - t < 20.0                          # one-time prologue incl. the exact phase pass (< 5 s measured on the B200 box)
     em = emu.EmuScenario(cfg, noise=False)
     for first in (2_600_000_000, 2_950_000_000, 1_312_000_000, 2_999_950_000):
         a = sc.generate_range(first, 50_000)
