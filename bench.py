@@ -14,6 +14,7 @@ the `acq` object carries the cells/s half with its own roofline / e2e / cpu_base
   python bench.py --workload e1c_8prn_60s_cn34_orbital.yaml      # another BASELINE.json config as the segment (weak: one per GPU)
   python bench.py --workload e1c_8prn_600s_cn34_orbital.yaml --strong --acq-snapshots 5000   # config 5: 600 s split over the ranks
   python bench.py --impl reference [...]                         # the reference algorithm on the host cores
+R4WB_BENCH_DEBUG=1 makes every rank print its own synthesis time, kernel times and host enqueue time on stderr.
 """
 from __future__ import annotations
 
