@@ -462,3 +462,54 @@ impl Drop for TrackingChannel {
         unsafe { sys::r4wb_track_destroy(self.h) }
     }
 }
+
+// ------------------------------------------------------------------------------------------------ r4w-sim composer
+/// The per-sample loops of `ScenarioEngine::generate_block` (crates/r4w-sim/src/scenario/engine.rs:105-135): Doppler rotation
+/// with the continuously accumulated `carrier_phases`, amplitude, sum over the emitters and receiver noise.  The engine keeps
+/// evaluating the block geometry (`EmitterState`, engine.rs:68-101) on the host and hands each block's per-emitter Doppler,
+/// amplitude and baseband here; `reset()` mirrors `ScenarioEngine::reset` (engine.rs:149-153).
+pub struct Composer {
+    h: *mut sys::r4wb_composer,
+    n_emitters: usize,
+}
+
+impl Composer {
+    /// `noise_std = sqrt(ScenarioConfig::noise_power_linear() / 2)` (engine.rs:126-127), `seed = ScenarioConfig::seed`
+    pub fn new(n_emitters: usize, sample_rate: f64, noise_std: f64, seed: u64) -> Self {
+        let mut h = std::ptr::null_mut();
+        check(unsafe { sys::r4wb_composer_create(n_emitters as u32, sample_rate, noise_std, seed, &mut h) });
+        Self { h, n_emitters }
+    }
+
+    /// One block: `baseband[e]` = `Emitter::generate_iq` of emitter `e` (all the same length), `active[e]` = the emitter passed the
+    /// engine's visibility test.  Returns the composite block; the carrier phases advance as engine.rs:108-113.
+    pub fn block(&mut self, baseband: &[Vec<IQSample>], doppler_hz: &[f64], amplitude: &[f64], active: &[bool]) -> Vec<IQSample> {
+        assert!(baseband.len() == self.n_emitters && doppler_hz.len() == self.n_emitters && amplitude.len() == self.n_emitters && active.len() == self.n_emitters);
+        let n = baseband.first().map_or(0, |b| b.len());
+        let flat: Vec<IQSample> = baseband.iter().flat_map(|b| { assert_eq!(b.len(), n); b.iter().copied() }).collect();
+        let act: Vec<u8> = active.iter().map(|&a| a as u8).collect();
+        let mut out = vec![IQSample::new(0.0, 0.0); n];
+        check(unsafe {
+            sys::r4wb_composer_block(self.h, flat.as_ptr().cast(), sys::R4WB_FMT_CF64, sys::R4WB_MEM_HOST, n as u64, doppler_hz.as_ptr(), amplitude.as_ptr(),
+                                     act.as_ptr(), out.as_mut_ptr().cast(), sys::R4WB_FMT_CF64, sys::R4WB_MEM_HOST)
+        });
+        out
+    }
+
+    /// `ScenarioEngine::carrier_phases` (radians) after the last block
+    pub fn carrier_phases(&self) -> Vec<f64> {
+        let mut out = vec![0f64; self.n_emitters];
+        check(unsafe { sys::r4wb_composer_phases(self.h, out.as_mut_ptr(), out.len() as u32) });
+        out
+    }
+
+    pub fn reset(&mut self) {
+        check(unsafe { sys::r4wb_composer_reset(self.h) })
+    }
+}
+
+impl Drop for Composer {
+    fn drop(&mut self) {
+        unsafe { sys::r4wb_composer_destroy(self.h) }
+    }
+}
