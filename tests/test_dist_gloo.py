@@ -61,3 +61,29 @@ def test_all_gather_single_process_is_identity():
     assert np.array_equal(all_gather_table(a), a)
     from r4w_b200.dist import all_reduce_power
     assert all_reduce_power(12.5, 100) == (12.5, 100)
+
+
+def test_segments_partition_the_file():
+    """time sharding (bench.py, weak and --strong): the ranks' segments tile [0, total) exactly, every inner edge is a multiple
+    of the alignment (a 4 ms snapshot), sizes differ by at most one unit, the ragged tail goes to the last rank"""
+    from r4w_b200.dist import segment_for_rank, snapshots_for_rank
+    for total, align in ((3_000_000_000, 20000), (100_000_000, 20000), (35_500, 5000), (19_999, 20000), (0, 5000)):
+        for world in (1, 2, 3, 4, 8):
+            pos = 0
+            sizes = []
+            for r in range(world):
+                first, n = segment_for_rank(total, align, r, world)
+                assert first == pos and n >= 0
+                if r < world - 1:
+                    assert (first + n) % align == 0
+                pos += n
+                sizes.append(n)
+            assert pos == total
+            assert max(sizes[:-1] or [0]) - min(sizes[:-1] or [0]) <= align
+    for n_snap, world in ((150_000, 8), (5000, 3), (7, 8), (0, 2)):
+        got = [snapshots_for_rank(n_snap, r, world) for r in range(world)]
+        assert got[0][0] == 0 and sum(c for _, c in got) == n_snap
+        assert all(got[r][0] + got[r][1] == got[r + 1][0] for r in range(world - 1))
+    import pytest
+    with pytest.raises(ValueError):
+        segment_for_rank(100, 10, 2, 2)
