@@ -203,6 +203,13 @@ r4wb_error r4wb_scenario_generate_block(r4wb_scenario* h, uint64_t n, void* dst,
  * throughput entry point (time-sharding across GPUs = disjoint [first, first+n) ranges). */
 r4wb_error r4wb_scenario_generate(r4wb_scenario* h, uint64_t first, uint64_t n, void* dst,
                                   r4wb_mem where, r4wb_fmt fmt);
+/* GnssScenario::generate, gnss/scenario.rs:549-561: `while !is_done { generate_block(block_size()) }` — everything from
+ * current_sample to the end into dst (capacity `cap` samples; InvalidSize when smaller than the remainder), *written =
+ * samples produced (0 when already done).  Leaves the handle done.  When every earlier generate_block call used the
+ * canonical block size the remainder is rendered in one pass (same samples as r4wb_scenario_generate); after odd-sized
+ * blocks it walks the reference's own block partition from current_sample. */
+r4wb_error r4wb_scenario_generate_rest(r4wb_scenario* h, void* dst, uint64_t cap, r4wb_mem where, r4wb_fmt fmt,
+                                       uint64_t* written);
 /* The CLI's file sink (`r4w gnss scenario --output`, crates/r4w-cli/src/main.rs:4483-4509: BufWriter + IqFormat::
  * write_samples per block, core/io/format.rs:191-227): renders the whole scenario [0, total_samples) in `fmt` and streams
  * it into `path` (created/truncated) — device staging -> pinned host buffers -> a writer thread, all three overlapped.

@@ -57,6 +57,7 @@ SYMBOLS = {
     "r4wb_scenario_current_sample": (_u64, [_vp]),
     "r4wb_scenario_generate_block": (_int, [_vp, _u64, _vp, _int, _int, C.POINTER(_u64)]),
     "r4wb_scenario_generate": (_int, [_vp, _u64, _u64, _vp, _int, _int]),
+    "r4wb_scenario_generate_rest": (_int, [_vp, _vp, _u64, _int, _int, C.POINTER(_u64)]),
     "r4wb_scenario_write_file": (_int, [_vp, C.c_char_p, _int, C.POINTER(_u64), C.POINTER(_u64), C.POINTER(_dbl)]),
     "r4wb_scenario_last_power_sum": (_int, [_vp, C.POINTER(_dbl)]),
     "r4wb_scenario_last_path": (C.c_uint32, [_vp]),
@@ -137,6 +138,22 @@ def ensure_init():
 
 def set_stream(cuda_stream: int):
     check(lib().r4wb_set_stream(C.c_void_p(cuda_stream)))
+
+
+class on_stream:
+    """`with on_stream(s):` — the library's thread-local stream is `s` for the calls inside and the default stream again
+    afterwards, so a later host-path call never runs on a stale (possibly destroyed) torch stream."""
+
+    def __init__(self, cuda_stream: int):
+        self._s = int(cuda_stream)
+
+    def __enter__(self):
+        set_stream(self._s)
+        return self
+
+    def __exit__(self, *exc):
+        lib().r4wb_set_stream(C.c_void_p(0))
+        return False
 
 
 def kernel_launches() -> int:

@@ -136,6 +136,7 @@ class PcpsAcquisition:
         return [[_result(pods[s * P + c]) for c in range(P)] for s in range(n_snapshots)]
 
     def acquire_batch_raw(self, input_, n_snapshots: int, snapshot_stride: int, n_input: int, codes, prns: Sequence[int]):
+        stream = None
         cs = np.ascontiguousarray(codes, np.int8)
         if cs.ndim != 2 or cs.shape[0] != len(prns):
             raise ValueError("codes must be [n_codes][code_len]")
@@ -147,16 +148,20 @@ class PcpsAcquisition:
             from .scenario import _device_ptr
             ptr, cap, fmt = _device_ptr(input_)
             where = _lib.MEM_DEVICE
-            _lib.set_stream(torch.cuda.current_stream(input_.device).cuda_stream)
+            stream = torch.cuda.current_stream(input_.device).cuda_stream
         else:
             x, fmt = _as_samples(input_)
             ptr, cap, where = x.ctypes.data, x.size, _lib.MEM_HOST
         if cap < need:
             raise ValueError(f"input holds {cap} samples, batch needs {need}")
         out = (AcqResultPod * max(n_snapshots * len(prns), 1))()
-        _lib.check(_lib.lib().r4wb_pcps_acquire_batch(self._h, C.c_void_p(ptr), fmt, where, n_snapshots, snapshot_stride,
-                                                      n_input, cs.ctypes.data_as(C.c_void_p), cs.shape[1],
-                                                      pr.ctypes.data_as(C.c_void_p), len(prns), out))
+        args = (self._h, C.c_void_p(ptr), fmt, where, n_snapshots, snapshot_stride, n_input, cs.ctypes.data_as(C.c_void_p), cs.shape[1],
+                pr.ctypes.data_as(C.c_void_p), len(prns), out)
+        if stream is None:
+            _lib.check(_lib.lib().r4wb_pcps_acquire_batch(*args))
+        else:
+            with _lib.on_stream(stream):          # device input: run on torch's current stream, then back to the default
+                _lib.check(_lib.lib().r4wb_pcps_acquire_batch(*args))
         return out
 
     def acquire_grid(self, input_, code) -> AcquisitionGrid:

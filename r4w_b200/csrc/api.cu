@@ -157,6 +157,13 @@ r4wb_error r4wb_scenario_generate(r4wb_scenario* h, uint64_t first, uint64_t n, 
     return guard_on(h, [&] { h->impl.generate(first, n, dst, where, fmt); });
 }
 
+r4wb_error r4wb_scenario_generate_rest(r4wb_scenario* h, void* dst, uint64_t cap, r4wb_mem where, r4wb_fmt fmt, uint64_t* written)
+{
+    if (!h || !written) { t_error = "handle/written is NULL"; return R4WB_ERR_NULL_POINTER; }
+    *written = 0;
+    return guard_on(h, [&] { *written = h->impl.generate_rest(dst, cap, where, fmt); });
+}
+
 r4wb_error r4wb_scenario_write_file(r4wb_scenario* h, const char* path, r4wb_fmt fmt, uint64_t* samples, uint64_t* bytes,
                                     double* power_sum)
 {

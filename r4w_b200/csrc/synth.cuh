@@ -243,6 +243,8 @@ public:
     void generate(uint64_t first, uint64_t n, void* dst, r4wb_mem where, r4wb_fmt fmt);
     // one reference block of min(n, remaining) samples at current_sample
     uint64_t generate_block(uint64_t n, void* dst, r4wb_mem where, r4wb_fmt fmt);
+    // GnssScenario::generate (scenario.rs:549-561): [current_sample, total) and done
+    uint64_t generate_rest(void* dst, uint64_t cap, r4wb_mem where, r4wb_fmt fmt);
     // the CLI's file sink (main.rs:4483-4509): the whole scenario, in `fmt`, streamed into `path`; returns sum |s|^2
     double write_file(const char* path, r4wb_fmt fmt, uint64_t* samples, uint64_t* bytes);
     double last_power_sum();
@@ -267,6 +269,7 @@ private:
 
     ScenarioModel md_;
     uint64_t current_ = 0;
+    bool seq_canonical_ = true;     // every generate_block so far was a canonical block (start on a multiple of B, B samples)
     SeqState seq_;
 
     // device state
@@ -302,6 +305,14 @@ private:
     cudaStream_t copy_stream_ = nullptr;      // D2H copies of the host-destination pipeline
     cudaEvent_t ev_fork_ = nullptr, ev_join_ = nullptr, ev_render_[2] = {nullptr, nullptr}, ev_copy_[2] = {nullptr, nullptr};
     void ensure_side_stream();
+    // Cached device tables (block table, tile records, period tables, phasors) are produced on whatever stream the call
+    // that built them ran on.  Every public call ends by recording ev_done_ on its stream; a later call on ANOTHER stream
+    // waits for that event first, so it never reads a table whose prologue kernels are still in flight (and never touches
+    // the old stream handle again, which may be gone by then).
+    struct StreamScope;
+    cudaEvent_t ev_done_ = nullptr;
+    cudaStream_t last_stream_ = nullptr;
+    bool has_last_ = false;
 };
 
 }  // namespace r4wb

@@ -66,9 +66,24 @@ Scenario::Scenario(const r4wb_scenario_cfg& cfg) : md_(cfg)
     R4WB_CUDA(cudaStreamSynchronize(st));
 }
 
+struct Scenario::StreamScope {
+    Scenario& s;
+    cudaStream_t st;
+    explicit StreamScope(Scenario& sc) : s(sc), st(current_stream())
+    {
+        if (!s.ev_done_) R4WB_CUDA(cudaEventCreateWithFlags(&s.ev_done_, cudaEventDisableTiming));
+        if (s.has_last_ && s.last_stream_ != st) R4WB_CUDA(cudaStreamWaitEvent(st, s.ev_done_, 0));
+    }
+    ~StreamScope()
+    {
+        if (cudaEventRecord(s.ev_done_, st) == cudaSuccess) { s.last_stream_ = st; s.has_last_ = true; }
+    }
+};
+
 Scenario::~Scenario()
 {
     delete per_;
+    if (ev_done_) cudaEventDestroy(ev_done_);
     for (cudaEvent_t e : {ev_fork_, ev_join_, ev_render_[0], ev_render_[1], ev_copy_[0], ev_copy_[1]})
         if (e) cudaEventDestroy(e);
     if (side_stream_) cudaStreamDestroy(side_stream_);
@@ -122,6 +137,7 @@ void Scenario::ensure_side_stream()
 void Scenario::reset()
 {
     current_ = 0;
+    seq_canonical_ = true;
     seq_.reset(md_.sc.n_sats);
 }
 
@@ -426,6 +442,7 @@ void Scenario::generate(uint64_t first, uint64_t n, void* dst, r4wb_mem where, r
     if ((unsigned)fmt > (unsigned)R4WB_FMT_CU8) fail(R4WB_ERR_INVALID_PARAMETER, "unknown sample format %d", (int)fmt);
     if (n == 0) return;
     if (!dst) fail(R4WB_ERR_NULL_POINTER, "dst is NULL");
+    StreamScope scope(*this);
     render_to(first, n, dst, where, fmt);
 }
 
@@ -438,6 +455,7 @@ uint64_t Scenario::generate_block(uint64_t n_req, void* dst, r4wb_mem where, r4w
     if (!dst) fail(R4WB_ERR_NULL_POINTER, "dst is NULL");
     if (n > 65536) fail(R4WB_ERR_NOT_SUPPORTED, "generate_block: at most 65536 samples per reference block");
     if ((unsigned)fmt > (unsigned)R4WB_FMT_CU8) fail(R4WB_ERR_INVALID_PARAMETER, "unknown sample format %d", (int)fmt);
+    StreamScope scope(*this);
     cudaStream_t st = current_stream();
     std::vector<BlockSat> tab;
     BlockHdr hdr[2];
@@ -456,8 +474,28 @@ uint64_t Scenario::generate_block(uint64_t n_req, void* dst, r4wb_mem where, r4w
     if (where != R4WB_MEM_DEVICE) R4WB_CUDA(cudaMemcpyAsync(dst, d_out, (size_t)n * bps, cudaMemcpyDeviceToHost, st));
     R4WB_CUDA(cudaStreamSynchronize(st));   // `tab`/`hdr` are stack/heap temporaries
     seq_.advance(md_, tab, (uint32_t)n);
+    if (current_ % sc.B != 0 || (n != sc.B && n != remaining)) seq_canonical_ = false;
     current_ += n;
     return n;
+}
+
+uint64_t Scenario::generate_rest(void* dst, uint64_t cap, r4wb_mem where, r4wb_fmt fmt)
+{
+    const ScenConst& sc = md_.sc;
+    const uint64_t remaining = sc.total > current_ ? sc.total - current_ : 0;
+    if (remaining == 0) return 0;
+    if (!dst) fail(R4WB_ERR_NULL_POINTER, "dst is NULL");
+    if (cap < remaining) fail(R4WB_ERR_INVALID_SIZE, "dst holds %llu samples, %llu remain", (unsigned long long)cap, (unsigned long long)remaining);
+    if (seq_canonical_ && current_ % sc.B == 0) {
+        generate(current_, remaining, dst, where, fmt);
+        current_ = sc.total;
+        return remaining;
+    }
+    // odd-sized blocks came before: the reference's partition continues from current_sample in block_size() steps
+    const size_t bps = fmt_bytes(fmt);
+    uint64_t done = 0;
+    while (current_ < sc.total) done += generate_block(sc.B, static_cast<unsigned char*>(dst) + done * bps, where, fmt);
+    return done;
 }
 
 // File sink: segments of ~16 Msamples are rendered into two pinned host buffers (render_to's own double-buffered D2H); a
@@ -485,6 +523,7 @@ double Scenario::write_file(const char* path, r4wb_fmt fmt, uint64_t* samples, u
     const int fd = ::open(path, O_WRONLY | O_CREAT | O_TRUNC, 0644);
     if (fd < 0) fail(R4WB_ERR_INVALID_PARAMETER, "cannot create '%s': %s", path, std::strerror(errno));
     const size_t bps = fmt_bytes(fmt);
+    StreamScope scope(*this);
     uint64_t unit = sc.B;                                                          // segment edges on period boundaries
     if (fmt == R4WB_FMT_CF32 && plan_periodic() && per_->L % sc.B == 0) unit = per_->L;
     const uint64_t seg = std::max<uint64_t>(1, (uint64_t)(16u << 20) / unit) * unit;
@@ -568,6 +607,7 @@ void Scenario::debug_block(uint64_t block, uint32_t sat, double* o)
 {
     const ScenConst& sc = md_.sc;
     if (block >= md_.n_blocks() || sat >= sc.n_sats) fail(R4WB_ERR_INVALID_PARAMETER, "block/sat out of range");
+    StreamScope scope(*this);
     build_canonical_table(md_.table_begin(block), block + 1);
     BlockSat e;
     cudaStream_t st = current_stream();

@@ -113,8 +113,14 @@ class GnssScenario:
         return out[: written.value]
 
     def generate(self, dtype=np.complex64) -> np.ndarray:
-        """generate (scenario.rs:549-561): the whole scenario, `while !is_done {generate_block(block_size())}`."""
-        return self.generate_range(0, self.total_samples(), dtype=dtype)
+        """generate (scenario.rs:549-561): `while !is_done {generate_block(block_size())}` — everything from
+        current_sample to the end, rendered in one call; leaves the scenario done."""
+        fmt = _lib.FMT_CF64 if np.dtype(dtype) == np.complex128 else _lib.FMT_CF32
+        out = np.empty(self.total_samples() - self.current_sample(), np.complex128 if fmt == _lib.FMT_CF64 else np.complex64)
+        written = C.c_uint64(0)
+        _lib.check(_lib.lib().r4wb_scenario_generate_rest(self._h, out.ctypes.data_as(C.c_void_p), out.size, _lib.MEM_HOST, fmt,
+                                                          C.byref(written)))
+        return out[: written.value]
 
     def satellite_status(self) -> List[SatelliteStatus]:
         n = len(self._config.satellites)
@@ -156,8 +162,8 @@ class GnssScenario:
         ptr, cap, fmt = _device_ptr(out)
         if cap < n:
             raise ValueError("output tensor too small")
-        _lib.set_stream(torch.cuda.current_stream(out.device).cuda_stream)
-        _lib.check(_lib.lib().r4wb_scenario_generate(self._h, int(first), int(n), C.c_void_p(ptr), _lib.MEM_DEVICE, fmt))
+        with _lib.on_stream(torch.cuda.current_stream(out.device).cuda_stream):
+            _lib.check(_lib.lib().r4wb_scenario_generate(self._h, int(first), int(n), C.c_void_p(ptr), _lib.MEM_DEVICE, fmt))
 
     def write_file(self, path, fmt: int = _lib.FMT_CF32):
         """The CLI's file sink (main.rs:4483-4509): the whole scenario streamed into `path` in `fmt` -> (samples written,

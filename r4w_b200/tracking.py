@@ -91,6 +91,7 @@ class TrackerBank:
         codes = np.ascontiguousarray(codes, np.int8).reshape(self._n, -1)
         assert codes.shape[1] >= self._code_length
         span = int(n_per_period) * int(n_periods)
+        stream = 0
         if isinstance(samples, np.ndarray):
             fmt = _lib.FMT_CF64 if samples.dtype == np.complex128 else _lib.FMT_CF32
             x = np.ascontiguousarray(samples, np.complex128 if fmt == _lib.FMT_CF64 else np.complex64)
@@ -100,12 +101,13 @@ class TrackerBank:
             import torch
             assert samples.is_cuda and samples.dtype == torch.complex64 and samples.is_contiguous()
             assert samples.numel() >= (span * self._n if per_channel_input else span)
-            _lib.set_stream(torch.cuda.current_stream(samples.device).cuda_stream)
+            stream = torch.cuda.current_stream(samples.device).cuda_stream
             ptr, where, fmt = C.c_void_p(samples.data_ptr()), _lib.MEM_DEVICE, _lib.FMT_CF32
         out = np.zeros((int(n_periods), self._n), TRACK_STATE_DTYPE)
-        _lib.check(_lib.lib().r4wb_track_process(self._h, ptr, fmt, where, int(n_per_period), int(n_periods),
-                                                 span if per_channel_input else 0, codes.ctypes.data_as(C.c_void_p), codes.shape[1],
-                                                 out.ctypes.data_as(C.c_void_p)))
+        with _lib.on_stream(stream):
+            _lib.check(_lib.lib().r4wb_track_process(self._h, ptr, fmt, where, int(n_per_period), int(n_periods),
+                                                     span if per_channel_input else 0, codes.ctypes.data_as(C.c_void_p), codes.shape[1],
+                                                     out.ctypes.data_as(C.c_void_p)))
         return out
 
     def state(self) -> List[TrackingState]:

@@ -202,11 +202,16 @@ impl GnssScenario {
         out
     }
 
-    /// scenario.rs:549: the whole scenario (the CLI loop's concatenation), rendered in one call
+    /// scenario.rs:549: everything from the current position to the end (the CLI loop's concatenation), rendered in one
+    /// call; leaves the scenario done like the reference's `while !self.is_done()` loop
     pub fn generate(&mut self) -> Vec<IQSample> {
-        let n = self.total_samples();
+        let n = self.total_samples() - unsafe { sys::r4wb_scenario_current_sample(self.h) } as usize;
         let mut out = vec![IQSample::new(0.0, 0.0); n];
-        check(unsafe { sys::r4wb_scenario_generate(self.h, 0, n as u64, out.as_mut_ptr().cast(), sys::R4WB_MEM_HOST, sys::R4WB_FMT_CF64) });
+        let mut written = 0u64;
+        check(unsafe {
+            sys::r4wb_scenario_generate_rest(self.h, out.as_mut_ptr().cast(), n as u64, sys::R4WB_MEM_HOST, sys::R4WB_FMT_CF64, &mut written)
+        });
+        out.truncate(written as usize);
         out
     }
 

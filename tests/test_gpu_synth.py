@@ -89,6 +89,53 @@ def test_sequential_api_matches_oracle(gpu, oracle):
     assert full.size == 35500 and _relrms(full, ofull) <= TOL
 
 
+def test_generate_starts_at_current_sample_and_leaves_done(gpu, oracle):
+    """generate (scenario.rs:549-561) = `while !is_done { generate_block(block_size()) }`: the remainder, then done"""
+    cfg = _cfg("e1c_8prn_60s_cn34_orbital")
+    cfg.output.duration_s = 0.0123
+    sc, orc = gpu.GnssScenario(cfg, noise=False), oracle.OracleScenario(cfg, noise=False)
+    sc.generate_block(5000); sc.generate_block(5000)
+    for _ in range(2):
+        orc.generate_block(5000)
+    rest = sc.generate()
+    want = np.concatenate([orc.generate_block(5000) for _ in range(11)])
+    assert rest.size == want.size == 61500 - 10000 and _relrms(rest, want) <= TOL
+    assert sc.is_done() and sc.progress() == 1.0 and sc.generate().size == 0
+    # after an odd-sized block the reference's partition continues from current_sample, not from a multiple of 5000
+    sc.reset(); orc.reset()
+    a, b = sc.generate_block(1234), orc.generate_block(1234)
+    assert _relrms(a, b) <= TOL
+    rest = sc.generate()
+    parts = []
+    while not orc.is_done():
+        parts.append(orc.generate_block(5000))
+    want = np.concatenate(parts)
+    assert rest.size == want.size and _relrms(rest, want) <= TOL and sc.is_done()
+
+
+def test_streams_are_restored_and_ordered(gpu):
+    """device-tensor calls run on torch's current stream and leave the library on the default stream; a table built on one
+    stream is safe to use from another (stale thread-local stream, unsynchronised table reuse)"""
+    import torch
+    cfg = _cfg("e1c_8prn_60s_cn34_orbital")
+    sc = gpu.GnssScenario(cfg, noise=True)
+    n = 400_000
+    a = torch.empty(n, dtype=torch.complex64, device="cuda")
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        sc.generate_device(1_000_000, n, a)             # builds the block table on the side stream
+    side.synchronize()
+    del side
+    b = sc.generate_range(1_000_000, n)                 # host path: default stream, table reused
+    assert np.array_equal(a.cpu().numpy(), b)
+    other = torch.cuda.Stream()
+    c = torch.empty(n, dtype=torch.complex64, device="cuda")
+    with torch.cuda.stream(other):
+        sc.generate_device(3_000_000, n, c)             # extends the table on another stream
+    other.synchronize()
+    assert np.array_equal(c.cpu().numpy(), sc.generate_range(3_000_000, n))
+
+
 def test_random_access_is_consistent(gpu):
     """any window reproduces the same samples bit for bit (what time-sharding across GPUs relies on), noise included"""
     cfg = _cfg("e1c_8prn_60s_cn34_orbital")
