@@ -24,7 +24,7 @@ def test_reference_arm_prints_one_json_line():
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["metric"] == "gnss_iq_synth_msamples_per_s" and d["unit"] == "Msamples/s"
     assert d["higher_is_better"] is True and d["n_gpus"] == 1 and d["steps"] == 1 and d["warmup"] == 0 and d["value"] > 0
-    assert "workload" in d["config"] and "e1c_8prn_20s_clean.yaml" in d["config"]["workload"]
+    assert "workload" in d["config"] and "e1c_8prn_600s_cn34_orbital.yaml" in d["config"]["workload"] and d["scaling"] == "strong"
     cb = d["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}

@@ -409,10 +409,10 @@ def test_presets_match_oracle(gpu, oracle, name):
     cfg = gpu.preset_config(name)
     n = cfg.total_samples()
     sc = gpu.GnssScenario(cfg, noise=False)
+    st, ost = sc.satellite_status(), oracle.OracleScenario(cfg).status()      # at current_sample = 0 (generate() leaves the scenario done)
     got = sc.generate()
     want = oracle.OracleScenario(cfg, noise=False).generate_range(0, n)
-    assert got.size == n and _relrms(got, want) <= TOL
-    st, ost = sc.satellite_status(), oracle.OracleScenario(cfg).status()
+    assert got.size == n and _relrms(got, want) <= TOL and sc.is_done()
     assert [s.prn for s in st] == [s.prn for s in ost] and [s.visible for s in st] == [bool(s.visible) for s in ost]
     for a, b in zip(st, ost):
         assert a.cn0_dbhz == pytest.approx(b.cn0_dbhz, abs=1e-6) and a.range_m == pytest.approx(b.range_m, rel=1e-12)
