@@ -226,7 +226,8 @@ r4wb_error r4wb_scenario_last_power_sum(const r4wb_scenario* h, double* power_su
 uint32_t r4wb_scenario_last_path(const r4wb_scenario* h);
 /* Optional device-side timing of the last generate call (measurement aid, no reference counterpart): when enabled, CUDA
  * events bracket every synthesis-kernel launch on its stream.  ms[3] / launches[3] are the summed durations and launch
- * counts of {k_synth, k_synth_periodic, k_periodic_fix}; last_profile waits for the events. */
+ * counts of {k_synth, k_synth_periodic, k_periodic_fix, k_synth_lat} (ms / launches: 4 entries each); last_profile waits
+ * for the events. */
 r4wb_error r4wb_scenario_set_profiling(r4wb_scenario* h, int enabled);
 r4wb_error r4wb_scenario_last_profile(r4wb_scenario* h, double* ms, uint64_t* launches);
 /* GnssScenario::satellite_status, gnss/scenario.rs:564-633 */

@@ -21,6 +21,7 @@ constexpr int kMaxYStride = 241;      // boundary-age classes per sign pattern: 
 constexpr int kPerBits = 2 * kCodeLen;   // half-chips of one Galileo E1 primary-code period (the longest supported)
 constexpr int kPerWords = 260;        // 8184 sign bits + 64 wrap-around bits, padded to a multiple of 4 words
 constexpr int kSynthThreads = 256;
+constexpr int kLatYStride = 33;       // row stride (words) of the lattice kernel's [class][pattern] table
 constexpr int kDirectWords = 320;     // packed chips of a "direct" satellite's primary code (GPS L5: 10 230 chips)
 
 // One piece of the reference's sequential f64 `phase += phase_inc` (gnss/scenario.rs:518-527) for a
@@ -132,12 +133,40 @@ struct TileSat {
     float wr, wi;       // e^{j phase advance over 2*kSynthThreads samples}, at the tile's first sample
     float th1, th2;     // radians: growth of that advance per sample index, and per step of 2*kSynthThreads samples
 };
-// one record per (table block, chunk, satellite): 96 bytes = 6 x 16
+// what the lattice kernel (k_synth_lat, synth_lattice.cuh) needs on top of TileSat, per (block, satellite)
+struct TileLat {
+    float r1r, r1i;     // e^{j 2 pi f}: rotation from sample i to i + 1 at the block start (f64-evaluated)
+    float rqr, rqi;     // e^{j 2 pi (q f + df q (q + 1) / 2)}: rotation from sample i to i + q at the block start
+    uint32_t patch;     // flagged blocks (TileSat.flags bit1): bits 0-15 = oversample index q* < D of the first of the two oversamples
+                        // of the block (q*, q* + D) that lie inside the f64 rounding band of a half-chip boundary; bits 16-17 / 18-19:
+                        // their codes, 0 = the reference's own f64 expression agrees with the lattice model, 1 = add +2 h[g - q*],
+                        // 2 = add -2 h[g - q*] to the windows that hold it
+    uint32_t ep0;       // origin of the block's sign table (half-chip hb) inside the satellite's code cycle: bits 0-7 primary-code
+                        // epoch, bits 8-31 half-chip inside the period (so the kernel builds sign words without a division)
+    uint32_t latb;      // bits 0-15: bin b = floor(frac(U) D) of the block's first sample, bits 16-31: sample offset `moff` of the
+                        // class table (class of sample m = clsn[b & 7][m + moff])
+    uint32_t fc32;      // (b + 1/2) / D as a 0.32 fraction: the bin-centred half-chip fraction of the block's first sample
+};
+// one record per (table block, chunk, satellite): 128 bytes = 8 x 16
 struct TileRec {
     TileSat ts;
     float yfix[8];      // first 8 FIR outputs of the block when its delay differs from its predecessor's (chunk 0, flags bit3)
+    TileLat lat;
 };
-static_assert(sizeof(TileSat) == 64 && sizeof(TileRec) == 96, "TileRec layout");
+static_assert(sizeof(TileSat) == 64 && sizeof(TileLat) == 32 && sizeof(TileRec) == 128, "TileRec layout");
+
+// constants of the sample lattice (ScenarioModel fills them when the lattice kernel applies, q = 0 otherwise): the
+// half-chip position advances by p / q half-chips per output sample (lowest terms), a block holds exactly 2 q samples,
+// half-chip fractions of oversamples lie on offset + k / D with D = 8 q
+struct LatConst {
+    uint32_t q, p;          // 2500, 1023 at 5 MHz
+    uint32_t pinv;          // p^-1 mod q
+    uint32_t pov;           // oversample step in units of 1 / D half-chips (2 ratB D / ratA; 1023 at 5 MHz)
+    uint32_t povinv;        // pov^-1 mod D
+    uint32_t K;             // quad steps per thread: ceil(q / (2 kSynthThreads))
+    uint32_t cls_len;       // entries per sub-residue table: q + 2 kSynthThreads K + 2
+    uint32_t d8_20, step20; // half-chips per sample / per 2 kSynthThreads samples, 2^-20 units (rounded)
+};
 
 struct SynthArgs {
     const BlockSat* tab;       // [n_tab_blocks][n_sats]
@@ -164,6 +193,12 @@ struct SynthArgs {
     uint32_t any_direct;       // some satellite is rendered by k_synth_direct
     uint32_t max_block_n;      // longest block of the table (grid of k_synth_direct)
     uint32_t out_aligned16;    // out is aligned to two samples of the output format: sample pairs may be stored as one vector
+    LatConst lat;              // lattice kernel constants (lat.q = 0: not applicable)
+    const uint8_t* clsn;       // [8][lat.cls_len] boundary-age class of sample index n per sub-residue b0 (synth_lattice.cuh)
+    const float* ytab2;        // [ystride][33] collapsed-FIR outputs, row = class, column = sign pattern; the odd row stride makes the
+                               // bank (class + pattern) mod 32: a warp's classes differ, so equal patterns no longer share a bank
+    uint32_t* stats;           // [2] written by k_tile_params: [0] = records that need per-sample sincos or a varying step phasor
+                               // beyond the lattice kernel's model (it then leaves the launch to k_synth)
     uint64_t delta46;
     uint32_t kmul;
     uint32_t cj[8];
@@ -194,6 +229,9 @@ struct ScenarioModel {
     float etab_f[64];
     std::vector<float> ytab;            // [32][sc.ystride]
     std::vector<uint8_t> clslut;        // [lut_den padded to 16]
+    LatConst lat{};                     // lattice kernel constants (q = 0: the scenario does not qualify)
+    std::vector<uint8_t> clsn;          // [8][lat.cls_len]
+    std::vector<float> ytab2;           // [sc.ystride][kLatYStride]
     int tile_k = 10;                    // samples per tile = 256 threads * 2 * tile_k
     uint32_t nw64 = 0;
     bool any_dynamic = false, any_var_visibility = false;
@@ -250,7 +288,7 @@ public:
     double last_power_sum();
     uint32_t last_path() const { return last_path_; }
     void set_profiling(bool on) { profiling_ = on; }
-    void last_profile(double* ms3, uint64_t* launches3);   // of the last generate call: {k_synth, k_synth_periodic, k_periodic_fix}
+    void last_profile(double* ms3, uint64_t* launches3);   // of the last generate call: {k_synth, k_synth_periodic, k_periodic_fix, k_synth_lat} (4 entries)
     void status(r4wb_sat_status* out, uint32_t cap, uint32_t* n) const { md_.status(current_, out, cap, n); }
     // test hook: entry of canonical block `block`, satellite `sat` -> 12 doubles
     void debug_block(uint64_t block, uint32_t sat, double* out12);
@@ -280,7 +318,11 @@ private:
     DevBuf<DirectSat> d_dsat_;
     DevBuf<uint32_t> d_dcode_;
     DevBuf<float> d_taps_, d_etab_, d_ytab_;
-    DevBuf<uint8_t> d_clslut_;
+    DevBuf<uint8_t> d_clslut_, d_clsn_;
+    DevBuf<float> d_ytab2_;
+    DevBuf<uint32_t> d_stats_;
+    uint32_t tab_lat_bad_ = 0;              // records of the canonical table the lattice kernel cannot render
+    bool phase_parallel_ = true;            // the last exact-phase pass ran the parallel kernels (false: serial fallback)
     DevBuf<BlockSat> d_tab_, d_seq_tab_;
     DevBuf<BlockHdr> d_hdr_, d_seq_hdr_;
     DevBuf<TileRec> d_tiles_, d_seq_tiles_;
@@ -305,6 +347,20 @@ private:
     cudaStream_t copy_stream_ = nullptr;      // D2H copies of the host-destination pipeline
     cudaEvent_t ev_fork_ = nullptr, ev_join_ = nullptr, ev_render_[2] = {nullptr, nullptr}, ev_copy_[2] = {nullptr, nullptr};
     void ensure_side_stream();
+    // ---- render-ahead ring of the sequential API (generate_block with the canonical block size, host destination): whole
+    // chunks of canonical blocks are rendered from the cached canonical table and copied into a pinned host ring ahead of the
+    // caller, so one generate_block call is a host memcpy (crates/r4w-cli/src/main.rs:4488-4500 is this loop)
+    struct BlockRing;
+    BlockRing* ring_ = nullptr;
+    uint64_t seq_pos_ = 0;                    // sample position the host-side SeqState corresponds to
+    uint64_t ring_block(uint64_t n, void* dst, r4wb_fmt fmt);
+    void ring_schedule(uint64_t chunk);
+    void ring_drop();
+    void seq_sync();                          // replay SeqState up to current_ (after ring-served blocks)
+    const void* last_block_ = nullptr;        // last ring-served block (lazy power sum)
+    uint64_t last_block_n_ = 0;
+    r4wb_fmt last_block_fmt_ = R4WB_FMT_CF32;
+
     // Cached device tables (block table, tile records, period tables, phasors) are produced on whatever stream the call
     // that built them ran on.  Every public call ends by recording ev_done_ on its stream; a later call on ANOTHER stream
     // waits for that event first, so it never reads a table whose prologue kernels are still in flight (and never touches

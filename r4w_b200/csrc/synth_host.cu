@@ -21,9 +21,13 @@ void launch_synth_kernel(const SynthArgs& a, int K, r4wb_fmt fmt, int grid, cuda
 int synth_max_blocks_per_sm(int K, r4wb_fmt fmt, size_t smem);
 void launch_synth_direct(const SynthArgs& a, r4wb_fmt fmt, cudaStream_t st);
 void launch_block_params(const ScenConst&, const SatConst*, const PhaseSegment*, uint64_t, uint32_t, BlockSat*, BlockHdr*, double*, double*, cudaStream_t);
-void launch_phase_exact(const ScenConst&, const SatConst*, uint32_t, BlockSat*, const double*, const double*, double*, PhaseQ*, cudaStream_t);
+bool launch_phase_exact(const ScenConst&, const SatConst*, uint32_t, BlockSat*, const double*, const double*, unsigned char* scratch, cudaStream_t);
+size_t phase_exact_scratch_bytes(uint32_t n_sats, uint32_t nblk, uint32_t B);
 void launch_phase_scan(const SatConst*, uint32_t, uint32_t, BlockSat*, cudaStream_t);
 void launch_tile_params(const SynthArgs& a, uint32_t tb_begin, uint32_t tb_count, uint32_t tile_samples, TileRec* out, cudaStream_t st);
+// lattice kernel (synth_lattice.cu)
+bool lat_supported(const SynthArgs& a);
+void launch_synth_lat(const SynthArgs& a, r4wb_fmt fmt, int sm_count, cudaStream_t st);
 // launchers (synth_periodic.cu)
 void launch_static_check(const BlockSat*, const SatConst*, uint32_t nblk, uint32_t n_sats, uint64_t B, uint32_t* bad, cudaStream_t);
 void launch_period_tables(const PeriodTableArgs&, uint32_t ns_padded, cudaStream_t);
@@ -46,6 +50,28 @@ struct Scenario::PeriodicState {
     DevBuf<float4> T;
 };
 
+// ---- render-ahead ring -------------------------------------------------------------------------------------------------
+struct Scenario::BlockRing {
+    static constexpr uint32_t kSlots = 4;           // pinned chunks
+    uint32_t C = 0;                                 // canonical blocks per chunk
+    r4wb_fmt fmt = R4WB_FMT_CF32;
+    size_t chunk_bytes = 0;
+    unsigned char* pin = nullptr;                   // kSlots * chunk_bytes, pinned
+    DevBuf<unsigned char> stage[2];
+    cudaEvent_t ev_done[kSlots] = {};               // chunk in slot is in host memory
+    cudaEvent_t ev_render[2] = {};
+    uint64_t chunk_of_slot[kSlots];
+    uint64_t synced_chunk = ~0ull;                  // chunk whose event the host has already waited for
+    uint64_t next_chunk = 0;                        // next chunk to schedule
+    uint64_t n_chunks = 0;
+    ~BlockRing()
+    {
+        for (cudaEvent_t e : ev_done) if (e) cudaEventDestroy(e);
+        for (cudaEvent_t e : ev_render) if (e) cudaEventDestroy(e);
+        if (pin) cudaFreeHost(pin);
+    }
+};
+
 Scenario::Scenario(const r4wb_scenario_cfg& cfg) : md_(cfg)
 {
     seq_.reset(md_.sc.n_sats);
@@ -61,6 +87,10 @@ Scenario::Scenario(const r4wb_scenario_cfg& cfg) : md_(cfg)
     R4WB_CUDA(cudaMemcpyAsync(d_taps_.reserve(64), md_.taps_f, sizeof md_.taps_f, cudaMemcpyHostToDevice, st));
     R4WB_CUDA(cudaMemcpyAsync(d_etab_.reserve(64), md_.etab_f, sizeof md_.etab_f, cudaMemcpyHostToDevice, st));
     R4WB_CUDA(cudaMemcpyAsync(d_clslut_.reserve(md_.clslut.size()), md_.clslut.data(), md_.clslut.size(), cudaMemcpyHostToDevice, st));
+    R4WB_CUDA(cudaMemcpyAsync(d_clsn_.reserve(md_.clsn.size()), md_.clsn.data(), md_.clsn.size(), cudaMemcpyHostToDevice, st));
+    R4WB_CUDA(cudaMemcpyAsync(d_ytab2_.reserve(md_.ytab2.size()), md_.ytab2.data(), md_.ytab2.size() * 4, cudaMemcpyHostToDevice, st));
+    d_stats_.reserve(2);
+    R4WB_CUDA(cudaMemsetAsync(d_stats_.p, 0, 2 * sizeof(uint32_t), st));
     d_power_.reserve(1);
     R4WB_CUDA(cudaMemsetAsync(d_power_.p, 0, sizeof(double), st));
     R4WB_CUDA(cudaStreamSynchronize(st));
@@ -82,6 +112,7 @@ struct Scenario::StreamScope {
 
 Scenario::~Scenario()
 {
+    ring_drop();
     delete per_;
     if (ev_done_) cudaEventDestroy(ev_done_);
     for (cudaEvent_t e : {ev_fork_, ev_join_, ev_render_[0], ev_render_[1], ev_copy_[0], ev_copy_[1]})
@@ -113,7 +144,7 @@ void Scenario::prof_end(cudaStream_t st)
 
 void Scenario::last_profile(double* ms3, uint64_t* launches3)
 {
-    for (int k = 0; k < 3; ++k) { ms3[k] = 0.0; launches3[k] = 0; }
+    for (int k = 0; k < 4; ++k) { ms3[k] = 0.0; launches3[k] = 0; }
     for (const Timed& t : timed_) {
         R4WB_CUDA(cudaEventSynchronize(t.b));
         float ms = 0.0f;
@@ -139,6 +170,9 @@ void Scenario::reset()
     current_ = 0;
     seq_canonical_ = true;
     seq_.reset(md_.sc.n_sats);
+    seq_pos_ = 0;
+    last_block_ = nullptr;
+    if (ring_) { ring_->synced_chunk = ~0ull; }      // chunks stay valid (same samples); the ring repositions on the next call
 }
 
 // Prologue: Phase-1 parameters + NCO start values of canonical blocks [blk_begin, blk_end) into d_tab_.
@@ -158,11 +192,12 @@ void Scenario::build_canonical_table(uint64_t blk_begin, uint64_t blk_end)
     // dynamic satellites: the reference's sequentially accumulated f64 carrier phase, reproduced exactly (synth_math.cuh:
     // block_phase_q / phase_after_block) unless the caller asked for the closed form; needs the table to start at block 0
     const bool exact_phase = md_.any_dynamic && !(sc.flags & R4WB_FLAG_CLOSED_FORM_PHASE) && blk_begin == 0 && sc.n_sats > 0;
-    DevBuf<double> dop, papprox, pstart;            // scratch of this build only
-    DevBuf<PhaseQ> pq;
+    DevBuf<double> dop, papprox;                    // scratch of this build only
+    DevBuf<unsigned char> pscratch;
     if (exact_phase) {
         const size_t ne = (size_t)nblk * sc.n_sats;
-        dop.reserve(2 * ne); papprox.reserve(ne); pstart.reserve(ne); pq.reserve(ne);
+        dop.reserve(2 * ne); papprox.reserve(ne);
+        pscratch.reserve(phase_exact_scratch_bytes(sc.n_sats, (uint32_t)nblk, (uint32_t)sc.B));
     }
     launch_block_params(sc, d_sat_.p, d_segments_.p, blk_begin, (uint32_t)nblk, d_tab_.p, d_hdr_.p, dop.p, papprox.p, st);
     if (sc.n_sats == 0) {   // headers still needed
@@ -176,17 +211,27 @@ void Scenario::build_canonical_table(uint64_t blk_begin, uint64_t blk_end)
     }
     if (md_.any_dynamic || md_.any_var_visibility) launch_phase_scan(d_sat_.p, sc.n_sats, (uint32_t)nblk, d_tab_.p, st);
     if (exact_phase) {
-        launch_phase_exact(sc, d_sat_.p, (uint32_t)nblk, d_tab_.p, dop.p, papprox.p, pstart.p, pq.p, st);
+        phase_parallel_ = launch_phase_exact(sc, d_sat_.p, (uint32_t)nblk, d_tab_.p, dop.p, papprox.p, pscratch.p, st);
         R4WB_CUDA(cudaStreamSynchronize(st));       // the scratch buffers are freed on return
     }
     tab_blk0_ = blk_begin;
     tab_blk1_ = blk_end;
     tab_valid_ = true;
-    // per-tile records for the canonical tiling (block size B)
+    // per-tile records for the canonical tiling (block size B); k_tile_params counts the records whose carrier model the
+    // lattice kernel cannot follow (large Doppler rate), read back once per table
     {
         SynthArgs a = base_args(d_tab_.p, d_hdr_.p, sc.B);
         d_tiles_.reserve(std::max<size_t>(1, (size_t)nblk * a.tiles_per_block * sc.n_sats));
+        tab_lat_bad_ = 0;
+        if (md_.lat.q != 0) {
+            a.stats = d_stats_.p;
+            R4WB_CUDA(cudaMemsetAsync(d_stats_.p, 0, 2 * sizeof(uint32_t), st));
+        }
         build_tiles(a, 0, (uint32_t)nblk, d_tiles_.p);
+        if (md_.lat.q != 0) {
+            R4WB_CUDA(cudaMemcpyAsync(&tab_lat_bad_, d_stats_.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+            R4WB_CUDA(cudaStreamSynchronize(st));
+        }
     }
 }
 
@@ -196,6 +241,7 @@ SynthArgs Scenario::base_args(const BlockSat* tab, const BlockHdr* hdr, uint64_t
     SynthArgs a{};
     a.tab = tab; a.hdr = hdr; a.perbits = d_perbits_.p; a.satcode = d_satcode_.p; a.taps = d_taps_.p; a.etab = d_etab_.p; a.ytab = d_ytab_.p; a.clslut = d_clslut_.p; a.lut_den = sc.lut_den; a.ystride = sc.ystride;
     a.dsat = d_dsat_.p; a.dcode = d_dcode_.p; a.any_direct = md_.any_direct ? 1u : 0u; a.max_block_n = (uint32_t)max_block_n;
+    a.lat = md_.lat; a.clsn = d_clsn_.p; a.ytab2 = d_ytab2_.p; a.stats = nullptr;
     const uint32_t tile = (uint32_t)synth_tile_samples(md_.tile_k);
     a.tiles_per_block = (uint32_t)((max_block_n + tile - 1) / tile);
     a.n_sats = sc.n_sats; a.nw64 = md_.nw64; a.flags = sc.flags;
@@ -215,6 +261,7 @@ void Scenario::launch_synth(const BlockSat* tab, const BlockHdr* hdr, const Tile
                             uint64_t out_first, uint64_t out_n, void* d_out, r4wb_fmt fmt, uint64_t max_block_n, cudaStream_t st)
 {
     SynthArgs a = base_args(tab, hdr, max_block_n);
+    const uint32_t tb_begin_all = tb_begin, tb_count_all = tb_count;
     a.tiles = tiles;
     a.out = d_out; a.power_sum = d_power_.p;
     a.out_first = out_first; a.out_n = out_n;
@@ -226,6 +273,29 @@ void Scenario::launch_synth(const BlockSat* tab, const BlockHdr* hdr, const Tile
         int dev = 0;
         R4WB_CUDA(cudaGetDevice(&dev));
         R4WB_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+    }
+    // Lattice kernel for the run of full canonical blocks; a partial last block of the scenario (or a caller-sized block of
+    // the sequential API) keeps k_synth.  Both write disjoint samples of the same output.
+    if (tiles == d_tiles_.p && max_block_n == md_.sc.B && tab_lat_bad_ == 0 && lat_supported(a)) {
+        const uint64_t nb_total = md_.n_blocks();
+        const bool last_partial = md_.sc.total % md_.sc.B != 0;
+        const uint64_t abs_last = tab_blk0_ + tb_begin + tb_count - 1;
+        uint32_t n_full = tb_count;
+        if (last_partial && abs_last == nb_total - 1) n_full -= 1;
+        if (n_full > 0) {
+            SynthArgs f = a;
+            f.tb_count = n_full;
+            prof_begin(3, st);
+            launch_synth_lat(f, fmt, sm_count, st);
+            prof_end(st);
+        }
+        if (n_full == tb_count) {
+            if (md_.any_direct) launch_synth_direct(a, fmt, st);
+            return;
+        }
+        a.tb_begin = tb_begin + n_full;
+        a.tb_count = tb_count - n_full;
+        tb_count = a.tb_count;
     }
     const int tile_k = md_.tile_k;
     const size_t smem = synth_smem_bytes(a.n_sats, a.nw64, a.lut_den, a.ystride);
@@ -242,7 +312,11 @@ void Scenario::launch_synth(const BlockSat* tab, const BlockHdr* hdr, const Tile
     prof_begin(0, st);
     launch_synth_kernel(a, tile_k, fmt, grid, st);
     prof_end(st);
-    if (md_.any_direct) launch_synth_direct(a, fmt, st);      // GPS L5 / GLONASS: added to what k_synth wrote
+    if (md_.any_direct) {                                     // GPS L5 / GLONASS: added to what the kernels above wrote
+        SynthArgs d = a;
+        d.tb_begin = tb_begin_all; d.tb_count = tb_count_all;
+        launch_synth_direct(d, fmt, st);
+    }
 }
 
 static bool periodic_enabled()
@@ -446,6 +520,96 @@ void Scenario::generate(uint64_t first, uint64_t n, void* dst, r4wb_mem where, r
     render_to(first, n, dst, where, fmt);
 }
 
+void Scenario::ring_drop()
+{
+    if (!ring_) return;
+    cudaStreamSynchronize(current_stream());
+    if (copy_stream_) cudaStreamSynchronize(copy_stream_);
+    delete ring_;
+    ring_ = nullptr;
+    last_block_ = nullptr;
+}
+
+// chunk j = canonical blocks [j C, (j + 1) C) -> device staging buffer j & 1 -> pinned slot j % kSlots
+void Scenario::ring_schedule(uint64_t j)
+{
+    BlockRing& R = *ring_;
+    const ScenConst& sc = md_.sc;
+    cudaStream_t st = current_stream();
+    const uint32_t slot = (uint32_t)(j % BlockRing::kSlots), sb = (uint32_t)(j & 1u);
+    const uint64_t first = j * R.C * sc.B, end = std::min<uint64_t>(sc.total, (j + 1) * R.C * sc.B);
+    // the staging buffer's previous copy (chunk j - 2, slot (j - 2) % kSlots) must have left the device
+    if (j >= 2) R4WB_CUDA(cudaStreamWaitEvent(st, R.ev_done[(j - 2) % BlockRing::kSlots], 0));
+    render_device(first, end - first, R.stage[sb].p, R.fmt);
+    R4WB_CUDA(cudaEventRecord(R.ev_render[sb], st));
+    R4WB_CUDA(cudaStreamWaitEvent(copy_stream_, R.ev_render[sb], 0));
+    R4WB_CUDA(cudaMemcpyAsync(R.pin + (size_t)slot * R.chunk_bytes, R.stage[sb].p, (size_t)(end - first) * fmt_bytes(R.fmt), cudaMemcpyDeviceToHost, copy_stream_));
+    R4WB_CUDA(cudaEventRecord(R.ev_done[slot], copy_stream_));
+    R.chunk_of_slot[slot] = j;
+}
+
+uint64_t Scenario::ring_block(uint64_t n, void* dst, r4wb_fmt fmt)
+{
+    const ScenConst& sc = md_.sc;
+    const size_t bps = fmt_bytes(fmt);
+    if (ring_ && ring_->fmt != fmt) ring_drop();
+    if (!ring_) {
+        StreamScope scope(*this);
+        ensure_side_stream();
+        build_canonical_table(0, md_.n_blocks());
+        ring_ = new BlockRing;
+        BlockRing& R = *ring_;
+        R.fmt = fmt;
+        R.C = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(md_.n_blocks(), (uint64_t)(1u << 20) / sc.B));   // ~1 Msample per chunk
+        R.chunk_bytes = (size_t)R.C * sc.B * bps;
+        R.n_chunks = (md_.n_blocks() + R.C - 1) / R.C;
+        R4WB_CUDA(cudaMallocHost((void**)&R.pin, R.chunk_bytes * BlockRing::kSlots));
+        for (auto& b : R.stage) b.reserve(R.chunk_bytes);
+        for (auto& e : R.ev_done) R4WB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        for (auto& e : R.ev_render) R4WB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        for (auto& c : R.chunk_of_slot) c = ~0ull;
+        R.next_chunk = (current_ / sc.B) / R.C;
+    }
+    BlockRing& R = *ring_;
+    const uint64_t blk = current_ / sc.B, c = blk / R.C;
+    const uint32_t slot = (uint32_t)(c % BlockRing::kSlots);
+    if (R.synced_chunk != c) {
+        // keep kSlots - 1 chunks in flight ahead of the one being consumed (the slot of chunk c - 1 is free by now)
+        if (R.chunk_of_slot[slot] != c && (R.next_chunk > c + BlockRing::kSlots - 1 || R.next_chunk < c)) R.next_chunk = c;   // repositioned
+        StreamScope scope(*this);
+        while (R.next_chunk < R.n_chunks && R.next_chunk < c + BlockRing::kSlots - 1) ring_schedule(R.next_chunk++);
+        if (R.chunk_of_slot[slot] != c) fail(R4WB_ERR_CUDA, "block ring lost chunk %llu", (unsigned long long)c);
+        R4WB_CUDA(cudaEventSynchronize(R.ev_done[slot]));
+        R.synced_chunk = c;
+    }
+    const unsigned char* src = R.pin + (size_t)slot * R.chunk_bytes + (size_t)(blk - c * R.C) * sc.B * bps;
+    std::memcpy(dst, src, (size_t)n * bps);
+    last_block_ = src; last_block_n_ = n; last_block_fmt_ = fmt;
+    current_ += n;
+    return n;
+}
+
+// The host-side SeqState lags behind while the ring serves canonical blocks; an odd-sized block afterwards continues the
+// reference's own partition, so the state is replayed block by block up to current_ (host f64 walk: ~0.3 ms per block)
+void Scenario::seq_sync()
+{
+    const ScenConst& sc = md_.sc;
+    std::vector<BlockSat> tab;
+    BlockHdr hdr[2];
+    while (seq_pos_ < current_) {
+        const uint32_t n = (uint32_t)std::min<uint64_t>(sc.B, current_ - seq_pos_);
+        seq_.make_table(md_, seq_pos_, n, tab, hdr);
+        seq_.advance(md_, tab, n);
+        seq_pos_ += n;
+    }
+}
+
+static bool ring_enabled()
+{
+    const char* e = std::getenv("R4WB_BLOCK_RING");          // A/B hook: 0 renders every block on demand
+    return !(e && e[0] == '0');
+}
+
 uint64_t Scenario::generate_block(uint64_t n_req, void* dst, r4wb_mem where, r4wb_fmt fmt)
 {
     const ScenConst& sc = md_.sc;
@@ -453,8 +617,13 @@ uint64_t Scenario::generate_block(uint64_t n_req, void* dst, r4wb_mem where, r4w
     const uint64_t n = std::min(remaining, n_req);
     if (n == 0) return 0;
     if (!dst) fail(R4WB_ERR_NULL_POINTER, "dst is NULL");
-    if (n > 65536) fail(R4WB_ERR_NOT_SUPPORTED, "generate_block: at most 65536 samples per reference block");
+    if (n > (1ull << 24)) fail(R4WB_ERR_NOT_SUPPORTED, "generate_block: at most 2^24 samples per reference block");
     if ((unsigned)fmt > (unsigned)R4WB_FMT_CU8) fail(R4WB_ERR_INVALID_PARAMETER, "unknown sample format %d", (int)fmt);
+    // the CLI loop (canonical block size, host destination): served from the render-ahead ring
+    if (where == R4WB_MEM_HOST && seq_canonical_ && current_ % sc.B == 0 && (n == sc.B || n == remaining) && n <= sc.B && ring_enabled())
+        return ring_block(n, dst, fmt);
+    ring_drop();
+    seq_sync();
     StreamScope scope(*this);
     cudaStream_t st = current_stream();
     std::vector<BlockSat> tab;
@@ -476,6 +645,8 @@ uint64_t Scenario::generate_block(uint64_t n_req, void* dst, r4wb_mem where, r4w
     seq_.advance(md_, tab, (uint32_t)n);
     if (current_ % sc.B != 0 || (n != sc.B && n != remaining)) seq_canonical_ = false;
     current_ += n;
+    seq_pos_ = current_;
+    last_block_ = nullptr;
     return n;
 }
 
@@ -596,6 +767,17 @@ double Scenario::write_file(const char* path, r4wb_fmt fmt, uint64_t* samples, u
 
 double Scenario::last_power_sum()
 {
+    if (last_block_) {                                   // ring-served block: sum |s|^2 of the samples handed out (float formats)
+        double acc = 0.0;
+        if (last_block_fmt_ == R4WB_FMT_CF32) {
+            const float* p = static_cast<const float*>(last_block_);
+            for (uint64_t i = 0; i < 2 * last_block_n_; ++i) acc += (double)p[i] * (double)p[i];
+        } else if (last_block_fmt_ == R4WB_FMT_CF64) {
+            const double* p = static_cast<const double*>(last_block_);
+            for (uint64_t i = 0; i < 2 * last_block_n_; ++i) acc += p[i] * p[i];
+        } else fail(R4WB_ERR_NOT_SUPPORTED, "power sum of a ring-served block is kept for the float formats only");
+        return acc;
+    }
     double v = 0.0;
     cudaStream_t st = current_stream();
     R4WB_CUDA(cudaMemcpyAsync(&v, d_power_.p, sizeof(double), cudaMemcpyDeviceToHost, st));

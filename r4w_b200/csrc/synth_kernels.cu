@@ -14,7 +14,7 @@
 // reference's own f64 expression the kernel evaluates that expression literally (exact path).
 #include <cuda_runtime.h>
 
-#include "synth_math.cuh"
+#include "synth_lattice.cuh"
 
 namespace r4wb {
 
@@ -43,6 +43,11 @@ __global__ void k_tile_params(SynthArgs a, uint32_t tb_begin, uint32_t tb_count,
         if (chunk == 0 && (r.ts.flags & 9u) == 9u && (uint32_t)i < hd.n)
             y = fir_block_start(row[s], a.tab, a.perbits + (size_t)s * kPerWords, a.taps, a.etab, i, KK, a.satcode[s]);
         r.yfix[i] = y;
+    }
+    r.lat = TileLat{};
+    if (a.lat.q != 0 && chunk == 0) {
+        r.lat = tile_lat(row[s], a.lat, a.perbits + (size_t)s * kPerWords, a.spc, a.satcode[s]);
+        if (a.stats && (r.ts.flags & 1u) && !lat_rotation_ok(r.ts)) atomicAdd(a.stats, 1u);
     }
     out[((size_t)tb * a.tiles_per_block + chunk) * a.n_sats + s] = r;
 }

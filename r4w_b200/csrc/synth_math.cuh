@@ -479,7 +479,9 @@ R4WB_HD TileSat tile_sat(const BlockSat& b, const BlockSat* __restrict__ tab, ui
         // the linearised step phasor is good to (th1 * tile)^2 / 2 and (th2 * K)^2 / 2: fall back to per-sample sincos beyond 1e-4
         if (fabsf(t.th1) * 8192.0f > 1e-4f || fabsf(t.th2) * 16.0f > 1e-4f) fl |= 4u;
     }
-    if (i_begin == 0 && !continues_prev(b, tab)) fl |= 8u;
+    // the first eight windows of a block reach into its predecessor: collapsed form across the boundary only when the code
+    // sequence continues exactly AND neither block has a boundary inside the f64 rounding band (fir_block_start is literal then)
+    if (i_begin == 0 && (!continues_prev(b, tab) || (b.flags & 2u) || (tab[b.prev].flags & 2u))) fl |= 8u;
     t.flags = fl;
     return t;
 }
@@ -503,6 +505,19 @@ R4WB_HD uint32_t sign_word(const uint32_t* __restrict__ per, uint32_t hb, uint32
     const uint32_t e1 = e + 1 == cd.epoch_period ? 0u : e + 1;
     const uint32_t se = 0u - ((uint32_t)(cd.epoch_bits >> e) & 1u), se1 = 0u - ((uint32_t)(cd.epoch_bits >> e1) & 1u);
     const uint32_t nlow = cd.per_len - p;                                     // bits of this word inside epoch e
+    const uint32_t lowmask = nlow >= 32u ? 0xffffffffu : ((1u << nlow) - 1u);
+    return bits ^ ((se & lowmask) | (se1 & ~lowmask));
+}
+
+// the same word for a table origin given as (epoch e0, half-chip p0 inside the period): no division
+R4WB_HD uint32_t sign_word_ep(const uint32_t* __restrict__ per, uint32_t e0, uint32_t p0, uint32_t w, const SatCode& cd)
+{
+    uint32_t p = p0 + 32u * w, e = e0;
+    while (p >= cd.per_len) { p -= cd.per_len; e = e + 1u == cd.epoch_period ? 0u : e + 1u; }
+    const uint32_t bits = funnel_r(per[p >> 5], per[(p >> 5) + 1], p);
+    const uint32_t e1 = e + 1u == cd.epoch_period ? 0u : e + 1u;
+    const uint32_t se = 0u - ((uint32_t)(cd.epoch_bits >> e) & 1u), se1 = 0u - ((uint32_t)(cd.epoch_bits >> e1) & 1u);
+    const uint32_t nlow = cd.per_len - p;
     const uint32_t lowmask = nlow >= 32u ? 0xffffffffu : ((1u << nlow) - 1u);
     return bits ^ ((se & lowmask) | (se1 & ~lowmask));
 }

@@ -388,6 +388,49 @@ ScenarioModel::ScenarioModel(const r4wb_scenario_cfg& c_in) : cfg(c_in)
         clslut.assign(16, 0);
     }
 
+    // Lattice kernel (synth_lattice.cuh): a block of B = 2 q samples whose half-chip position advances by p / q per sample
+    // (direct-path satellites are skipped by it like by k_synth; k_synth_direct adds them afterwards)
+    lat = LatConst{};
+    {
+        const char* env = std::getenv("R4WB_SYNTH_LATTICE");                 // A/B hook: 0 keeps every launch on k_synth
+        const uint32_t D = sc.lut_den;
+        const uint64_t g2 = gcd_u64(2 * sc.ratB, sc.ratA);
+        const uint64_t pov = 2 * sc.ratB / g2;                                // oversample step = pov / D half-chips, gcd(pov, D) = 1
+        const uint32_t q = D / 8u;
+        if (!(env && env[0] == '0') && D != 0 && D % 8u == 0 && q % 2u == 0 && sc.B == 2ull * q && pov < D && sc.ystride <= 200u &&
+            sc.n_sats >= 1 && sc.n_sats <= 16) {
+            const uint32_t K = (q + 2u * kSynthThreads - 1u) / (2u * kSynthThreads);
+            auto inv_mod = [](uint64_t a, uint64_t m) {                       // a^-1 mod m (gcd = 1), extended Euclid
+                long long t = 0, nt = 1, r = (long long)m, nr = (long long)(a % m);
+                while (nr != 0) { const long long qq = r / nr; long long x = t - qq * nt; t = nt; nt = x; x = r - qq * nr; r = nr; nr = x; }
+                return (uint64_t)(t < 0 ? t + (long long)m : t);
+            };
+            if ((K == 4 || K == 5) && gcd_u64(pov, q) == 1) {
+                lat.q = q; lat.p = (uint32_t)pov; lat.pov = (uint32_t)pov;
+                lat.pinv = (uint32_t)inv_mod(pov, q); lat.povinv = (uint32_t)inv_mod(pov, D);
+                lat.K = K; lat.cls_len = (q + 2u * kSynthThreads * K + 2u + 15u) & ~15u;
+                lat.d8_20 = (uint32_t)llround((double)pov / (double)q * 1048576.0);
+                lat.step20 = (uint32_t)llround((double)(2 * kSynthThreads) * (double)pov / (double)q * 1048576.0);
+                // class of sample index n for sub-residue b0: bin 8 (p n mod q) + b0 (bin centre, extended precision as above)
+                const long double Sl = (long double)sc.ratA / (2.0L * (long double)sc.ratB);
+                clsn.assign((size_t)8 * lat.cls_len, 0);
+                for (uint32_t b0 = 0; b0 < 8; ++b0)
+                    for (uint32_t n = 0; n < lat.cls_len; ++n) {
+                        const uint32_t bin = 8u * (uint32_t)(((uint64_t)pov * (n % q)) % q) + b0;
+                        const long double t0 = ((long double)bin + 0.5L) / (long double)D * Sl;
+                        uint32_t dsum = 0;
+                        for (int j = 0; j < 4; ++j) dsum += (uint32_t)floorl(t0 + (long double)j * Sl);
+                        clsn[(size_t)b0 * lat.cls_len + n] = (uint8_t)(dsum - sc.dsum0);
+                    }
+                // the collapsed-FIR table transposed: row = class (256 B), column = sign pattern
+                ytab2.assign(((size_t)sc.ystride * kLatYStride + 3) & ~(size_t)3, 0.0f);
+                for (uint32_t c = 0; c < sc.ystride; ++c)
+                    for (uint32_t pat = 0; pat < 32; ++pat) ytab2[(size_t)c * kLatYStride + pat] = ytab[(size_t)pat * sc.ystride + c];
+            }
+        }
+    }
+    if (clsn.empty()) clsn.assign(16, 0);
+    if (ytab2.empty()) ytab2.assign(64, 0.0f);
     tile_k = 10;
     if (const char* e = std::getenv("R4WB_SYNTH_TILE_K")) { if (std::atoi(e) == 5) tile_k = 5; }   // tuning hook
     {

@@ -9,6 +9,8 @@
 // contraction the device evaluates the same IEEE operations in the same order as the oracle and the reference.
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+
 #include "synth_math.cuh"
 
 namespace r4wb {
@@ -81,27 +83,57 @@ __global__ void __launch_bounds__(1024) k_phase_scan(const SatConst* __restrict_
 }
 
 // ---- exact carrier phase of dynamic satellites (synth_math.cuh: ref_phase_inc .. phase_after_block) ----------------------
-// One warp per satellite: exclusive prefix of the approximate block advances (predicts the binade of the phase at each block).
-__global__ void __launch_bounds__(32) k_phase_prefix(uint32_t n_sats, uint32_t nblk, const double* __restrict__ papprox, double* __restrict__ pstart)
+// The reference adds 3e9 f64 increments in order.  A block whose phase provably stays inside one binade advances by an INTEGER
+// multiple of that binade's ulp (PhaseQ.Q) — associative — so only the few blocks per satellite that cross a binade, hold an
+// exact tie or start near zero ("walk" blocks, on the order of a hundred of 600 000) are sequential:
+//   k_phase_prefix   CTA per satellite: scan of the real-number block advances -> predicted start phase / binade of every block
+//   k_phase_q        thread per (block, satellite): Q = sum over the block of rint(inc_i / ulp); walk flag from the prediction
+//   k_phase_runs     CTA per satellite: wrapping prefix sum of Q over the non-walk blocks + ordered list of the walk blocks
+//   k_phase_chain    warp per satellite: hops from walk block to walk block (run advance = difference of two prefix entries,
+//                    exact), walks each walk block sample by sample (the reference's own loop) -> phase at the start of every run
+//   k_phase_fill     thread per (block, satellite): phase = run start + (prefix difference) ulp; VERIFIES with that exact phase
+//                    that the block really stays inside its binade (the predicate of the serial walk).  Any violation is
+//                    counted and the host falls back to the serial kernel (k_phase_exact) — the first violating block of a
+//                    satellite has a correct phase by induction, so none can go unnoticed.
+
+// CTA per satellite: exclusive prefix of the approximate block advances
+__global__ void __launch_bounds__(1024) k_phase_prefix(uint32_t n_sats, uint32_t nblk, const double* __restrict__ papprox, double* __restrict__ pstart)
 {
-    const uint32_t s = blockIdx.x, lane = threadIdx.x;
-    double carry = 0.0;
-    for (uint32_t b0 = 0; b0 < nblk; b0 += 32) {
-        const uint32_t b = b0 + lane;
-        const double v = b < nblk ? papprox[(size_t)b * n_sats + s] : 0.0;
-        double x = v;
-        for (int off = 1; off < 32; off <<= 1) {
-            const double y = __shfl_up_sync(0xffffffffu, x, off);
-            if ((int)lane >= off) x += y;
-        }
-        if (b < nblk) pstart[(size_t)b * n_sats + s] = carry + (x - v);
-        carry += __shfl_sync(0xffffffffu, x, 31);
+    __shared__ double s_sum[1024];
+    const uint32_t s = blockIdx.x, t = threadIdx.x;
+    const uint32_t chunk = (nblk + 1023u) / 1024u;
+    const uint32_t lo = min(nblk, t * chunk), hi = min(nblk, lo + chunk);
+    double sum = 0.0;
+    for (uint32_t b = lo; b < hi; ++b) sum += papprox[(size_t)b * n_sats + s];
+    s_sum[t] = sum;
+    __syncthreads();
+    for (int off = 1; off < 1024; off <<= 1) {
+        double v = 0.0;
+        if ((int)t >= off) v = s_sum[t - off];
+        __syncthreads();
+        if ((int)t >= off) s_sum[t] += v;
+        __syncthreads();
+    }
+    double run = t > 0 ? s_sum[t - 1] : 0.0;
+    for (uint32_t b = lo; b < hi; ++b) {
+        pstart[(size_t)b * n_sats + s] = run;
+        run += papprox[(size_t)b * n_sats + s];
     }
 }
 
+// frac[i] = fl(i / n) for i < n: the first division of ref_phase_inc, shared by every block of n samples
+__global__ void k_phase_frac(uint32_t n, double* __restrict__ frac)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) frac[i] = div_rn((double)i, (double)n);
+}
+
 // One thread per (block, satellite): the integer sum of the block's increments rounded to the ulp of the predicted binade.
+// PhaseQ.ok: bit0 = Q usable while the phase stays in binade k, bit1 = "walk" block (predicted phase does not provably stay inside
+// the binade over the block, a tie, or a start below 2^8 rad)
 __global__ void k_phase_q(double fs, const SatConst* __restrict__ sats, uint32_t n_sats, uint32_t nblk, const BlockSat* __restrict__ tab,
-                          const double* __restrict__ dop, const double* __restrict__ pstart, PhaseQ* __restrict__ out)
+                          const double* __restrict__ dop, const double* __restrict__ pstart, const double* __restrict__ frac, uint32_t frac_n,
+                          PhaseQ* __restrict__ out)
 {
     const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (uint64_t)nblk * n_sats) return;
@@ -116,18 +148,130 @@ __global__ void k_phase_q(double fs, const SatConst* __restrict__ sats, uint32_t
         if (p != 0.0) {
             r.k = ilogb(p);
             if (r.k >= 8) {
-                bool tie;
-                block_phase_q(ds, de, e.n, fs, r.k, &r.Q, &tie);
+                bool tie = false;
+                if (e.n == frac_n) {                         // same operations as block_phase_q, i / n from the table
+                    long long q = 0;
+                    const double dd = add_rn(de, -ds);
+                    for (uint32_t i = 0; i < e.n; ++i) {
+                        const double dopp = add_rn(ds, mul_rn(frac[i], dd));
+                        const double x = scalbn(div_rn(mul_rn(6.283185307179586, dopp), fs), 52 - r.k);
+                        const double fl = floor(x), rr = x - fl;
+                        if (rr == 0.5) tie = true;
+                        q += (long long)fl + (rr > 0.5 ? 1 : 0);
+                    }
+                    r.Q = q;
+                } else {
+                    block_phase_q(ds, de, e.n, fs, r.k, &r.Q, &tie);
+                }
                 r.ok = tie ? 0u : 1u;
             }
         }
+        if (!phase_stays_in_binade(p, r)) r.ok |= 2u;
     }
     out[idx] = r;
 }
 
-// One warp per dynamic satellite walks the blocks in order with the exact f64 phase: a block whose phase stays inside the
-// predicted binade advances by its integer sum, any other block is walked sample by sample (lanes evaluate 32 increments at a
-// time, the additions stay sequential).  Writes the phase before the block's first increment into the table.
+// CTA per dynamic satellite: prefQ[b] = wrapping sum of Q over the non-walk blocks before b; walk blocks listed in order
+__global__ void __launch_bounds__(1024) k_phase_runs(const SatConst* __restrict__ sats, uint32_t n_sats, uint32_t nblk, const PhaseQ* __restrict__ pq,
+                                                      unsigned long long* __restrict__ prefq, uint32_t* __restrict__ wlist, uint32_t* __restrict__ nwalk)
+{
+    __shared__ unsigned long long s_sum[1024];
+    __shared__ uint32_t s_cnt[1024];
+    const uint32_t s = blockIdx.x, t = threadIdx.x;
+    if (sats[s].static_phase) { if (t == 0) nwalk[s] = 0; return; }
+    const uint32_t chunk = (nblk + 1023u) / 1024u;
+    const uint32_t lo = min(nblk, t * chunk), hi = min(nblk, lo + chunk);
+    unsigned long long sum = 0;
+    uint32_t cnt = 0;
+    for (uint32_t b = lo; b < hi; ++b) {
+        const PhaseQ& r = pq[(size_t)b * n_sats + s];
+        if (r.ok & 2u) ++cnt; else sum += (unsigned long long)r.Q;
+    }
+    s_sum[t] = sum; s_cnt[t] = cnt;
+    __syncthreads();
+    for (int off = 1; off < 1024; off <<= 1) {
+        unsigned long long v = 0; uint32_t c = 0;
+        if ((int)t >= off) { v = s_sum[t - off]; c = s_cnt[t - off]; }
+        __syncthreads();
+        if ((int)t >= off) { s_sum[t] += v; s_cnt[t] += c; }
+        __syncthreads();
+    }
+    unsigned long long run = t > 0 ? s_sum[t - 1] : 0ull;
+    uint32_t w = t > 0 ? s_cnt[t - 1] : 0u;
+    for (uint32_t b = lo; b < hi; ++b) {
+        const PhaseQ& r = pq[(size_t)b * n_sats + s];
+        prefq[(size_t)b * n_sats + s] = run;
+        if (r.ok & 2u) wlist[(size_t)s * nblk + w++] = b; else run += (unsigned long long)r.Q;
+    }
+    if (t == 1023) nwalk[s] = s_cnt[1023];
+}
+
+// exact advance of a run: (prefix difference) x ulp of the binade of the run's start phase (both multiples of that ulp, the sum
+// stays inside the binade: exact).  dq = 0 leaves the phase untouched (runs of invisible blocks, empty runs).
+__device__ __forceinline__ double run_phase(double ph0, unsigned long long dq)
+{
+    if (dq == 0ull) return ph0;
+    return ph0 + scalbn((double)(long long)dq, ilogb(ph0) - 52);
+}
+
+// One warp per dynamic satellite: from walk block to walk block.  runph[s][i] = exact phase at the first block after walk block
+// i - 1 (i = 0: block 0), i.e. at the start of run i, which ends with walk block i (the last run has no walk block).
+__global__ void __launch_bounds__(32) k_phase_chain(double fs, const SatConst* __restrict__ sats, uint32_t n_sats, uint32_t nblk,
+                                                     const BlockSat* __restrict__ tab, const double* __restrict__ dop,
+                                                     const unsigned long long* __restrict__ prefq, const uint32_t* __restrict__ wlist,
+                                                     const uint32_t* __restrict__ nwalk, double* __restrict__ runph)
+{
+    const uint32_t s = blockIdx.x, lane = threadIdx.x;
+    if (sats[s].static_phase) return;
+    const uint32_t nw = nwalk[s];
+    const uint32_t* wl = wlist + (size_t)s * nblk;
+    double* rp = runph + (size_t)s * ((size_t)nblk + 1);
+    double ph = 0.0;
+    uint32_t start = 0;                                       // first block of the current run
+    for (uint32_t i = 0; i < nw; ++i) {
+        if (lane == 0) rp[i] = ph;
+        const uint32_t w = wl[i];
+        const size_t idx = (size_t)w * n_sats + s;
+        ph = run_phase(ph, prefq[idx] - prefq[(size_t)start * n_sats + s]);
+        const double ds = dop[2 * idx], de = dop[2 * idx + 1];
+        const uint32_t n = tab[idx].n;
+        const double nf = (double)n;
+        for (uint32_t i0 = 0; i0 < n; i0 += 32) {
+            const uint32_t ii = i0 + lane;
+            const double inc = ii < n ? ref_phase_inc(ds, de, ii, nf, fs) : 0.0;       // + 0.0 leaves the phase as it is
+#pragma unroll
+            for (int jj = 0; jj < 32; ++jj) ph = ph + __shfl_sync(0xffffffffu, inc, jj);
+        }
+        start = w + 1;
+    }
+    if (lane == 0) rp[nw] = ph;
+}
+
+// One thread per (block, satellite): phase before the block's first increment -> tab[].phi; verification (see above)
+__global__ void k_phase_fill(const SatConst* __restrict__ sats, uint32_t n_sats, uint32_t nblk, BlockSat* __restrict__ tab,
+                             const PhaseQ* __restrict__ pq, const unsigned long long* __restrict__ prefq, const uint32_t* __restrict__ wlist,
+                             const uint32_t* __restrict__ nwalk, const double* __restrict__ runph, uint32_t* __restrict__ bad)
+{
+    const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (uint64_t)nblk * n_sats) return;
+    const uint32_t s = (uint32_t)(idx % n_sats), b = (uint32_t)(idx / n_sats);
+    if (sats[s].static_phase) return;
+    const uint32_t nw = nwalk[s];
+    const uint32_t* wl = wlist + (size_t)s * nblk;
+    uint32_t lo = 0, hi = nw;                                 // i = number of walk blocks before b = index of b's run
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (wl[mid] < b) lo = mid + 1; else hi = mid;
+    }
+    const uint32_t start = lo > 0 ? wl[lo - 1] + 1 : 0u;
+    const double ph = run_phase(runph[(size_t)s * ((size_t)nblk + 1) + lo], prefq[idx] - prefq[(size_t)start * n_sats + s]);
+    tab[idx].phi = cycles_to_fixed(ph / (2.0 * kPi));
+    const PhaseQ r = pq[idx];
+    if ((tab[idx].flags & 1u) && !(r.ok & 2u) && !phase_stays_in_binade(ph, r)) atomicAdd(bad, 1u);
+}
+
+// Serial reference implementation of the same result (fallback when k_phase_fill reports a violation; also the A/B hook
+// R4WB_PHASE_SERIAL=1): one warp per dynamic satellite walks the blocks in order with the exact f64 phase.
 __global__ void __launch_bounds__(32) k_phase_exact(double fs, const SatConst* __restrict__ sats, uint32_t n_sats, uint32_t nblk,
                                                      BlockSat* __restrict__ tab, const double* __restrict__ dop, const PhaseQ* __restrict__ pq)
 {
@@ -142,6 +286,7 @@ __global__ void __launch_bounds__(32) k_phase_exact(double fs, const SatConst* _
         if (b < nblk) {
             const size_t idx = (size_t)b * n_sats + s;
             s_rec[lane] = pq[idx];
+            s_rec[lane].ok &= 1u;
             s_ds[lane] = dop[2 * idx]; s_de[lane] = dop[2 * idx + 1];
             s_n[lane] = tab[idx].n; s_vis[lane] = tab[idx].flags & 1u;
         }
@@ -166,17 +311,61 @@ __global__ void __launch_bounds__(32) k_phase_exact(double fs, const SatConst* _
     }
 }
 
-void launch_phase_exact(const ScenConst& sc, const SatConst* d_sats, uint32_t nblk, BlockSat* d_tab, const double* d_dop,
-                        const double* d_papprox, double* d_pstart, PhaseQ* d_pq, cudaStream_t st)
+// scratch of the exact-phase pass (caller-owned, sized by phase_exact_scratch_bytes)
+struct PhaseScratch {
+    double* pstart; PhaseQ* pq; double* frac; unsigned long long* prefq; uint32_t* wlist; uint32_t* nwalk; double* runph; uint32_t* bad;
+};
+
+size_t phase_exact_scratch_bytes(uint32_t n_sats, uint32_t nblk, uint32_t B)
 {
-    if (nblk == 0 || sc.n_sats == 0) return;
-    k_phase_prefix<<<sc.n_sats, 32, 0, st>>>(sc.n_sats, nblk, d_papprox, d_pstart);
+    const size_t ne = (size_t)nblk * n_sats;
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    return al(ne * 8) + al(ne * sizeof(PhaseQ)) + al((size_t)B * 8) + al(ne * 8) + al(ne * 4) + al((size_t)n_sats * 4 + 4) + al((ne + n_sats) * 8) + 256;
+}
+
+// returns false when the parallel pass found a violation of its own premise and the serial kernel was run instead
+bool launch_phase_exact(const ScenConst& sc, const SatConst* d_sats, uint32_t nblk, BlockSat* d_tab, const double* d_dop,
+                        const double* d_papprox, unsigned char* scratch, cudaStream_t st)
+{
+    if (nblk == 0 || sc.n_sats == 0) return true;
+    const uint32_t ns = sc.n_sats;
+    const size_t ne = (size_t)nblk * ns;
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    PhaseScratch S;
+    unsigned char* p = scratch;
+    S.pstart = reinterpret_cast<double*>(p); p += al(ne * 8);
+    S.pq = reinterpret_cast<PhaseQ*>(p); p += al(ne * sizeof(PhaseQ));
+    S.frac = reinterpret_cast<double*>(p); p += al((size_t)sc.B * 8);
+    S.prefq = reinterpret_cast<unsigned long long*>(p); p += al(ne * 8);
+    S.wlist = reinterpret_cast<uint32_t*>(p); p += al(ne * 4);
+    S.nwalk = reinterpret_cast<uint32_t*>(p); p += al((size_t)ns * 4 + 4);
+    S.runph = reinterpret_cast<double*>(p); p += al((ne + ns) * 8);
+    S.bad = reinterpret_cast<uint32_t*>(p);
+
+    k_phase_prefix<<<ns, 1024, 0, st>>>(ns, nblk, d_papprox, S.pstart);
     R4WB_LAUNCH_CHECK();
-    const uint64_t total = (uint64_t)nblk * sc.n_sats;
-    k_phase_q<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(sc.fs, d_sats, sc.n_sats, nblk, d_tab, d_dop, d_pstart, d_pq);
+    k_phase_frac<<<(unsigned)((sc.B + 255) / 256), 256, 0, st>>>((uint32_t)sc.B, S.frac);
     R4WB_LAUNCH_CHECK();
-    k_phase_exact<<<sc.n_sats, 32, 0, st>>>(sc.fs, d_sats, sc.n_sats, nblk, d_tab, d_dop, d_pq);
+    k_phase_q<<<(unsigned)((ne + 127) / 128), 128, 0, st>>>(sc.fs, d_sats, ns, nblk, d_tab, d_dop, S.pstart, S.frac, (uint32_t)sc.B, S.pq);
     R4WB_LAUNCH_CHECK();
+    static const bool serial = [] { const char* e = std::getenv("R4WB_PHASE_SERIAL"); return e && e[0] == '1'; }();
+    uint32_t bad = 0;
+    if (!serial) {
+        R4WB_CUDA(cudaMemsetAsync(S.bad, 0, sizeof(uint32_t), st));
+        k_phase_runs<<<ns, 1024, 0, st>>>(d_sats, ns, nblk, S.pq, S.prefq, S.wlist, S.nwalk);
+        R4WB_LAUNCH_CHECK();
+        k_phase_chain<<<ns, 32, 0, st>>>(sc.fs, d_sats, ns, nblk, d_tab, d_dop, S.prefq, S.wlist, S.nwalk, S.runph);
+        R4WB_LAUNCH_CHECK();
+        k_phase_fill<<<(unsigned)((ne + 127) / 128), 128, 0, st>>>(d_sats, ns, nblk, d_tab, S.pq, S.prefq, S.wlist, S.nwalk, S.runph, S.bad);
+        R4WB_LAUNCH_CHECK();
+        R4WB_CUDA(cudaMemcpyAsync(&bad, S.bad, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        R4WB_CUDA(cudaStreamSynchronize(st));
+        if (bad == 0) return true;
+    }
+    k_phase_exact<<<ns, 32, 0, st>>>(sc.fs, d_sats, ns, nblk, d_tab, d_dop, S.pq);
+    R4WB_LAUNCH_CHECK();
+    R4WB_CUDA(cudaStreamSynchronize(st));
+    return serial;
 }
 
 void launch_block_params(const ScenConst& sc, const SatConst* d_sats, const PhaseSegment* d_segs, uint64_t blk0, uint32_t nblk,

@@ -179,7 +179,7 @@ class GnssScenario:
         return float(v.value)
 
     def last_path(self) -> int:
-        """0: k_synth rendered the last generate call, 1: the period-resident kernels did (diagnostic)."""
+        """0: k_synth / k_synth_lat rendered the last generate call, 1: the period-resident kernels did (diagnostic)."""
         return int(_lib.lib().r4wb_scenario_last_path(self._h))
 
     def set_profiling(self, enabled: bool = True):
@@ -187,10 +187,10 @@ class GnssScenario:
 
     def last_profile(self):
         """{kernel: (summed CUDA-event ms, launches)} of the last generate call (profiling must be enabled)."""
-        ms = np.zeros(3, np.float64)
-        n = np.zeros(3, np.uint64)
+        ms = np.zeros(4, np.float64)
+        n = np.zeros(4, np.uint64)
         _lib.check(_lib.lib().r4wb_scenario_last_profile(self._h, ms.ctypes.data_as(C.c_void_p), n.ctypes.data_as(C.c_void_p)))
-        return {k: (float(ms[i]), int(n[i])) for i, k in enumerate(("k_synth", "k_synth_periodic", "k_periodic_fix"))}
+        return {k: (float(ms[i]), int(n[i])) for i, k in enumerate(("k_synth", "k_synth_periodic", "k_periodic_fix", "k_synth_lat"))}
 
     def _debug_block_params(self, block: int, sat: int) -> np.ndarray:
         out = np.zeros(12, np.float64)

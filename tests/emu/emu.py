@@ -34,6 +34,8 @@ def lib():
         L.emu_scenario_total_samples.argtypes = [vp]; L.emu_scenario_total_samples.restype = u64
         L.emu_scenario_block_size.argtypes = [vp]; L.emu_scenario_block_size.restype = u64
         L.emu_scenario_segments.argtypes = [vp]; L.emu_scenario_segments.restype = C.c_uint32
+        L.emu_scenario_set_lattice.argtypes = [vp, C.c_int]
+        L.emu_scenario_patched.argtypes = [vp]; L.emu_scenario_patched.restype = u64
         L.emu_scenario_generate.argtypes = [vp, u64, u64, vp, C.c_int, C.POINTER(u64)]
         L.emu_scenario_generate_block.argtypes = [vp, u64, vp, C.POINTER(u64)]
         L.emu_block_params.argtypes = [vp, u64, C.c_uint32, vp]
@@ -58,6 +60,14 @@ class EmuScenario:
         if getattr(self, "_h", None):
             lib().emu_scenario_destroy(self._h)
             self._h = None
+
+    def set_lattice(self, on: bool = True) -> bool:
+        """replay k_synth_lat (synth_lattice.cuh) for full blocks; False when the scenario does not qualify"""
+        return bool(lib().emu_scenario_set_lattice(self._h, int(on)))
+
+    def patched(self) -> int:
+        """windows-with-a-disputed-oversample records met so far by the lattice replay"""
+        return int(lib().emu_scenario_patched(self._h))
 
     def total_samples(self): return int(lib().emu_scenario_total_samples(self._h))
     def block_size(self): return int(lib().emu_scenario_block_size(self._h))

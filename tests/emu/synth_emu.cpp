@@ -9,7 +9,7 @@
 #include <memory>
 #include <vector>
 
-#include "../../r4w_b200/csrc/synth_math.cuh"
+#include "../../r4w_b200/csrc/synth_lattice.cuh"
 
 using namespace r4wb;
 
@@ -180,9 +180,86 @@ struct Emu {
         }
     }
 
+    // k_synth_lat (synth_lattice.cu), thread loops flattened: full canonical blocks only.  Returns the number of patched windows.
+    template <int K>
+    uint64_t render_lat_t(const BlockSat* tb_tab, const BlockHdr* tb_hdr, uint32_t tb_begin, uint32_t tb_count, uint64_t out_first,
+                          uint64_t out_n, float* out, int only_sat)
+    {
+        const ScenConst& sc = md.sc;
+        const LatConst& L = md.lat;
+        const uint32_t ns = sc.n_sats, n_ent = lat_n_ent(L), n_w = lat_n_words(L);
+        const SynthK KK = make_synth_k(sc.delta46, sc.kmul, sc.cj, sc.dsum0, sc.spc, sc.lut_den, sc.ystride);
+        const uint64_t d8_46 = sc.delta46 * (uint64_t)kOversample;
+        const bool noise = !(sc.flags & R4WB_FLAG_NOISE_OFF);
+        std::vector<TileRec> rec(ns);
+        std::vector<uint32_t> W((size_t)ns * n_w);
+        std::vector<uint4> ent((size_t)ns * n_ent);
+        uint64_t patched = 0;
+        for (uint32_t tile = 0; tile < tb_count; ++tile) {
+            const uint32_t tb = tb_begin + tile;
+            const BlockHdr hd = tb_hdr[tb];
+            if (hd.n != 2 * L.q) fail(R4WB_ERR_INVALID_SIZE, "lattice replay: partial block");
+            if (hd.first + hd.n <= out_first || hd.first >= out_first + out_n) continue;
+            const BlockSat* row = tb_tab + (size_t)tb * ns;
+            for (uint32_t s = 0; s < ns; ++s) {                              // k_tile_params
+                rec[s].ts = tile_sat(row[s], tb_tab, 0, KK.d8);
+                for (uint32_t i = 0; i < 8; ++i)
+                    rec[s].yfix[i] = (rec[s].ts.flags & 9u) == 9u ? fir_block_start(row[s], tb_tab, md.perbits.data() + s * kPerWords, md.taps_f, md.etab_f, (int)i, KK, md.satcode[s]) : 0.0f;
+                rec[s].lat = tile_lat(row[s], L, md.perbits.data() + s * kPerWords, sc.spc, md.satcode[s]);
+                if ((rec[s].ts.flags & 1u) && !lat_rotation_ok(rec[s].ts)) fail(R4WB_ERR_NOT_SUPPORTED, "lattice replay: carrier model out of range");
+                for (int e = 0; e < 2; ++e) if ((rec[s].lat.patch >> (16 + 2 * e)) & 3u) ++patched;
+                for (uint32_t w = 0; w < n_w; ++w) {
+                    W[s * n_w + w] = sign_word_ep(md.perbits.data() + s * kPerWords, rec[s].lat.ep0 & 0xffu, rec[s].lat.ep0 >> 8, w, md.satcode[s]);
+                    if (W[s * n_w + w] != sign_word(md.perbits.data() + s * kPerWords, rec[s].ts.hb, w, md.satcode[s])) fail(R4WB_ERR_CUDA, "sign_word_ep != sign_word");
+                }
+                for (uint32_t j = 0; j < n_ent; ++j) ent[s * n_ent + j] = lat_entry(W.data() + s * n_w, j, L.p);
+            }
+            for (uint32_t tid = 0; tid < (uint32_t)kSynthThreads; ++tid) {
+                float2 arA[K], aiA[K], arB[K], aiB[K];
+                for (int k = 0; k < K; ++k) arA[k] = aiA[k] = arB[k] = aiB[k] = make_float2(0.0f, 0.0f);
+                for (uint32_t s = 0; s < ns; ++s) {
+                    if (only_sat >= 0 && (int)s != only_sat) continue;
+                    if (!(rec[s].ts.flags & 1u)) continue;
+                    lat_sat_accumulate<K>(rec[s], L, d8_46, ent.data() + s * n_ent, md.ytab2.data(), md.clsn.data(), md.taps_f, tid, arA, aiA, arB, aiB);
+                }
+                for (int k = 0; k < K; ++k) {
+                    const uint32_t ia = 2 * tid + 2 * kSynthThreads * k;
+                    if (ia >= L.q) continue;
+                    for (uint32_t v = 0; v < 4; ++v) {
+                        const uint32_t i = ia + (v & 1u) + ((v & 2u) ? L.q : 0u);
+                        const uint64_t m = hd.first + i;
+                        if (m < out_first || m >= out_first + out_n) continue;
+                        const float2& r2 = (v & 2u) ? arB[k] : arA[k];
+                        const float2& i2 = (v & 2u) ? aiB[k] : aiA[k];
+                        float2 val = (v & 1u) ? make_float2(r2.y, i2.y) : make_float2(r2.x, i2.x);
+                        if (noise && only_sat < 0) {
+                            const float2 g = noise_of_sample(m, sc.seed);
+                            val.x = fmaf(g.x, sc.noise_std, val.x);
+                            val.y = fmaf(g.y, sc.noise_std, val.y);
+                        }
+                        out[2 * (m - out_first)] = val.x;
+                        out[2 * (m - out_first) + 1] = val.y;
+                    }
+                }
+            }
+        }
+        return patched;
+    }
+
+    bool use_lattice = false;      // emu_scenario_set_lattice: replay k_synth_lat for full blocks instead of k_synth
+    uint64_t n_patched = 0;
+
     void render(const BlockSat* tb_tab, const BlockHdr* tb_hdr, uint32_t tb_begin, uint32_t tb_count, uint64_t out_first,
                 uint64_t out_n, float* out, uint64_t max_block_n, int only_sat, uint64_t* n_ambiguous)
     {
+        if (use_lattice && md.lat.q != 0 && max_block_n == md.sc.B && !md.any_direct) {
+            uint32_t n_full = tb_count;
+            if (tb_hdr[tb_begin + tb_count - 1].n != md.sc.B) n_full -= 1;
+            if (n_full) n_patched += md.lat.K == 5 ? render_lat_t<5>(tb_tab, tb_hdr, tb_begin, n_full, out_first, out_n, out, only_sat)
+                                                   : render_lat_t<4>(tb_tab, tb_hdr, tb_begin, n_full, out_first, out_n, out, only_sat);
+            if (n_full == tb_count) return;
+            tb_begin += n_full; tb_count -= n_full;
+        }
         if (md.tile_k == 5) render_t<5>(tb_tab, tb_hdr, tb_begin, tb_count, out_first, out_n, out, max_block_n, only_sat, n_ambiguous);
         else render_t<10>(tb_tab, tb_hdr, tb_begin, tb_count, out_first, out_n, out, max_block_n, only_sat, n_ambiguous);
         if (!md.any_direct) return;
@@ -263,6 +340,9 @@ void emu_scenario_destroy(void* h) { delete static_cast<Emu*>(h); }
 uint64_t emu_scenario_total_samples(void* h) { return static_cast<Emu*>(h)->md.sc.total; }
 uint64_t emu_scenario_block_size(void* h) { return static_cast<Emu*>(h)->md.sc.B; }
 uint32_t emu_scenario_segments(void* h) { return (uint32_t)static_cast<Emu*>(h)->md.segments.size(); }
+// 1: replay k_synth_lat for full blocks.  Returns whether the scenario qualifies (lattice constants present).
+int emu_scenario_set_lattice(void* h, int on) { Emu* e = static_cast<Emu*>(h); e->use_lattice = on != 0; return e->md.lat.q != 0 ? 1 : 0; }
+uint64_t emu_scenario_patched(void* h) { return static_cast<Emu*>(h)->n_patched; }
 
 // canonical-partition random access (mirror of Scenario::generate)
 int emu_scenario_generate(void* h, uint64_t first, uint64_t n, float* out_cf32, int only_sat, uint64_t* n_ambiguous)

@@ -113,6 +113,36 @@ def test_generate_starts_at_current_sample_and_leaves_done(gpu, oracle):
     assert rest.size == want.size and _relrms(rest, want) <= TOL and sc.is_done()
 
 
+def test_block_loop_is_served_from_the_render_ahead_ring(gpu, oracle):
+    """`while !is_done { generate_block(block_size) }` (crates/r4w-cli/src/main.rs:4488-4500): canonical blocks come out of the
+    pinned ring — bit-identical to generate_range, reset() repositions, an odd-sized block afterwards continues the
+    reference's partition (host state replayed), and a block larger than 65 536 samples is one reference block too"""
+    cfg = _cfg("e1c_8prn_60s_cn34_orbital")
+    cfg.output.duration_s = 0.6314                               # 631.4 blocks: three ring chunks and a partial last block
+    sc = gpu.GnssScenario(cfg, noise=True)
+    whole = gpu.GnssScenario(cfg, noise=True).generate_range(0, sc.total_samples())
+    parts = []
+    while not sc.is_done():
+        parts.append(sc.generate_block(5000))
+        assert sc.last_power_sum() == pytest.approx(float(np.sum(np.abs(parts[-1].astype(np.complex128)) ** 2)), rel=1e-12)
+    assert len(parts) == 632 and parts[-1].size == 2000 and np.array_equal(np.concatenate(parts), whole)
+    assert sc.generate_block(5000).size == 0
+    sc.reset()
+    assert np.array_equal(sc.generate_block(5000), whole[:5000])
+    for _ in range(250):
+        sc.generate_block(5000)
+    assert np.array_equal(sc.generate_block(5000, dtype=np.complex128), whole[1_255_000:1_260_000].astype(np.complex128))
+    # odd-sized block after 7 ring-served blocks: compare with the oracle walking the same partition
+    clean = _cfg("e1c_8prn_60s_cn34_orbital"); clean.output.duration_s = 0.2
+    g, o = gpu.GnssScenario(clean, noise=False), oracle.OracleScenario(clean, noise=False)
+    for _ in range(7):
+        a, b = g.generate_block(5000), o.generate_block(5000)
+    assert _relrms(a, b) <= TOL
+    for bs in (1234, 5000, 100_000):
+        a, b = g.generate_block(bs), o.generate_block(bs)
+        assert a.size == b.size == bs and _relrms(a, b) <= TOL
+
+
 def test_streams_are_restored_and_ordered(gpu):
     """device-tensor calls run on torch's current stream and leave the library on the default stream; a table built on one
     stream is safe to use from another (stale thread-local stream, unsynchronised table reuse)"""
@@ -134,6 +164,27 @@ def test_streams_are_restored_and_ordered(gpu):
         sc.generate_device(3_000_000, n, c)             # extends the table on another stream
     other.synchronize()
     assert np.array_equal(c.cpu().numpy(), sc.generate_range(3_000_000, n))
+
+
+@pytest.mark.parametrize("name,first,n", [
+    ("e1c_8prn_60s_cn34_orbital", 12_345_000, 400_000),
+    ("e1c_60s_all_prns", 299_400_000, 600_000),                 # ends with the scenario's last block
+    ("e1c_8prn_600s_cn34_orbital", 2_650_000_000, 1_000_000),   # ~2 % of the entries flagged: the patched windows
+])
+def test_lattice_kernel_equals_general_kernel(gpu, monkeypatch, name, first, n):
+    """k_synth_lat (quads on the sample lattice, disputed oversamples patched) and k_synth (per-sample NCO, literal re-evaluation of
+    disputed windows) render the same samples to f32 rounding, noise included; R4WB_SYNTH_LATTICE=0 is the A/B switch"""
+    cfg = _cfg(name)
+    a_sc = gpu.GnssScenario(cfg, noise=True)
+    a_sc.set_profiling(True)
+    a = a_sc.generate_range(first, n)
+    assert a_sc.last_profile()["k_synth_lat"][1] >= 1
+    monkeypatch.setenv("R4WB_SYNTH_LATTICE", "0")
+    b_sc = gpu.GnssScenario(cfg, noise=True)
+    b_sc.set_profiling(True)
+    b = b_sc.generate_range(first, n)
+    assert b_sc.last_profile()["k_synth_lat"][1] == 0 and b_sc.last_profile()["k_synth"][1] >= 1
+    assert np.max(np.abs(a - b)) < 1e-6 * np.max(np.abs(a)) and _relrms(a, b) < 5e-7   # the signal parts differ by f32 rounding only
 
 
 def test_random_access_is_consistent(gpu):
@@ -343,7 +394,8 @@ print(hashlib.sha256(np.ascontiguousarray(x).tobytes()).hexdigest())
 
 def test_class_table_path_equals_arithmetic_path(gpu):
     """k_synth with the boundary-age class table and with the arithmetic floor sums: byte-identical IQ (noise on)"""
-    assert _run_py(_SYNTH_HASH, {}) == _run_py(_SYNTH_HASH, {"R4WB_SYNTH_NO_LUT": "1"})
+    off = {"R4WB_SYNTH_LATTICE": "0"}                      # keep both runs on k_synth (the lattice kernel needs the class table)
+    assert _run_py(_SYNTH_HASH, off) == _run_py(_SYNTH_HASH, {"R4WB_SYNTH_NO_LUT": "1", **off})
 
 
 @pytest.mark.parametrize("fmt,lsb", [("ci16", 1), ("ci8", 1), ("cu8", 1)])

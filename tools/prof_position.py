@@ -22,8 +22,10 @@ for t0 in offsets:
     for r in range(3):
         s.generate_device(first, n, out)
         torch.cuda.synchronize()
-        ms.append(s.last_profile()["k_synth"][0])
-    print(f"t0 {t0:4d} s: k_synth {min(ms):.3f} ms for {n} samples = {n / min(ms) / 1e6:.1f} Gs/s", flush=True)
+        pr = s.last_profile()
+        kn = max(pr, key=lambda k: pr[k][0])
+        ms.append(pr[kn][0])
+    print(f"t0 {t0:4d} s: {kn} {min(ms):.3f} ms for {n} samples = {n / min(ms) / 1e6:.1f} Gs/s", flush=True)
 rng = np.random.default_rng(1)
 for t0 in ((0, 270, 530) if len(sys.argv) == 1 else ()):
     flags = []
