@@ -171,6 +171,14 @@ const char* r4wb_version(void);                 /* static NUL-terminated, like r
 const char* r4wb_last_error(void);              /* thread-local text of the last failure */
 r4wb_error r4wb_init(int device);               /* cudaSetDevice(device) + context warm-up; -1 keeps the current device */
 r4wb_error r4wb_device_count(int* n);
+/* Multi-GPU inside the library (the caller is one host process, e.g. `r4w gnss scenario`,
+ * crates/r4w-cli/src/main.rs:4442): initialise devices 0 .. n_gpus-1 (n_gpus <= 0: every visible device).  From then on the
+ * host-buffer batch calls shard their independent units over those devices — r4wb_pcps_acquire_batch by snapshot,
+ * r4wb_scenario_generate(..., R4WB_MEM_HOST) by time segment — each device working into its slice of the caller's buffers;
+ * nothing is exchanged between devices (the 32-byte results / samples go straight to the host).  Handles stay bound to the
+ * device that was current at creation for everything else.  r4wb_init_devices(1) switches the sharding off again. */
+r4wb_error r4wb_init_devices(int n_gpus);
+int r4wb_devices_initialised(void);             /* devices the batch calls shard over (1 until r4wb_init_devices) */
 /* Launch all subsequent work of this thread's handles on `cuda_stream` (a cudaStream_t; NULL = default stream). */
 r4wb_error r4wb_set_stream(void* cuda_stream);
 /* pinned host memory for callers that want full-rate D2H/H2D (optional) */

@@ -4,7 +4,7 @@ FFT-based PCPS acquisition.  Host-side mirror of the reference's `GnssScenarioCo
 from .config import (GnssScenarioConfig, SatelliteConfig, ReceiverConfig, EnvironmentConfig, OutputConfig,  # noqa: F401
                      LlaPosition, AntennaPattern, ReceiverTrajectory, load_config, loads_config, preset_config, PRESETS,
                      gps_time_from_utc)
-from ._lib import R4wB200Error, init, kernel_launches, device_count, version, build  # noqa: F401
+from ._lib import R4wB200Error, init, init_devices, kernel_launches, device_count, version, build  # noqa: F401
 from .scenario import GnssScenario, SatelliteStatus  # noqa: F401
 from .tracking import TrackingChannel, TrackerBank, TrackingState  # noqa: F401
 from .acquisition import (PcpsAcquisition, AcquisitionResult, AcquisitionGrid, e1_code, e1c_secondary,  # noqa: F401

@@ -43,6 +43,8 @@ SYMBOLS = {
     "r4wb_last_error": (C.c_char_p, []),
     "r4wb_init": (_int, [_int]),
     "r4wb_device_count": (_int, [C.POINTER(_int)]),
+    "r4wb_init_devices": (_int, [_int]),
+    "r4wb_devices_initialised": (_int, []),
     "r4wb_set_stream": (_int, [_vp]),
     "r4wb_host_alloc": (_int, [C.POINTER(_vp), C.c_size_t]),
     "r4wb_host_free": (_int, [_vp]),
@@ -129,6 +131,15 @@ def init(device: int = -1):
     global _initialised
     check(lib().r4wb_init(device))
     _initialised = True
+
+
+def init_devices(n_gpus: int = 0) -> int:
+    """Multi-GPU inside the library: host-buffer batch calls (acquire_batch, generate into host memory) shard over devices
+    0 .. n_gpus-1 (0 = every visible device).  Returns the number of devices in use."""
+    global _initialised
+    check(lib().r4wb_init_devices(int(n_gpus)))
+    _initialised = True
+    return int(lib().r4wb_devices_initialised())
 
 
 def ensure_init():

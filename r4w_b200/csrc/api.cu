@@ -2,8 +2,11 @@
 // Every entry point converts internal failures into r4wb_error + a thread-local message; nothing unwinds.
 #include <cmath>
 #include <cstring>
+#include <memory>
 #include <mutex>
 #include <new>
+#include <thread>
+#include <vector>
 
 #include "acq.cuh"
 #include "compose.cuh"
@@ -13,6 +16,7 @@
 namespace r4wb {
 
 std::atomic<uint64_t> g_kernel_launches{0};
+static std::atomic<int> g_n_devices{1};            // devices the host-buffer batch calls shard over (r4wb_init_devices)
 static thread_local cudaStream_t t_stream = nullptr;
 static thread_local std::string t_error;
 
@@ -65,10 +69,64 @@ using namespace r4wb;
 // A handle lives on the device that was current when it was created; every call that touches the device re-selects it, so a
 // handle can be used from a host thread whose current device is another one (new threads start on device 0).
 static int device_now() { int d = 0; cudaGetDevice(&d); return d; }
-struct r4wb_scenario { int device = device_now(); Scenario impl; explicit r4wb_scenario(const r4wb_scenario_cfg& c) : impl(c) {} };
+// `peers[d]` (d != device): the same object on another device, created on first use by a sharded batch call
+struct r4wb_scenario {
+    int device = device_now();
+    Scenario impl;
+    std::vector<std::unique_ptr<Scenario>> peers;
+    double multi_power = -1.0;                     // sum |s|^2 of the last sharded generate (-1: last call was single-device)
+    explicit r4wb_scenario(const r4wb_scenario_cfg& c) : impl(c) {}
+    ~r4wb_scenario()
+    {
+        for (size_t d = 0; d < peers.size(); ++d) if (peers[d]) { cudaSetDevice((int)d); peers[d].reset(); }
+        cudaSetDevice(device);
+    }
+};
 // `PcpsAcquisition::acquire(&self)` is re-entrant in the reference; here a handle owns device scratch, so concurrent calls on
 // one handle take turns (`mu`)
-struct r4wb_pcps { int device = device_now(); Pcps impl; std::mutex mu; r4wb_pcps(uint64_t n, double fs) : impl(n, fs) {} };
+struct r4wb_pcps {
+    int device = device_now();
+    Pcps impl;
+    std::mutex mu;
+    uint64_t code_length; double fs;
+    double dmax = 5000.0, dstep = 500.0, threshold = 2.5; uint64_t coherent = 1;
+    std::vector<std::unique_ptr<Pcps>> peers;
+    r4wb_pcps(uint64_t n, double f) : impl(n, f), code_length(n), fs(f) {}
+    ~r4wb_pcps()
+    {
+        for (size_t d = 0; d < peers.size(); ++d) if (peers[d]) { cudaSetDevice((int)d); peers[d].reset(); }
+        cudaSetDevice(device);
+    }
+    Pcps& on(int d)                                // the engine of device d (current device must be d)
+    {
+        if (d == device) return impl;
+        if (peers.size() <= (size_t)d) peers.resize(d + 1);
+        if (!peers[d]) peers[d].reset(new Pcps(code_length, fs));
+        Pcps& p = *peers[d];
+        p.set_doppler_range(dmax, dstep); p.set_threshold(threshold); p.set_coherent_periods(coherent);
+        return p;
+    }
+};
+
+// units [0, n) split into `parts` contiguous shares; runs body(part, begin, end) on one host thread per part (part 0 on the
+// calling thread), each with its own current device set by the body.  The first failure is rethrown on the caller.
+template <typename F>
+static void run_sharded(int parts, uint64_t n, F&& body)
+{
+    std::vector<std::thread> th;
+    std::vector<Failure> err(parts, Failure{R4WB_OK, ""});
+    auto one = [&](int p) {
+        const uint64_t b = n * (uint64_t)p / (uint64_t)parts, e = n * (uint64_t)(p + 1) / (uint64_t)parts;
+        try { if (e > b) body(p, b, e); }
+        catch (const Failure& f) { err[p] = f; }
+        catch (const std::exception& x) { err[p] = Failure{R4WB_ERR_INVALID_PARAMETER, x.what()}; }
+        catch (...) { err[p] = Failure{R4WB_ERR_INVALID_PARAMETER, "unknown failure"}; }
+    };
+    for (int p = 1; p < parts; ++p) th.emplace_back(one, p);
+    one(0);
+    for (auto& t : th) t.join();
+    for (const Failure& f : err) if (f.code != R4WB_OK) throw f;
+}
 struct r4wb_composer { int device = device_now(); Composer impl; r4wb_composer(uint32_t n, double fs, double sd, uint64_t seed) : impl(n, fs, sd, seed) {} };
 struct r4wb_tracker { int device = device_now(); TrackerBank impl; r4wb_tracker(const r4wb_track_cfg* c, uint32_t n) : impl(c, n) {} };
 
@@ -85,6 +143,26 @@ r4wb_error r4wb_init(int device)
         R4WB_CUDA(cudaFree(nullptr));
     });
 }
+
+r4wb_error r4wb_init_devices(int n_gpus)
+{
+    return guard([&] {
+        require_device();
+        int have = 0, cur = 0;
+        R4WB_CUDA(cudaGetDeviceCount(&have));
+        R4WB_CUDA(cudaGetDevice(&cur));
+        const int n = n_gpus <= 0 ? have : n_gpus;
+        if (n > have) fail(R4WB_ERR_INVALID_PARAMETER, "%d devices requested, %d visible", n, have);
+        for (int d = 0; d < n; ++d) {
+            R4WB_CUDA(cudaSetDevice(d));
+            R4WB_CUDA(cudaFree(nullptr));
+        }
+        R4WB_CUDA(cudaSetDevice(cur));
+        g_n_devices.store(n);
+    });
+}
+
+int r4wb_devices_initialised(void) { return g_n_devices.load(); }
 
 r4wb_error r4wb_device_count(int* n)
 {
@@ -154,6 +232,35 @@ r4wb_error r4wb_scenario_generate_block(r4wb_scenario* h, uint64_t n, void* dst,
 r4wb_error r4wb_scenario_generate(r4wb_scenario* h, uint64_t first, uint64_t n, void* dst, r4wb_mem where, r4wb_fmt fmt)
 {
     if (!h) { t_error = "handle is NULL"; return R4WB_ERR_NULL_POINTER; }
+    const int nd = g_n_devices.load();
+    const uint64_t B = h->impl.block_size();
+    if (nd > 1 && current_stream() == nullptr && where == R4WB_MEM_HOST && dst && B && n >= (uint64_t)nd * 64 * B && first <= h->impl.total_samples() &&
+        n <= h->impl.total_samples() - first && (unsigned)fmt <= (unsigned)R4WB_FMT_CU8) {
+        // time segments on 1 ms block boundaries, one per device, each straight into its slice of the caller's buffer
+        const r4wb_error rc = guard([&] {
+            const uint64_t b0 = (first + B - 1) / B, b1 = (first + n) / B;       // whole blocks inside the range
+            std::vector<double> pw(nd, 0.0);
+            const size_t bps = fmt_bytes(fmt);
+            if (h->peers.size() < (size_t)nd) h->peers.resize(nd);
+            run_sharded(nd, b1 - b0, [&](int p, uint64_t lo, uint64_t hi) {
+                R4WB_CUDA(cudaSetDevice(p));
+                const uint64_t s0 = p == 0 ? first : (b0 + lo) * B, s1 = p == nd - 1 ? first + n : (b0 + hi) * B;
+                Scenario* sc = &h->impl;
+                if (p != h->device) {
+                    if (!h->peers[p]) h->peers[p].reset(new Scenario(h->impl.config()));
+                    sc = h->peers[p].get();
+                }
+                sc->generate(s0, s1 - s0, static_cast<unsigned char*>(dst) + (size_t)(s0 - first) * bps, R4WB_MEM_HOST, fmt);
+                pw[p] = sc->last_power_sum();
+            });
+            double t = 0.0;
+            for (double v : pw) t += v;
+            h->multi_power = t;
+        });
+        cudaSetDevice(h->device);
+        return rc;
+    }
+    h->multi_power = -1.0;
     return guard_on(h, [&] { h->impl.generate(first, n, dst, where, fmt); });
 }
 
@@ -177,6 +284,7 @@ r4wb_error r4wb_scenario_write_file(r4wb_scenario* h, const char* path, r4wb_fmt
 r4wb_error r4wb_scenario_last_power_sum(const r4wb_scenario* h, double* power_sum)
 {
     if (!h || !power_sum) { t_error = "handle/power_sum is NULL"; return R4WB_ERR_NULL_POINTER; }
+    if (h->multi_power >= 0.0) { *power_sum = h->multi_power; return R4WB_OK; }
     return guard_on(h, [&] { *power_sum = const_cast<r4wb_scenario*>(h)->impl.last_power_sum(); });
 }
 
@@ -284,13 +392,14 @@ void r4wb_pcps_destroy(r4wb_pcps* h) { delete h; }
 r4wb_error r4wb_pcps_set_doppler_range(r4wb_pcps* h, double max_hz, double step_hz)
 {
     if (!h) { t_error = "handle is NULL"; return R4WB_ERR_NULL_POINTER; }
-    return guard_on(h, [&] { h->impl.set_doppler_range(max_hz, step_hz); });
+    return guard_on(h, [&] { h->impl.set_doppler_range(max_hz, step_hz); h->dmax = max_hz; h->dstep = step_hz; });
 }
 
 r4wb_error r4wb_pcps_set_threshold(r4wb_pcps* h, double threshold)
 {
     if (!h) { t_error = "handle is NULL"; return R4WB_ERR_NULL_POINTER; }
     h->impl.set_threshold(threshold);
+    h->threshold = threshold;
     return R4WB_OK;
 }
 
@@ -298,12 +407,19 @@ r4wb_error r4wb_pcps_set_coherent_periods(r4wb_pcps* h, uint64_t periods)
 {
     if (!h) { t_error = "handle is NULL"; return R4WB_ERR_NULL_POINTER; }
     h->impl.set_coherent_periods(periods);
+    h->coherent = periods;
     return R4WB_OK;
 }
 
 uint64_t r4wb_pcps_fft_size(const r4wb_pcps* h) { return h ? h->impl.fft_size() : 0; }
 uint32_t r4wb_pcps_num_doppler_bins(const r4wb_pcps* h) { return h ? h->impl.num_bins() : 0; }
-uint64_t r4wb_pcps_guard_count(const r4wb_pcps* h) { return h ? h->impl.guard_count() : 0; }
+uint64_t r4wb_pcps_guard_count(const r4wb_pcps* h)
+{
+    if (!h) return 0;
+    uint64_t n = h->impl.guard_count();
+    for (const auto& p : h->peers) if (p) n += p->guard_count();
+    return n;
+}
 
 r4wb_error r4wb_pcps_set_profiling(r4wb_pcps* h, int enabled)
 {
@@ -332,6 +448,32 @@ r4wb_error r4wb_pcps_acquire_batch(r4wb_pcps* h, const void* input, r4wb_fmt fmt
 {
     if (!h || !input || !codes || !out) { t_error = "NULL argument"; return R4WB_ERR_NULL_POINTER; }
     std::lock_guard<std::mutex> lk(h->mu);
+    const int nd = g_n_devices.load();
+    if (nd > 1 && current_stream() == nullptr && n_snapshots >= (uint64_t)(2 * nd) && (fmt == R4WB_FMT_CF32 || fmt == R4WB_FMT_CF64)) {
+        // snapshots are independent: device p takes a contiguous share and writes its rows of `out` itself
+        const r4wb_error rc = guard([&] {
+            const size_t bps = fmt_bytes(fmt);
+            if (h->peers.size() < (size_t)nd) h->peers.resize(nd);
+            run_sharded(nd, n_snapshots, [&](int p, uint64_t lo, uint64_t hi) {
+                R4WB_CUDA(cudaSetDevice(p));
+                Pcps& eng = h->on(p);
+                const unsigned char* src = static_cast<const unsigned char*>(input) + (size_t)lo * snapshot_stride * bps;
+                r4wb_acq_result* dst = out + (size_t)lo * n_codes;
+                if (where == R4WB_MEM_HOST || p == h->device) {
+                    eng.acquire_batch(src, fmt, where, hi - lo, snapshot_stride, n_input, codes, code_len, prns, n_codes, dst);
+                } else {
+                    // device-resident input lives on the handle's device: the share is copied over NVLink first
+                    const size_t bytes = ((size_t)(hi - lo - 1) * snapshot_stride + n_input) * bps;
+                    DevBuf<unsigned char> tmp;
+                    tmp.reserve(bytes);
+                    R4WB_CUDA(cudaMemcpyPeer(tmp.p, p, src, h->device, bytes));
+                    eng.acquire_batch(tmp.p, fmt, R4WB_MEM_DEVICE, hi - lo, snapshot_stride, n_input, codes, code_len, prns, n_codes, dst);
+                }
+            });
+        });
+        cudaSetDevice(h->device);
+        return rc;
+    }
     return guard_on(h, [&] { h->impl.acquire_batch(input, fmt, where, n_snapshots, snapshot_stride, n_input, codes, code_len, prns, n_codes, out); });
 }
 

@@ -270,6 +270,7 @@ public:
     explicit Scenario(const r4wb_scenario_cfg& cfg);
     ~Scenario();
 
+    const r4wb_scenario_cfg& config() const { return md_.cfg; }      // what the handle was created from (satellite array owned by the model)
     uint64_t total_samples() const { return md_.sc.total; }
     uint64_t block_size() const { return md_.sc.B; }
     uint64_t current_sample() const { return current_; }

@@ -47,9 +47,10 @@ __device__ __forceinline__ void lat_store_pair(void* out, uint64_t o, float4 v) 
 }
 
 constexpr int kLatThreads = kSynthThreads;
+constexpr int kLatCtasPerSm = 3;      // 80 registers per thread, ~64 KB of shared memory per CTA (8 satellites): 24 warps per SM
 
 struct LatSmem {
-    float* ytab2; float* taps; uint8_t* clsn; uint32_t* per; uint32_t* W; uint4* ent; TileRec* trec;
+    float* ytab2; float* taps; uint8_t* clsn; uint32_t* W; uint4* ent; TileRec* trec;
 };
 
 __host__ __device__ inline size_t lat_smem_layout(uint32_t n_sats, uint32_t ystride, const LatConst& L, LatSmem* m, unsigned char* raw)
@@ -59,22 +60,23 @@ __host__ __device__ inline size_t lat_smem_layout(uint32_t n_sats, uint32_t ystr
     const size_t o_ytab = take((size_t)ystride * kLatYStride * 4);
     const size_t o_taps = take(64 * 4);
     const size_t o_cls = take((size_t)8 * L.cls_len);
-    const size_t o_per = take((size_t)n_sats * kPerWords * 4);
     const size_t o_w = take((size_t)n_sats * lat_n_words(L) * 4);
     const size_t o_ent = take((size_t)2 * n_sats * lat_n_ent(L) * 16);
     const size_t o_rec = take((size_t)2 * n_sats * sizeof(TileRec));
     if (m) {
         m->ytab2 = reinterpret_cast<float*>(raw + o_ytab); m->taps = reinterpret_cast<float*>(raw + o_taps);
-        m->clsn = raw + o_cls; m->per = reinterpret_cast<uint32_t*>(raw + o_per); m->W = reinterpret_cast<uint32_t*>(raw + o_w);
+        m->clsn = raw + o_cls; m->W = reinterpret_cast<uint32_t*>(raw + o_w);
         m->ent = reinterpret_cast<uint4*>(raw + o_ent); m->trec = reinterpret_cast<TileRec*>(raw + o_rec);
     }
     return off;
 }
 
+constexpr size_t kLatMaxSmem = 110 * 1024;     // beyond ~74 KB fewer than kLatCtasPerSm CTAs fit an SM (more than 8 satellites)
+
 size_t lat_smem_bytes(uint32_t n_sats, uint32_t ystride, const LatConst& L) { return lat_smem_layout(n_sats, ystride, L, nullptr, nullptr); }
 
 template <int K, int FMT>
-__global__ void __launch_bounds__(kLatThreads, 2) k_synth_lat(SynthArgs a)
+__global__ void __launch_bounds__(kLatThreads, kLatCtasPerSm) k_synth_lat(SynthArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     LatSmem sm;
@@ -94,7 +96,6 @@ __global__ void __launch_bounds__(kLatThreads, 2) k_synth_lat(SynthArgs a)
     for (uint32_t k = tid; k < 64; k += kLatThreads) sm.taps[k] = a.taps[k];
     for (uint32_t k = tid; k < (8u * L.cls_len + 15u) / 16u; k += kLatThreads)
         reinterpret_cast<uint4*>(sm.clsn)[k] = reinterpret_cast<const uint4*>(a.clsn)[k];
-    for (uint32_t k = tid; k < a.n_sats * kPerWords; k += kLatThreads) sm.per[k] = a.perbits[k];
 
     float pow_acc = 0.0f;
     const uint32_t n_tiles = a.tb_count;                                       // one tile = one block
@@ -113,7 +114,7 @@ __global__ void __launch_bounds__(kLatThreads, 2) k_synth_lat(SynthArgs a)
         for (uint32_t s = tid >> 5; s < a.n_sats; s += kLatThreads / 32) {
             const uint32_t ep0 = __ldg(&g_recs[(size_t)t * a.n_sats + s].lat.ep0);
             const SatCode cd = a.satcode[s];
-            for (uint32_t w = lane; w < n_w; w += 32) sm.W[s * n_w + w] = sign_word_ep(sm.per + s * kPerWords, ep0 & 0xffu, ep0 >> 8, w, cd);
+            for (uint32_t w = lane; w < n_w; w += 32) sm.W[s * n_w + w] = sign_word_ep(a.perbits + s * kPerWords, ep0 & 0xffu, ep0 >> 8, w, cd);
         }
     };
     auto build_entries = [&](uint32_t buf) {
@@ -215,7 +216,7 @@ static void launch_lat_t(const SynthArgs& a, int grid, size_t smem, cudaStream_t
 {
     static bool attr_done = false;
     if (!attr_done) {
-        R4WB_CUDA(cudaFuncSetAttribute(k_synth_lat<K, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+        R4WB_CUDA(cudaFuncSetAttribute(k_synth_lat<K, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLatMaxSmem));
         attr_done = true;
     }
     k_synth_lat<K, FMT><<<grid, kLatThreads, smem, st>>>(a);
@@ -240,13 +241,21 @@ bool lat_supported(const SynthArgs& a)
 {
     if (a.lat.q == 0 || a.n_sats == 0 || a.n_sats > (uint32_t)kLatMaxSats || a.tiles_per_block != 1) return false;
     if (a.lat.K != 4 && a.lat.K != 5) return false;
-    return lat_smem_bytes(a.n_sats, a.ystride, a.lat) <= 110 * 1024;
+    return lat_smem_bytes(a.n_sats, a.ystride, a.lat) <= kLatMaxSmem;
 }
 
 void launch_synth_lat(const SynthArgs& a, r4wb_fmt fmt, int sm_count, cudaStream_t st)
 {
     const size_t smem = lat_smem_bytes(a.n_sats, a.ystride, a.lat);
-    const int grid = (int)std::max<uint32_t>(1u, std::min<uint32_t>(a.tb_count, (uint32_t)sm_count * 2u));
+    static int per_sm[kLatMaxSats + 1] = {};
+    int& ps = per_sm[a.n_sats];
+    if (!ps) {
+        int nb = 0;
+        R4WB_CUDA(cudaFuncSetAttribute(k_synth_lat<5, R4WB_FMT_CF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLatMaxSmem));
+        R4WB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_synth_lat<5, R4WB_FMT_CF32>, kLatThreads, smem));
+        ps = std::max(1, nb);
+    }
+    const int grid = (int)std::max<uint32_t>(1u, std::min<uint32_t>(a.tb_count, (uint32_t)(sm_count * ps)));
     if (a.lat.K == 5) launch_lat_k<5>(a, fmt, grid, smem, st);
     else launch_lat_k<4>(a, fmt, grid, smem, st);
 }

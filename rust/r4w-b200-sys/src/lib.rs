@@ -229,6 +229,8 @@ extern "C" {
     pub fn r4wb_version() -> *const c_char;
     pub fn r4wb_last_error() -> *const c_char;
     pub fn r4wb_init(device: c_int) -> c_int;
+    pub fn r4wb_init_devices(n_gpus: c_int) -> c_int;
+    pub fn r4wb_devices_initialised() -> c_int;
     pub fn r4wb_device_count(n: *mut c_int) -> c_int;
     pub fn r4wb_set_stream(cuda_stream: *mut c_void) -> c_int;
     pub fn r4wb_host_alloc(p: *mut *mut c_void, bytes: usize) -> c_int;

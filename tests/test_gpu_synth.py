@@ -539,6 +539,7 @@ def test_antenna_patterns_match_oracle(gpu, oracle, kind):
     cfg.output.duration_s = 0.02
     sc = gpu.GnssScenario(cfg, noise=False)
     want = oracle.OracleScenario(cfg, noise=False).generate_range(0, 100_000)
+    status = sc.satellite_status()                        # at current_sample = 0; generate() leaves the scenario done
     assert _relrms(sc.generate(), want) <= TOL
-    for a, b in zip(sc.satellite_status(), oracle.OracleScenario(cfg).status()):
+    for a, b in zip(status, oracle.OracleScenario(cfg).status()):
         assert a.antenna_gain_dbi == pytest.approx(b.antenna_gain_dbi, abs=1e-9) and a.cn0_dbhz == pytest.approx(b.cn0_dbhz, abs=1e-6)
