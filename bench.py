@@ -212,6 +212,44 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------- GPU arm
+def numa_bind(local: int):
+    """Pin this rank's host threads and its future host allocations (the pinned e2e buffers) to the NUMA node of its GPU:
+    eight ranks copying device -> host through one socket's memory controllers is what capped the aggregate D2H rate in
+    round 1.  Best effort: a container may not allow the CPUs / memory nodes of the other socket; what happened is reported."""
+    info = {"gpu": local}
+    try:
+        import ctypes
+        import torch
+        pr = torch.cuda.get_device_properties(local)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        base = f"/sys/bus/pci/devices/{bdf}"
+        node = int(open(base + "/numa_node").read().strip())
+        cpus = open(base + "/local_cpulist").read().strip()
+        info.update({"pci": bdf, "numa_node": node, "local_cpulist": cpus})
+        want = set()
+        for part in cpus.split(","):
+            if "-" in part:
+                a, b = part.split("-"); want.update(range(int(a), int(b) + 1))
+            elif part:
+                want.add(int(part))
+        allowed = os.sched_getaffinity(0)
+        use = want & allowed
+        if use:
+            os.sched_setaffinity(0, use)
+            info["cpu_affinity"] = f"{len(use)} local CPUs"
+        else:
+            info["cpu_affinity"] = f"unchanged ({len(allowed)} allowed CPUs, none local to the GPU)"
+        if node >= 0:
+            libc = ctypes.CDLL(None, use_errno=True)
+            mask = ctypes.c_ulong(1 << node)
+            MPOL_PREFERRED = 1
+            rc = libc.syscall(238, MPOL_PREFERRED, ctypes.byref(mask), ctypes.c_ulong(64))      # set_mempolicy (x86-64)
+            info["mempolicy"] = "preferred node %d" % node if rc == 0 else "set_mempolicy failed (errno %d)" % ctypes.get_errno()
+    except Exception as e:                                                                   # noqa: BLE001
+        info["error"] = repr(e)[:120]
+    return info
+
+
 def fp32_peak():
     """Measured FP32 FMA rate of this box (tools/ubench/fp32_peak, built by __graft_entry__.build()) or the nominal figure."""
     exe = os.path.join(ROOT, "tools", "ubench", "fp32_peak")
@@ -235,6 +273,7 @@ def run_b200(args):
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    numa = numa_bind(local) if not args.no_numa_bind else {"gpu": local, "skipped": True}
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -605,6 +644,7 @@ def run_b200(args):
             "avg_power": {"value": pw_sum / max(pw_cnt, 1), "samples": pw_cnt, "note": "sum |s|^2 / count all-reduced over the ranks (the CLI's avg-power line)"},
             "gpu_launches": int(M["launches"]),
             "clocks": M["clocks"],
+            "numa_rank0": numa,
         }
         if per_config:
             line["per_config"] = per_config
@@ -655,6 +695,7 @@ def main():
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle comparison of random acquisition results")
     ap.add_argument("--no-block-api", action="store_true", help="skip the generate_block loop leg")
     ap.add_argument("--block-api-seconds", type=float, default=10.0)
+    ap.add_argument("--no-numa-bind", action="store_true", help="leave CPU affinity / memory policy alone")
     ap.add_argument("--track", action="store_true", help="add the tracking-channel leg (SURVEY.md section 8 f2)")
     args = ap.parse_args()
     quiet_stdout()

@@ -97,6 +97,25 @@ def test_clean_anchor_values(gpu, oracle):
         assert (int(r.code_phase), int(round((r.doppler_hz + 5000.0) / 250.0))) == (lag, dbin), prn
 
 
+def test_acquire_grid_e1c_size_matches_oracle(gpu, oracle):
+    """acquire_grid (acquisition.rs:199-249) at the E1C shape: fft_size 32 768, 41 x 20 000 surface, noisy 34 dB-Hz input —
+    every cell against the oracle's f64 surface, the same first maximum"""
+    cfg = _cfg("e1c_8prn_60s_cn34_orbital")
+    x = oracle.OracleScenario(cfg, noise=True).generate_range(40_000, 20000)                  # f64
+    a = gpu.PcpsAcquisition(20000, 5e6).with_doppler_range(5000.0, 250.0)
+    o = oracle.OraclePcps(20000, 5e6).with_doppler_range(5000.0, 250.0)
+    assert a.fft_size() == 32768
+    for prn in (3, 16):
+        rep = gpu.e1c_replica(prn, 5e6, 20000)
+        g = a.acquire_grid(x, rep)
+        og, olin = o.acquire_grid(x, rep)
+        assert g.power.shape == og.shape == (41, 20000)
+        assert np.max(np.abs(g.power - og)) <= 1e-9 * np.max(og)
+        dop, lag, best = g.find_peak()
+        d, p = divmod(olin, 20000)
+        assert (lag, dop) == (float(p), -5000.0 + 250.0 * d) and best == pytest.approx(float(og[d, p]), rel=1e-9)
+
+
 def test_default_doppler_grid_and_cf64_input(gpu, oracle):
     """reference defaults (+-5 kHz / 500 Hz = 21 bins, threshold 2.5) and Complex64 input as the Rust API passes it"""
     cfg = _cfg("e1c_8prn_20s_clean")

@@ -122,3 +122,37 @@ def test_other_sample_rates(gpu, oracle, monkeypatch, fs, periodic):
         assert _relrms(x[n - m:], want) <= TOL
         want = oracle.OracleScenario(cfg, noise=False).generate_range(first, L)
         assert _relrms(x[:L], want) <= TOL
+
+
+def test_periodic_kernel_matches_oracle_across_the_file(gpu, oracle, monkeypatch):
+    """The benchmarked static configuration at 64 period-aligned offsets over the whole 20 s file — half of them the periods in
+    which a satellite's f64 carrier phase crosses a binade (a new PhaseSegment of the exact-phase emulation),
+    the rest random.  Each offset is rendered as 40 periods (so the period-resident kernels take it) and the middle period
+    is compared with the oracle."""
+    monkeypatch.setenv("R4WB_SYNTH_PERIODIC", "1")
+    cfg = _cfg("e1c_8prn_20s_clean")
+    L, fs = 20000, 5e6
+    n_periods = int(cfg.output.duration_s * fs) // L
+    rng = np.random.default_rng(7)
+    cross = []
+    for s in cfg.satellites:                                   # |phase| = 2 pi |f| m / fs reaches 2^k at sample m
+        k = 4
+        while True:
+            m = (2.0 ** k) * fs / (2 * np.pi * abs(s.doppler_hz))
+            if m >= n_periods * L:
+                break
+            cross.append(int(m) // L)
+            k += 1
+    cross = sorted(set(p for p in cross if 20 <= p < n_periods - 20))
+    picks = list(rng.choice(cross, size=min(32, len(cross)), replace=False)) + list(rng.integers(20, n_periods - 20, 64))
+    picks = sorted(set(int(p) for p in picks))[:64]
+    assert len(picks) >= 48
+    sc = gpu.GnssScenario(cfg, noise=False)
+    orc = oracle.OracleScenario(cfg, noise=False, threads=8)
+    worst = 0.0
+    for p in picks:
+        got = sc.generate_range((p - 20) * L, 40 * L)
+        assert sc.last_path() == 1
+        want = orc.generate_range(p * L, L)
+        worst = max(worst, _relrms(got[20 * L:21 * L], want))
+    assert worst <= 1e-5, worst
