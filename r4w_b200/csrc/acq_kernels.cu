@@ -249,10 +249,9 @@ template <typename T, int MODE>
 static void launch_fwd_t(const AcqGeom& g, uint32_t rows, const void* input, uint32_t in64, uint64_t stride, uint32_t take,
                          const int8_t* codes, uint64_t code_len, const cx<T>* W, cx<T>* out, cudaStream_t st)
 {
-    static bool attr = false;
-    if (!attr) {
+    static PerDeviceOnce attr;
+    if (attr.first()) {
         R4WB_CUDA(cudaFuncSetAttribute(k_fwd<T, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr = true;
     }
     if (rows == 0) return;
     k_fwd<T, MODE><<<rows << g.logF, FftThreads<T>::value, fft_smem_bytes<T>(g.logM), st>>>(g, input, in64, stride, take, codes, code_len, W, out);
@@ -276,10 +275,9 @@ template <typename T>
 void launch_inv_peak(const AcqGeom& g, uint32_t rows, const cx<T>* X, const cx<T>* C, const cx<T>* W, RowPeak* peaks, double* grid,
                      cudaStream_t st)
 {
-    static bool attr = false;
-    if (!attr) {
+    static PerDeviceOnce attr;
+    if (attr.first()) {
         R4WB_CUDA(cudaFuncSetAttribute(k_inv_peak<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr = true;
     }
     const uint64_t items = ((uint64_t)rows * g.P) << g.logF;
     if (items == 0) return;

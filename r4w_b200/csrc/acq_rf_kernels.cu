@@ -389,10 +389,9 @@ static size_t rf_inv_smem() { return (size_t)(rf::kXbufFloats + 2 * rf::kM) * 4;
 void launch_rf_fwd_input(const AcqGeom& g, uint32_t rows, const void* input, uint32_t in64, uint64_t stride, uint32_t take, const cf* W,
                          cf* out, cudaStream_t st)
 {
-    static bool attr = false;
-    if (!attr) {
+    static PerDeviceOnce attr;
+    if (attr.first()) {
         R4WB_CUDA(cudaFuncSetAttribute(k_rf_fwd<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rf_fwd_smem()));
-        attr = true;
     }
     if (rows == 0) return;
     k_rf_fwd<0><<<rows, rf::kNT, rf_fwd_smem(), st>>>(g, input, in64, stride, take, nullptr, 0, W, out);
@@ -402,10 +401,9 @@ void launch_rf_fwd_input(const AcqGeom& g, uint32_t rows, const void* input, uin
 void launch_rf_fwd_codes(const AcqGeom& g, uint32_t n_codes, const int8_t* codes, uint64_t code_len, uint32_t take, const cf* W, cf* out,
                          cudaStream_t st)
 {
-    static bool attr = false;
-    if (!attr) {
+    static PerDeviceOnce attr;
+    if (attr.first()) {
         R4WB_CUDA(cudaFuncSetAttribute(k_rf_fwd<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rf_fwd_smem()));
-        attr = true;
     }
     if (n_codes == 0) return;
     k_rf_fwd<1><<<n_codes, rf::kNT, rf_fwd_smem(), st>>>(g, nullptr, 0, 0, take, codes, code_len, W, out);
@@ -423,20 +421,18 @@ bool rf_use_tmem()
 void launch_rf_inv_peak(const AcqGeom& g, uint32_t rows, const cf* X, const cf* C, const cf* W, RowPeak* peaks, cudaStream_t st)
 {
     if (rf_use_tmem()) {
-        static bool attr_tm = false;
-        if (!attr_tm) {
+        static PerDeviceOnce attr_tm;
+        if (attr_tm.first()) {
             R4WB_CUDA(cudaFuncSetAttribute(k_rf_inv_peak_tm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rf_inv_smem()));
-            attr_tm = true;
         }
         if (rows == 0) return;
         k_rf_inv_peak_tm<<<rows, rf::kNT, rf_inv_smem(), st>>>(g, X, C, W, peaks);
         R4WB_LAUNCH_CHECK();
         return;
     }
-    static bool attr = false;
-    if (!attr) {
+    static PerDeviceOnce attr;
+    if (attr.first()) {
         R4WB_CUDA(cudaFuncSetAttribute(k_rf_inv_peak, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rf_inv_smem()));
-        attr = true;
     }
     const uint64_t items = (uint64_t)rows * g.P;
     if (items == 0) return;

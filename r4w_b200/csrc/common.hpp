@@ -48,6 +48,19 @@ inline void count_launch(int n = 1) { g_kernel_launches.fetch_add((uint64_t)n, s
         R4WB_CUDA(cudaGetLastError());      \
     } while (0)
 
+// One-time per-DEVICE set-up of a kernel (function attributes such as the dynamic shared-memory limit belong to the device's
+// context, and a process may drive several devices: r4wb_init_devices).  `static PerDeviceOnce once; if (once.first()) ...`
+struct PerDeviceOnce {
+    std::atomic<unsigned long long> mask{0};
+    bool first()
+    {
+        int d = 0;
+        cudaGetDevice(&d);
+        const unsigned long long bit = 1ull << (d & 63);
+        return !(mask.fetch_or(bit) & bit);
+    }
+};
+
 template <typename T>
 struct DevBuf {   // owning device allocation, grows on demand
     T* p = nullptr;

@@ -192,6 +192,7 @@ struct SynthArgs {
     const uint32_t* dcode;     // [n_sats][kDirectWords] packed chips, bit = 1 -> -1
     uint32_t any_direct;       // some satellite is rendered by k_synth_direct
     uint32_t max_block_n;      // longest block of the table (grid of k_synth_direct)
+    uint32_t direct_y0;        // first table block (relative to tb_begin) of this k_synth_direct launch slab
     uint32_t out_aligned16;    // out is aligned to two samples of the output format: sample pairs may be stored as one vector
     LatConst lat;              // lattice kernel constants (lat.q = 0: not applicable)
     const uint8_t* clsn;       // [8][lat.cls_len] boundary-age class of sample index n per sub-residue b0 (synth_lattice.cuh)

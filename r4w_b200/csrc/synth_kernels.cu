@@ -14,6 +14,8 @@
 // reference's own f64 expression the kernel evaluates that expression literally (exact path).
 #include <cuda_runtime.h>
 
+#include <algorithm>
+
 #include "synth_lattice.cuh"
 
 namespace r4wb {
@@ -294,7 +296,7 @@ template <typename OutT>
 __global__ void __launch_bounds__(256) k_synth_direct(SynthArgs a)
 {
     __shared__ double s_dp[8];
-    const uint32_t tb = a.tb_begin + blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t tb = a.tb_begin + blockIdx.y + a.direct_y0, i = blockIdx.x * blockDim.x + threadIdx.x;
     const BlockHdr hd = a.hdr[tb];
     const uint64_t m = hd.first + i;
     double dp = 0.0;
@@ -336,10 +338,15 @@ void launch_synth_direct(const SynthArgs& a, r4wb_fmt fmt, cudaStream_t st)
     if (fmt != R4WB_FMT_CF32 && fmt != R4WB_FMT_CF64)
         fail(R4WB_ERR_NOT_SUPPORTED, "GPS L5 / GLONASS satellites are rendered in the float formats only (cf32, cf64)");
     if (a.tb_count == 0 || a.max_block_n == 0) return;
-    const dim3 grid((a.max_block_n + 255) / 256, a.tb_count);
-    if (fmt == R4WB_FMT_CF32) k_synth_direct<float2><<<grid, 256, 0, st>>>(a);
-    else k_synth_direct<double2><<<grid, 256, 0, st>>>(a);
-    R4WB_LAUNCH_CHECK();
+    // gridDim.y is limited to 65 535: long renders go in slabs of table blocks
+    for (uint32_t y0 = 0; y0 < a.tb_count; y0 += 65535u) {
+        SynthArgs b = a;
+        b.direct_y0 = y0;
+        const dim3 grid((a.max_block_n + 255) / 256, std::min<uint32_t>(65535u, a.tb_count - y0));
+        if (fmt == R4WB_FMT_CF32) k_synth_direct<float2><<<grid, 256, 0, st>>>(b);
+        else k_synth_direct<double2><<<grid, 256, 0, st>>>(b);
+        R4WB_LAUNCH_CHECK();
+    }
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -347,10 +354,9 @@ void launch_synth_direct(const SynthArgs& a, r4wb_fmt fmt, cudaStream_t st)
 template <int K, int FMT>
 static void launch_synth_t(const SynthArgs& a, int grid, size_t smem, cudaStream_t st)
 {
-    static bool attr_done = false;
-    if (!attr_done) {
+    static PerDeviceOnce attr_done;
+    if (attr_done.first()) {
         R4WB_CUDA(cudaFuncSetAttribute(k_synth<K, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_done = true;
     }
     k_synth<K, FMT><<<grid, kThreads, smem, st>>>(a);
     R4WB_LAUNCH_CHECK();

@@ -11,6 +11,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 
 #include "synth_lattice.cuh"
 
@@ -47,7 +48,7 @@ __device__ __forceinline__ void lat_store_pair(void* out, uint64_t o, float4 v) 
 }
 
 constexpr int kLatThreads = kSynthThreads;
-constexpr int kLatCtasPerSm = 3;      // 80 registers per thread, ~64 KB of shared memory per CTA (8 satellites): 24 warps per SM
+constexpr int kLatCtasPerSm = 2;      // 16 warps per SM; a third CTA fits (80 registers, 64 KB) but measured 5 % slower: the kernel is bound by shared-memory wavefronts and issue slots, not latency
 
 struct LatSmem {
     float* ytab2; float* taps; uint8_t* clsn; uint32_t* W; uint4* ent; TileRec* trec;
@@ -214,10 +215,9 @@ __global__ void __launch_bounds__(kLatThreads, kLatCtasPerSm) k_synth_lat(SynthA
 template <int K, int FMT>
 static void launch_lat_t(const SynthArgs& a, int grid, size_t smem, cudaStream_t st)
 {
-    static bool attr_done = false;
-    if (!attr_done) {
+    static PerDeviceOnce attr_done;
+    if (attr_done.first()) {
         R4WB_CUDA(cudaFuncSetAttribute(k_synth_lat<K, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLatMaxSmem));
-        attr_done = true;
     }
     k_synth_lat<K, FMT><<<grid, kLatThreads, smem, st>>>(a);
     R4WB_LAUNCH_CHECK();
@@ -247,13 +247,14 @@ bool lat_supported(const SynthArgs& a)
 void launch_synth_lat(const SynthArgs& a, r4wb_fmt fmt, int sm_count, cudaStream_t st)
 {
     const size_t smem = lat_smem_bytes(a.n_sats, a.ystride, a.lat);
-    static int per_sm[kLatMaxSats + 1] = {};
-    int& ps = per_sm[a.n_sats];
+    static std::atomic<int> per_sm[kLatMaxSats + 1];
+    int ps = per_sm[a.n_sats].load();
     if (!ps) {
         int nb = 0;
         R4WB_CUDA(cudaFuncSetAttribute(k_synth_lat<5, R4WB_FMT_CF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLatMaxSmem));
         R4WB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_synth_lat<5, R4WB_FMT_CF32>, kLatThreads, smem));
         ps = std::max(1, nb);
+        per_sm[a.n_sats].store(ps);
     }
     const int grid = (int)std::max<uint32_t>(1u, std::min<uint32_t>(a.tb_count, (uint32_t)(sm_count * ps)));
     if (a.lat.K == 5) launch_lat_k<5>(a, fmt, grid, smem, st);

@@ -401,10 +401,9 @@ template <int NS>
 static void launch_periodic_t(const PeriodicArgs& a, cudaStream_t st)
 {
     const size_t smem = (size_t)(kPerThreads / 32) * a.KI * NS * sizeof(float4);
-    static bool attr_done = false;
-    if (!attr_done) {
+    static PerDeviceOnce attr_done;
+    if (attr_done.first()) {
         R4WB_CUDA(cudaFuncSetAttribute(k_synth_periodic<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-        attr_done = true;
     }
     k_synth_periodic<NS><<<a.n_tiles * a.n_chunks, kPerThreads, smem, st>>>(a);
     R4WB_LAUNCH_CHECK();

@@ -262,6 +262,13 @@ void TrackerBank::process(const void* samples, r4wb_fmt fmt, r4wb_mem where, uin
     d_nav_.reserve((size_t)n * nav_cap);
     d_nav_n_.reserve(n);
     const size_t smem = (max_cl + 15u) & ~15u;
+    {   // codes above ~47 K chips need the opt-in dynamic shared-memory limit (code_length is accepted up to 65 536)
+        static PerDeviceOnce once;
+        if (once.first()) {
+            R4WB_CUDA(cudaFuncSetAttribute(k_track<float2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
+            R4WB_CUDA(cudaFuncSetAttribute(k_track<double2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
+        }
+    }
     // cluster size: as many CTAs per channel as keep the whole bank resident (148 SMs), up to the portable maximum of 8
     static int sm_count = 0;
     if (!sm_count) {
