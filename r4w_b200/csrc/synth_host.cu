@@ -739,6 +739,9 @@ double Scenario::write_file(const char* path, r4wb_fmt fmt, uint64_t* samples, u
     double power = 0.0;
     uint64_t done = 0;
     try {
+        // the block table of the whole file once, up front: a table that only ever grows from block 0 (dynamic scenarios) would
+        // otherwise be rebuilt for every segment — prologue work quadratic in the file length
+        if (sc.total > 0) build_canonical_table(md_.table_begin(0), md_.n_blocks());
         for (auto*& p : pin) R4WB_CUDA(cudaMallocHost((void**)&p, (size_t)cap * bps));
         for (uint32_t c = 0; done < sc.total; ++c) {
             const uint64_t n = std::min(seg, sc.total - done);
