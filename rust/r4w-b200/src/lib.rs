@@ -290,15 +290,38 @@ impl Drop for GnssScenario {
 pub struct PcpsAcquisition {
     h: *mut sys::r4wb_pcps,
     code_length: usize,
+    doppler_max_hz: f64,
+    doppler_step_hz: f64,
 }
 unsafe impl Send for PcpsAcquisition {}
 unsafe impl Sync for PcpsAcquisition {}
 
-/// gnss/acquisition.rs:257-286
+/// gnss/acquisition.rs:257-286: the reference's own fields
+#[derive(Debug, Clone)]
 pub struct AcquisitionGrid {
-    pub power: Vec<Vec<f64>>,
+    /// Doppler frequency bins (Hz): `-doppler_max + d * doppler_step`
     pub doppler_bins: Vec<f64>,
-    pub code_length: usize,
+    /// Code phase bins (samples, `0 .. code_length`)
+    pub code_phases: Vec<f64>,
+    /// Correlation power [doppler][code_phase]
+    pub correlation_power: Vec<Vec<f64>>,
+}
+
+impl AcquisitionGrid {
+    /// acquisition.rs:270-285: first strict maximum in scan order -> (doppler_hz, code_phase, power)
+    pub fn find_peak(&self) -> (f64, f64, f64) {
+        let (mut best_power, mut best_doppler, mut best_phase) = (0.0_f64, 0.0, 0.0);
+        for (d, row) in self.correlation_power.iter().enumerate() {
+            for (p, &power) in row.iter().enumerate() {
+                if power > best_power {
+                    best_power = power;
+                    best_doppler = self.doppler_bins[d];
+                    best_phase = self.code_phases[p];
+                }
+            }
+        }
+        (best_doppler, best_phase, best_power)
+    }
 }
 
 impl PcpsAcquisition {
@@ -306,10 +329,12 @@ impl PcpsAcquisition {
     pub fn new(code_length: usize, sample_rate: f64) -> Self {
         let mut h = std::ptr::null_mut();
         check(unsafe { sys::r4wb_pcps_create(code_length as u64, sample_rate, &mut h) });
-        Self { h, code_length }
+        Self { h, code_length, doppler_max_hz: 5000.0, doppler_step_hz: 500.0 }
     }
-    pub fn with_doppler_range(self, max_hz: f64, step_hz: f64) -> Self {
+    pub fn with_doppler_range(mut self, max_hz: f64, step_hz: f64) -> Self {
         check(unsafe { sys::r4wb_pcps_set_doppler_range(self.h, max_hz, step_hz) });
+        self.doppler_max_hz = max_hz;
+        self.doppler_step_hz = step_hz;
         self
     }
     pub fn with_threshold(self, threshold: f64) -> Self {
@@ -356,7 +381,11 @@ impl PcpsAcquisition {
             sys::r4wb_pcps_acquire_grid(self.h, input.as_ptr().cast(), sys::R4WB_FMT_CF64, input.len() as u64, code.as_ptr(), code.len() as u64,
                                         flat.as_mut_ptr(), flat.len() as u64)
         });
-        AcquisitionGrid { power: flat.chunks(self.code_length).map(|r| r.to_vec()).collect(), doppler_bins: Vec::new(), code_length: self.code_length }
+        AcquisitionGrid {
+            doppler_bins: (0..bins).map(|d| -self.doppler_max_hz + d as f64 * self.doppler_step_hz).collect(),      // acquisition.rs:213-220
+            code_phases: (0..self.code_length).map(|i| i as f64).collect(),
+            correlation_power: flat.chunks(self.code_length).map(|r| r.to_vec()).collect(),
+        }
     }
 }
 
