@@ -1,4 +1,4 @@
 mkdir -p gpurun_out
-python tools/prof_prologue.py > gpurun_out/prologue_r2j.log 2>&1; cat gpurun_out/prologue_r2j.log
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/prologue_launches_r2j.csv python tools/prof_prologue.py > /dev/null 2>&1; grep -E "k_phase_q|k_phase_chain" gpurun_out/prologue_launches_r2j.csv | awk -F'","' '{print $5, $NF}' | head -4
-timeout 1200 python -m pytest tests/test_gpu_synth.py -x -q -m gpu -k "600s or prologue or phase or cn0 or lattice or block_loop" 2>&1 | tail -4
+for mix in 0 1; do echo "mix $mix"; R4WB_LAT_MIX_NOISE=$mix python tools/prof_position.py 0 530 2>&1 | tee -a gpurun_out/mix_r2l.log; done
+R4WB_LAT_MIX_NOISE=1 timeout 600 ncu --set full --clock-control none --import-source on --kernel-name-base function -k "regex:k_synth_lat" -c 1 -f -o gpurun_out/prof_lat_r2l python tools/prof_position.py 530 > gpurun_out/ncu_lat_r2l.log 2>&1; echo "ncu rc=$?"
+timeout 900 python -m pytest tests/test_gpu_synth.py -x -q -m gpu -k "lattice or random_access or block_loop or clean_iq or cn0" 2>&1 | tail -4

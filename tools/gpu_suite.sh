@@ -20,9 +20,10 @@ benchN)
         > gpurun_out/bench_$tag.json 2> gpurun_out/bench_$tag.err; echo "bench rc=$?"; tail -c 400 gpurun_out/bench_$tag.json ;;
 launches)
     tag=$1; shift
-    python bench.py --steps 1 --warmup 1 --acq-snapshots 296 --no-cpu-baseline > gpurun_out/plain_$tag.log 2>&1 && \
-    ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/launches_$tag.csv \
-        python bench.py --steps 1 --warmup 1 --acq-snapshots 296 --no-cpu-baseline > gpurun_out/ncu_launches_$tag.log 2>&1
+    F="--steps 2 --warmup 1 --no-per-config --no-cpu-baseline --no-block-api --acq-snapshots 296"
+    python bench.py $F > gpurun_out/plain_$tag.log 2>&1 && \
+    ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file gpurun_out/launches_$tag.csv \
+        python bench.py $F > gpurun_out/ncu_launches_$tag.log 2>&1
     echo "launch list rc=$?"; wc -l gpurun_out/launches_$tag.csv ;;
 ncu)
     tag=$1; regex=$2; shift 2
