@@ -162,38 +162,56 @@ __global__ void __launch_bounds__(kLatThreads, kLatCtasPerSm) k_synth_lat(SynthA
             lat_sat_accumulate<K>(trec[s], L, d8_46, sm.ent + (cur * a.n_sats + s) * n_ent, sm.ytab2, sm.clsn, sm.taps, tid, arA, aiA, arB, aiB);
         }
 
-        // noise, power, store
+        // noise, power, store.  The usual case (block inside the requested range, output aligned to sample pairs) is one straight
+        // run of 16-byte stores; the masked variant for ragged range ends lives in its own loop so that it stays out of the hot
+        // instruction stream (the per-block code path is ~40 KB, close to what the instruction cache holds).
         const uint64_t m0 = hd.first;                                         // even (blocks of 2 q samples, q even)
         const bool plain = a.out_aligned16 && m0 >= a.out_first && m0 + hd.n <= a.out_first + a.out_n && ((m0 - a.out_first) & 1ull) == 0;
+        if (plain) {
 #pragma unroll
-        for (int k = 0; k < K; ++k) {
-            const uint32_t ia = 2u * tid + (uint32_t)(2 * kLatThreads * k);
-            if (ia >= q) continue;
+            for (int k = 0; k < K; ++k) {
+                const uint32_t ia = 2u * tid + (uint32_t)(2 * kLatThreads * k);
+                if (ia >= q) continue;
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const uint32_t i = ia + (h ? q : 0u);
-                const uint64_t m = m0 + i;
-                float4 v = h ? make_float4(arB[k].x, aiB[k].x, arB[k].y, aiB[k].y) : make_float4(arA[k].x, aiA[k].x, arA[k].y, aiA[k].y);
+                for (int h = 0; h < 2; ++h) {
+                    const uint64_t m = m0 + ia + (h ? q : 0u);
+                    float4 v = h ? make_float4(arB[k].x, aiB[k].x, arB[k].y, aiB[k].y) : make_float4(arA[k].x, aiA[k].x, arA[k].y, aiA[k].y);
+                    if (noise_on) {
+                        float2 ga, gb2;
+                        noise_of_counter(m >> 1, PK, ga, gb2);
+                        v.x = fmaf(ga.x, a.noise_std, v.x); v.y = fmaf(ga.y, a.noise_std, v.y);
+                        v.z = fmaf(gb2.x, a.noise_std, v.z); v.w = fmaf(gb2.y, a.noise_std, v.w);
+                    }
+                    pow_acc += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+                    lat_store_pair<FMT>(a.out, m - a.out_first, v);
+                }
+            }
+        } else {
+#pragma unroll 1
+            for (int kk = 0; kk < 2 * K; ++kk) {
+                const int k = kk >> 1, h = kk & 1;
+                const uint32_t ia = 2u * tid + (uint32_t)(2 * kLatThreads * k);
+                if (ia >= q) continue;
+                const uint64_t m = m0 + ia + (h ? q : 0u);
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int c = 0; c < K; ++c)                                   // static register indices: select, do not index
+                    if (c == k) v = h ? make_float4(arB[c].x, aiB[c].x, arB[c].y, aiB[c].y) : make_float4(arA[c].x, aiA[c].x, arA[c].y, aiA[c].y);
                 if (noise_on) {
                     float2 ga, gb2;
                     noise_of_counter(m >> 1, PK, ga, gb2);
                     v.x = fmaf(ga.x, a.noise_std, v.x); v.y = fmaf(ga.y, a.noise_std, v.y);
                     v.z = fmaf(gb2.x, a.noise_std, v.z); v.w = fmaf(gb2.y, a.noise_std, v.w);
                 }
-                if (plain) {
-                    pow_acc += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
-                    lat_store_pair<FMT>(a.out, m - a.out_first, v);
-                } else {
-                    const bool wa = m >= a.out_first && m < a.out_first + a.out_n;
-                    const bool wb = (m + 1) >= a.out_first && (m + 1) < a.out_first + a.out_n;
-                    if (wa) pow_acc += v.x * v.x + v.y * v.y;
-                    if (wb) pow_acc += v.z * v.z + v.w * v.w;
-                    const uint64_t o = m - a.out_first;                       // only meaningful when wa (wraps otherwise)
-                    if (wa && wb && ((o & 1ull) == 0) && a.out_aligned16) lat_store_pair<FMT>(a.out, o, v);
-                    else {
-                        if (wa) lat_store_sample<FMT>(a.out, o, v.x, v.y);
-                        if (wb) lat_store_sample<FMT>(a.out, o + 1, v.z, v.w);
-                    }
+                const bool wa = m >= a.out_first && m < a.out_first + a.out_n;
+                const bool wb = (m + 1) >= a.out_first && (m + 1) < a.out_first + a.out_n;
+                if (wa) pow_acc += v.x * v.x + v.y * v.y;
+                if (wb) pow_acc += v.z * v.z + v.w * v.w;
+                const uint64_t o = m - a.out_first;                           // only meaningful when wa (wraps otherwise)
+                if (wa && wb && ((o & 1ull) == 0) && a.out_aligned16) lat_store_pair<FMT>(a.out, o, v);
+                else {
+                    if (wa) lat_store_sample<FMT>(a.out, o, v.x, v.y);
+                    if (wb) lat_store_sample<FMT>(a.out, o + 1, v.z, v.w);
                 }
             }
         }
