@@ -108,14 +108,31 @@ __global__ void __launch_bounds__(kLatThreads, kLatCtasPerSm) k_synth_lat(SynthA
     auto load_rec = [&](uint32_t tile) {
         return (tile < n_tiles && tid < rec_f4) ? __ldg(recs + (size_t)tile * a.tiles_per_block * rec_f4 + tid) : make_float4(0.f, 0.f, 0.f, 0.f);
     };
-    // sign words of block `t` (the table origin hb comes straight from the record in global memory: L2-resident, prefetched)
+    // Sign words of a block: a warp takes a satellite (two when there are more than eight), its lanes the words — no index
+    // division.  The table origin `ep0` of the warp's satellites is fetched from the records in global memory one block ahead
+    // (registers), the satellites' code structures once per kernel, so the prologue of a block waits for no global load.
     const TileRec* g_recs = a.tiles + (size_t)a.tb_begin * a.tiles_per_block * a.n_sats;
-    // (a warp takes a satellite, its lanes the words: no index division)
-    auto build_words = [&](uint32_t t) {
-        for (uint32_t s = tid >> 5; s < a.n_sats; s += kLatThreads / 32) {
-            const uint32_t ep0 = __ldg(&g_recs[(size_t)t * a.n_sats + s].lat.ep0);
-            const SatCode cd = a.satcode[s];
-            for (uint32_t w = lane; w < n_w; w += 32) sm.W[s * n_w + w] = sign_word_ep(a.perbits + s * kPerWords, ep0 & 0xffu, ep0 >> 8, w, cd);
+    constexpr uint32_t kWarps = kLatThreads / 32, kSatsPerWarp = (kLatMaxSats + kWarps - 1) / kWarps;
+    SatCode my_cd[kSatsPerWarp];
+#pragma unroll
+    for (uint32_t u = 0; u < kSatsPerWarp; ++u) {
+        const uint32_t s = (tid >> 5) + u * kWarps;
+        my_cd[u] = a.satcode[s < a.n_sats ? s : 0];
+    }
+    auto load_ep0 = [&](uint32_t t, uint32_t (&ep)[kSatsPerWarp]) {
+#pragma unroll
+        for (uint32_t u = 0; u < kSatsPerWarp; ++u) {
+            const uint32_t s = (tid >> 5) + u * kWarps;
+            ep[u] = (t < n_tiles && s < a.n_sats) ? __ldg(&g_recs[(size_t)t * a.n_sats + s].lat.ep0) : 0u;
+        }
+    };
+    auto build_words = [&](const uint32_t (&ep)[kSatsPerWarp]) {
+#pragma unroll
+        for (uint32_t u = 0; u < kSatsPerWarp; ++u) {
+            const uint32_t s = (tid >> 5) + u * kWarps;
+            if (s >= a.n_sats) break;
+            for (uint32_t w = lane; w < n_w; w += 32)
+                sm.W[s * n_w + w] = sign_word_ep(a.perbits + s * kPerWords, ep[u] & 0xffu, ep[u] >> 8, w, my_cd[u]);
         }
     };
     auto build_entries = [&](uint32_t buf) {
@@ -127,13 +144,17 @@ __global__ void __launch_bounds__(kLatThreads, kLatCtasPerSm) k_synth_lat(SynthA
     uint32_t tile = blockIdx.x;
     {
         const float4 r0 = load_rec(tile);
+        uint32_t ep_first[kSatsPerWarp];
+        load_ep0(tile, ep_first);
         if (tid < rec_f4) reinterpret_cast<float4*>(sm.trec)[tid] = r0;
         __syncthreads();                                                       // kernel-lifetime tables in place
-        if (tile < n_tiles) build_words(tile);
+        if (tile < n_tiles) build_words(ep_first);
         __syncthreads();
         if (tile < n_tiles) build_entries(0);
     }
     float4 pre = load_rec(tile + gridDim.x);
+    uint32_t ep_next[kSatsPerWarp];
+    load_ep0(tile + gridDim.x, ep_next);
 
     for (uint32_t it = 0; tile < n_tiles; tile += gridDim.x, ++it) {
         const uint32_t cur = it & 1u, nxt = cur ^ 1u;
@@ -143,7 +164,8 @@ __global__ void __launch_bounds__(kLatThreads, kLatCtasPerSm) k_synth_lat(SynthA
         __syncthreads();
         if (tid < rec_f4) reinterpret_cast<float4*>(sm.trec + nxt * a.n_sats)[tid] = pre;
         pre = load_rec(tile + 2u * gridDim.x);
-        if (has_next) build_words(tile + gridDim.x);
+        if (has_next) build_words(ep_next);
+        load_ep0(tile + 2u * gridDim.x, ep_next);
         __syncthreads();
         if (has_next) build_entries(nxt);
 
