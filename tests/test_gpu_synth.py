@@ -187,6 +187,30 @@ def test_lattice_kernel_equals_general_kernel(gpu, monkeypatch, name, first, n):
     assert np.max(np.abs(a - b)) < 1e-6 * np.max(np.abs(a)) and _relrms(a, b) < 5e-7   # the signal parts differ by f32 rounding only
 
 
+def test_whole_600s_file_lattice_equals_general_kernel(gpu, monkeypatch):
+    """BASELINE config 5 at full size (3e9 samples, noise off): every sample of the lattice kernel's render against k_synth's —
+    two independent evaluations of the reference's chip index (lattice bins + resolved disputed oversamples vs per-sample NCO
+    + literal re-evaluation), compared on the device in 1e8-sample pieces"""
+    import torch
+    cfg = _cfg("e1c_8prn_600s_cn34_orbital")
+    n1 = 100_000_000
+    a_sc = gpu.GnssScenario(cfg, noise=False)
+    monkeypatch.setenv("R4WB_SYNTH_LATTICE", "0")
+    b_sc = gpu.GnssScenario(cfg, noise=False)
+    total = a_sc.total_samples()
+    assert total == 3_000_000_000
+    a = torch.empty(n1, dtype=torch.complex64, device="cuda")
+    b = torch.empty(n1, dtype=torch.complex64, device="cuda")
+    worst, num, den = 0.0, 0.0, 0.0
+    for first in range(0, total, n1):
+        a_sc.generate_device(first, n1, a)
+        b_sc.generate_device(first, n1, b)
+        d = torch.view_as_real(a) - torch.view_as_real(b)
+        worst = max(worst, float(d.abs().max()))
+        num += float(d.double().square().sum()); den += float(torch.view_as_real(b).double().square().sum())
+    assert worst < 5e-6 and (num / den) ** 0.5 < 5e-7, (worst, (num / den) ** 0.5)
+
+
 def test_random_access_is_consistent(gpu):
     """any window reproduces the same samples bit for bit (what time-sharding across GPUs relies on), noise included"""
     cfg = _cfg("e1c_8prn_60s_cn34_orbital")
