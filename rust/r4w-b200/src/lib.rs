@@ -436,14 +436,17 @@ impl TrackingChannel {
         check(unsafe { sys::r4wb_track_create(&cfg, 1, &mut h) });
         Self { h, cfg }
     }
-    /// tracking.rs:156 (builders run before the first `process`, so the channel is simply rebuilt)
+    /// tracking.rs:156 (builders run before the first `process`, so the channel is simply rebuilt).  `bw_hz` must be positive:
+    /// the C-ABI reads a bandwidth <= 0 as "the reference default" (1 Hz DLL / 15 Hz PLL), it does not build a zero-gain loop.
     pub fn with_dll_bandwidth(self, bw_hz: f64) -> Self {
+        assert!(bw_hz > 0.0, "loop bandwidth must be positive");
         let mut cfg = self.cfg;
         cfg.dll_bandwidth_hz = bw_hz;
         Self::build(cfg)
     }
-    /// tracking.rs:163
+    /// tracking.rs:163 (same rule)
     pub fn with_pll_bandwidth(self, bw_hz: f64) -> Self {
+        assert!(bw_hz > 0.0, "loop bandwidth must be positive");
         let mut cfg = self.cfg;
         cfg.pll_bandwidth_hz = bw_hz;
         Self::build(cfg)
