@@ -327,7 +327,9 @@ void r4wb_composer_destroy(r4wb_composer* h);
 r4wb_error r4wb_composer_reset(r4wb_composer* h);
 /* One block: baseband is [n_emitters][n] (Emitter::generate_iq of every emitter; rows of inactive emitters are ignored),
  * doppler_hz / amplitude / active are per emitter (active may be NULL = all active).  out[n] = sum of the Doppler-rotated,
- * scaled emitters + receiver noise; the carrier phases advance as engine.rs:108-113. */
+ * scaled emitters + receiver noise; the carrier phases advance as engine.rs:108-113 (f64, exactly).  The per-sample products
+ * and the sum over emitters are formed in f32: a CF64 output carries f32-precision values widened to f64 (the reference sums
+ * Complex64), and n = 0 (no samples) writes nothing — pass the block length even when no emitter is active to get the noise. */
 r4wb_error r4wb_composer_block(r4wb_composer* h, const void* baseband, r4wb_fmt in_fmt, r4wb_mem in_where, uint64_t n,
                                const double* doppler_hz, const double* amplitude, const uint8_t* active, void* out,
                                r4wb_fmt out_fmt, r4wb_mem out_where);
