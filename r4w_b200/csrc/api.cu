@@ -132,7 +132,7 @@ struct r4wb_tracker { int device = device_now(); TrackerBank impl; r4wb_tracker(
 
 extern "C" {
 
-const char* r4wb_version(void) { return "r4w_b200 0.1.0 (sm_100a)"; }
+const char* r4wb_version(void) { return "r4w_b200 0.2.0 (sm_100a)"; }
 const char* r4wb_last_error(void) { return t_error.c_str(); }
 
 r4wb_error r4wb_init(int device)
