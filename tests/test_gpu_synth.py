@@ -417,6 +417,23 @@ print(hashlib.sha256(np.ascontiguousarray(x).tobytes()).hexdigest())
 """
 
 
+_PHASE_HASH = """
+import hashlib, numpy as np, r4w_b200 as R
+from tests.conftest import config_path
+R.init(0)
+cfg = R.load_config(config_path('e1c_8prn_600s_cn34_orbital'), cli_elevation_mask_deg=5.0)
+sc = R.GnssScenario(cfg, noise=False)
+x = np.concatenate([sc.generate_range(f, 20_000) for f in (1_234_000, 1_300_000_000, 2_999_980_000)])
+print(hashlib.sha256(np.ascontiguousarray(x).tobytes()).hexdigest())
+"""
+
+
+def test_parallel_exact_phase_equals_serial_walk(gpu):
+    """the segmented-scan exact-phase pass (k_phase_runs / _chain / _fill) and the one-warp serial walk (k_phase_exact) give
+    byte-identical IQ at the start, in the middle and at the end of the 600 s file"""
+    assert _run_py(_PHASE_HASH, {}) == _run_py(_PHASE_HASH, {"R4WB_PHASE_SERIAL": "1"})
+
+
 def test_class_table_path_equals_arithmetic_path(gpu):
     """k_synth with the boundary-age class table and with the arithmetic floor sums: byte-identical IQ (noise on)"""
     off = {"R4WB_SYNTH_LATTICE": "0"}                      # keep both runs on k_synth (the lattice kernel needs the class table)
