@@ -304,7 +304,7 @@ private:
     bool render_periodic(uint64_t first, uint64_t n, void* d_out);      // false: not applicable to this range
     SynthArgs base_args(const BlockSat* tab, const BlockHdr* hdr, uint64_t max_block_n) const;
     void build_tiles(const SynthArgs& a, uint32_t tb_begin, uint32_t tb_count, TileRec* out);
-    void build_canonical_table(uint64_t blk_begin, uint64_t blk_end);   // fills d_tab_/d_hdr_ for [blk_begin, blk_end)
+    void build_canonical_table(uint64_t blk_begin, uint64_t blk_end, uint64_t need_begin = ~0ull);   // fills d_tab_/d_hdr_ for [blk_begin, blk_end)
     void render_to(uint64_t first, uint64_t n, void* dst, r4wb_mem where, r4wb_fmt fmt);
 
     ScenarioModel md_;
@@ -324,6 +324,7 @@ private:
     DevBuf<float> d_ytab2_;
     DevBuf<uint32_t> d_stats_;
     uint32_t tab_lat_bad_ = 0;              // records of the canonical table the lattice kernel cannot render
+    uint64_t tiles_lo_ = 0;                 // d_tiles_ holds records for table blocks [tiles_lo_, table end) (relative to tab_blk0_)
     bool phase_parallel_ = true;            // the last exact-phase pass ran the parallel kernels (false: serial fallback)
     DevBuf<BlockSat> d_tab_, d_seq_tab_;
     DevBuf<BlockHdr> d_hdr_, d_seq_hdr_;

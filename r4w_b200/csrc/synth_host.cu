@@ -177,11 +177,31 @@ void Scenario::reset()
 
 // Prologue: Phase-1 parameters + NCO start values of canonical blocks [blk_begin, blk_end) into d_tab_.
 // The table is kept between calls (a bench loop re-rendering the same range pays for it once).
-void Scenario::build_canonical_table(uint64_t blk_begin, uint64_t blk_end)
+// `need_begin` (absolute block index, default blk_begin): first block the caller is going to render.  The block table of a
+// dynamic scenario must start at block 0 (the phase prefix), the per-tile records are only needed from one block before
+// `need_begin` on — the last rank of a time-sharded run builds an N-th of them.
+void Scenario::build_canonical_table(uint64_t blk_begin, uint64_t blk_end, uint64_t need_begin)
 {
-    if (tab_valid_ && blk_begin >= tab_blk0_ && blk_end <= tab_blk1_ && (blk_begin == tab_blk0_ || !(md_.any_dynamic || md_.any_var_visibility)))
-        return;
     const ScenConst& sc = md_.sc;
+    if (need_begin == ~0ull || need_begin < blk_begin) need_begin = blk_begin;
+    if (tab_valid_ && blk_begin >= tab_blk0_ && blk_end <= tab_blk1_ && (blk_begin == tab_blk0_ || !(md_.any_dynamic || md_.any_var_visibility))) {
+        // cached table: make sure the tile records reach down to the block before the first one rendered
+        const uint64_t lo = need_begin > tab_blk0_ ? need_begin - tab_blk0_ - 1 : 0;
+        if (lo < tiles_lo_) {
+            cudaStream_t st = current_stream();
+            SynthArgs a = base_args(d_tab_.p, d_hdr_.p, sc.B);
+            if (md_.lat.q != 0) { a.stats = d_stats_.p; R4WB_CUDA(cudaMemsetAsync(d_stats_.p, 0, 2 * sizeof(uint32_t), st)); }
+            build_tiles(a, (uint32_t)lo, (uint32_t)(tiles_lo_ - lo), d_tiles_.p);
+            if (md_.lat.q != 0) {
+                uint32_t bad = 0;
+                R4WB_CUDA(cudaMemcpyAsync(&bad, d_stats_.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+                R4WB_CUDA(cudaStreamSynchronize(st));
+                tab_lat_bad_ += bad;
+            }
+            tiles_lo_ = lo;
+        }
+        return;
+    }
     const uint64_t nblk = blk_end - blk_begin;
     if (nblk > 0x7fffffffull / std::max(1u, sc.n_sats)) fail(R4WB_ERR_INVALID_SIZE, "too many blocks in one call");
     cudaStream_t st = current_stream();
@@ -227,7 +247,8 @@ void Scenario::build_canonical_table(uint64_t blk_begin, uint64_t blk_end)
             a.stats = d_stats_.p;
             R4WB_CUDA(cudaMemsetAsync(d_stats_.p, 0, 2 * sizeof(uint32_t), st));
         }
-        build_tiles(a, 0, (uint32_t)nblk, d_tiles_.p);
+        tiles_lo_ = need_begin > blk_begin ? need_begin - blk_begin - 1 : 0;
+        build_tiles(a, (uint32_t)tiles_lo_, (uint32_t)(nblk - tiles_lo_), d_tiles_.p);
         if (md_.lat.q != 0) {
             R4WB_CUDA(cudaMemcpyAsync(&tab_lat_bad_, d_stats_.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
             R4WB_CUDA(cudaStreamSynchronize(st));
@@ -473,7 +494,7 @@ void Scenario::render_to(uint64_t first, uint64_t n, void* dst, r4wb_mem where, 
     timed_.clear();
 
     const uint64_t b0 = first / sc.B, b1 = (first + n - 1) / sc.B;
-    build_canonical_table(md_.table_begin(b0), b1 + 1);
+    build_canonical_table(md_.table_begin(b0), b1 + 1, b0);
 
     if (where == R4WB_MEM_DEVICE) {
         render_device(first, n, dst, fmt);
