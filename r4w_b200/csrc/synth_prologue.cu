@@ -152,9 +152,14 @@ __global__ void k_phase_q(double fs, double inv_fs, int fast_div, const SatConst
             r.k = ilogb(p);
             if (r.k >= 8) {
                 bool tie = false;
-                if (e.n == frac_n) {                         // same operations as block_phase_q, i / n from the table
-                    long long q = 0;
+                if (e.n == frac_n) {
+                    // The same increments as block_phase_q (i / n from the table), rounded to the ulp of binade k without leaving
+                    // FP64: x = inc 2^(52-k) (exact), y = rint(x) by the 1.5 2^52 trick (|x| < 2^37 here), sum of the y exact in a
+                    // double (< 2^50).  rint differs from block_phase_q's floor + (r > 0.5) only at an exact tie, and a block
+                    // with a tie is walked sample by sample anyway.
+                    double qd = 0.0;
                     const double dd = add_rn(de, -ds);
+                    const double scale = scalbn(1.0, 52 - r.k), magic = 6755399441055744.0;
                     for (uint32_t i = 0; i < e.n; ++i) {
                         const double dopp = add_rn(ds, mul_rn(frac[i], dd));
                         const double a = mul_rn(6.283185307179586, dopp);
@@ -165,12 +170,12 @@ __global__ void k_phase_q(double fs, double inv_fs, int fast_div, const SatConst
                         } else {
                             inc = div_rn(a, fs);
                         }
-                        const double x = scalbn(inc, 52 - r.k);
-                        const double fl = floor(x), rr = x - fl;
-                        if (rr == 0.5) tie = true;
-                        q += (long long)fl + (rr > 0.5 ? 1 : 0);
+                        const double x = mul_rn(inc, scale);
+                        const double y = add_rn(add_rn(x, magic), -magic);
+                        if (fabs(add_rn(x, -y)) == 0.5) tie = true;
+                        qd = add_rn(qd, y);
                     }
-                    r.Q = q;
+                    r.Q = (long long)qd;
                 } else {
                     block_phase_q(ds, de, e.n, fs, r.k, &r.Q, &tie);
                 }
