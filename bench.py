@@ -499,22 +499,48 @@ def run_b200(args):
         nb = bsc.block_size()
         bsc.generate_block(nb); bsc.reset()                         # table built, ring allocated: the loop below is the steady state
         torch.cuda.synchronize()
-        # the loop a Rust caller runs, with one preallocated block buffer: C-ABI calls only (no numpy allocation per block)
+        # the loop a Rust caller runs, with one preallocated block buffer, as a compiled caller of the C-ABI
+        # (tools/ubench/block_loop.c; a ctypes call costs ~1 us of interpreter time, a third of the 40 KB block's copy)
         L_ = _lib.lib()
-        gb, done_f, h_ = L_.r4wb_scenario_generate_block, L_.r4wb_scenario_is_done, bsc._h
+        h_ = bsc._h
         blkbuf = np.empty(nb, np.complex64)
+        loop_so = os.path.join(ROOT, "tools", "ubench", "libblock_loop.so")
+        if not os.path.exists(loop_so):
+            raise RuntimeError(f"{loop_so} is missing: run __graft_entry__.build()")
+        BL = C.CDLL(loop_so).r4wb_block_loop
+        BL.restype = C.c_int
+        BL.argtypes = [C.c_void_p] * 4 + [C.c_uint64, C.c_void_p, C.c_int, C.c_uint64] + [C.POINTER(C.c_uint64)] * 2 + [C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
+        fp = lambda f: C.cast(f, C.c_void_p)
+
+        def block_loop(mode):
+            bsc.reset()
+            got, calls, sec, fold = C.c_uint64(0), C.c_uint64(0), C.c_double(0), C.c_uint64(0)
+            rc = BL(fp(L_.r4wb_scenario_generate_block), fp(L_.r4wb_scenario_generate_block_view), fp(L_.r4wb_scenario_is_done), h_,
+                    nb, blkbuf.ctypes.data, mode, 8, C.byref(got), C.byref(calls), C.byref(sec), C.byref(fold))
+            _lib.check(rc)
+            return {"value": got.value / sec.value / 1e6, "unit": "Msamples/s", "samples": got.value, "ms": sec.value * 1e3,
+                    "us_per_call": sec.value / max(1, calls.value) * 1e6}
+
+        # ... and through ctypes, as round 1 and the first round-2 records measured it
+        gb, done_f = L_.r4wb_scenario_generate_block, L_.r4wb_scenario_is_done
         pbuf, wr = C.c_void_p(blkbuf.ctypes.data), C.c_uint64(0)
         pwr = C.byref(wr)
+        bsc.reset()
         ts = time.perf_counter()
         got = 0
         while not done_f(h_):
             gb(h_, nb, pbuf, _lib.MEM_HOST, _lib.FMT_CF32, pwr)
             got += wr.value
         dtb = time.perf_counter() - ts
-        blk = {"value": got / dtb / 1e6, "unit": "Msamples/s", "samples": got, "block_size": nb, "ms": dtb * 1e3,
-               "us_per_call": dtb / max(1, got // nb) * 1e6,
-               "api": f"r4wb_scenario_generate_block({nb}) until is_done through ctypes, {CONFIGS[2]} truncated to {args.block_api_seconds} s, "
-                      f"host cf32 out; canonical blocks are served from the library's render-ahead ring (pinned host chunks)"}
+        blk = block_loop(0)
+        blk.update({"block_size": nb,
+                    "api": f"r4wb_scenario_generate_block({nb}) until is_done from a compiled loop (tools/ubench/block_loop.c), {CONFIGS[2]} truncated to "
+                           f"{args.block_api_seconds} s, host cf32 out; canonical blocks are served from the library's render-ahead ring (pinned host chunks), "
+                           f"one host copy per block",
+                    "view": dict(block_loop(1), api="r4wb_scenario_generate_block_view: the ring's pinned block is handed out, no host copy"),
+                    "view_read": dict(block_loop(2), api="r4wb_scenario_generate_block_view and the consumer reads every byte of the block"),
+                    "ctypes": {"value": got / dtb / 1e6, "unit": "Msamples/s", "us_per_call": dtb / max(1, got // nb) * 1e6,
+                               "api": "the same copying loop driven from Python (one ctypes call per block)"}})
         bsc.close()
 
     # ---- all five BASELINE configs at the rank's share (bounded repetitions: 1 warm-up + 2 timed)

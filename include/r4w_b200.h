@@ -205,6 +205,13 @@ uint64_t r4wb_scenario_current_sample(const r4wb_scenario* h);
  * main.rs:4488-4500) and advances.  *written = 0 when done (the reference returns an empty Vec). */
 r4wb_error r4wb_scenario_generate_block(r4wb_scenario* h, uint64_t n, void* dst, r4wb_mem where,
                                         r4wb_fmt fmt, uint64_t* written);
+/* The same call for a host consumer that only READS the block (the CLI's sink: IqFormat::write_samples into a BufWriter,
+ * crates/r4w-cli/src/main.rs:4488-4500; a `&[IQSample]` on the Rust side): *block points at the next min(n, remaining)
+ * samples in pinned host memory owned by the handle — for canonical block sizes the render-ahead ring itself, so the call
+ * copies nothing — and stays valid until the next call on this handle.  *written = 0 and *block = NULL when done.
+ * Same samples, same advance, same last_power_sum as r4wb_scenario_generate_block. */
+r4wb_error r4wb_scenario_generate_block_view(r4wb_scenario* h, uint64_t n, r4wb_fmt fmt, const void** block,
+                                             uint64_t* written);
 /* Random access to the stream the CLI loop (`while !is_done { generate_block(block_size()) }`,
  * main.rs:4488-4500 / GnssScenario::generate, scenario.rs:549-561) would produce: samples
  * [first, first+n) of the canonical block partition.  Does not move current_sample.  This is the

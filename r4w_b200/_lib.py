@@ -58,6 +58,7 @@ SYMBOLS = {
     "r4wb_scenario_reset": (_int, [_vp]),
     "r4wb_scenario_current_sample": (_u64, [_vp]),
     "r4wb_scenario_generate_block": (_int, [_vp, _u64, _vp, _int, _int, C.POINTER(_u64)]),
+    "r4wb_scenario_generate_block_view": (_int, [_vp, _u64, _int, C.POINTER(_vp), C.POINTER(_u64)]),
     "r4wb_scenario_generate": (_int, [_vp, _u64, _u64, _vp, _int, _int]),
     "r4wb_scenario_generate_rest": (_int, [_vp, _vp, _u64, _int, _int, C.POINTER(_u64)]),
     "r4wb_scenario_write_file": (_int, [_vp, C.c_char_p, _int, C.POINTER(_u64), C.POINTER(_u64), C.POINTER(_dbl)]),

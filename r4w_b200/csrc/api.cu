@@ -229,6 +229,14 @@ r4wb_error r4wb_scenario_generate_block(r4wb_scenario* h, uint64_t n, void* dst,
     return guard_on(h, [&] { *written = h->impl.generate_block(n, dst, where, fmt); });
 }
 
+r4wb_error r4wb_scenario_generate_block_view(r4wb_scenario* h, uint64_t n, r4wb_fmt fmt, const void** block, uint64_t* written)
+{
+    if (!h || !block || !written) { t_error = "handle/block/written is NULL"; return R4WB_ERR_NULL_POINTER; }
+    *written = 0;
+    *block = nullptr;
+    return guard_on(h, [&] { *block = h->impl.generate_block_view(n, fmt, written); });
+}
+
 r4wb_error r4wb_scenario_generate(r4wb_scenario* h, uint64_t first, uint64_t n, void* dst, r4wb_mem where, r4wb_fmt fmt)
 {
     if (!h) { t_error = "handle is NULL"; return R4WB_ERR_NULL_POINTER; }

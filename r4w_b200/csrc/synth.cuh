@@ -283,6 +283,8 @@ public:
     void generate(uint64_t first, uint64_t n, void* dst, r4wb_mem where, r4wb_fmt fmt);
     // one reference block of min(n, remaining) samples at current_sample
     uint64_t generate_block(uint64_t n, void* dst, r4wb_mem where, r4wb_fmt fmt);
+    // the same block, borrowed: pointer into pinned host memory of the handle, valid until the next call on it
+    const void* generate_block_view(uint64_t n, r4wb_fmt fmt, uint64_t* n_out);
     // GnssScenario::generate (scenario.rs:549-561): [current_sample, total) and done
     uint64_t generate_rest(void* dst, uint64_t cap, r4wb_mem where, r4wb_fmt fmt);
     // the CLI's file sink (main.rs:4483-4509): the whole scenario, in `fmt`, streamed into `path`; returns sum |s|^2
@@ -360,6 +362,8 @@ private:
     void ring_schedule(uint64_t chunk);
     void ring_drop();
     void seq_sync();                          // replay SeqState up to current_ (after ring-served blocks)
+    void* view_buf_ = nullptr;                // pinned bounce buffer of generate_block_view for blocks the ring does not serve
+    size_t view_cap_ = 0;
     const void* last_block_ = nullptr;        // last ring-served block (lazy power sum)
     uint64_t last_block_n_ = 0;
     r4wb_fmt last_block_fmt_ = R4WB_FMT_CF32;

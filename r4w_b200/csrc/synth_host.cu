@@ -113,6 +113,7 @@ struct Scenario::StreamScope {
 Scenario::~Scenario()
 {
     ring_drop();
+    if (view_buf_) cudaFreeHost(view_buf_);
     delete per_;
     if (ev_done_) cudaEventDestroy(ev_done_);
     for (cudaEvent_t e : {ev_fork_, ev_join_, ev_render_[0], ev_render_[1], ev_copy_[0], ev_copy_[1]})
@@ -608,7 +609,7 @@ uint64_t Scenario::ring_block(uint64_t n, void* dst, r4wb_fmt fmt)
         R.synced_chunk = c;
     }
     const unsigned char* src = R.pin + (size_t)slot * R.chunk_bytes + (size_t)(blk - c * R.C) * sc.B * bps;
-    std::memcpy(dst, src, (size_t)n * bps);
+    if (dst) std::memcpy(dst, src, (size_t)n * bps);   // dst == NULL: generate_block_view hands out `src` itself
     last_block_ = src; last_block_n_ = n; last_block_fmt_ = fmt;
     current_ += n;
     return n;
@@ -673,6 +674,33 @@ uint64_t Scenario::generate_block(uint64_t n_req, void* dst, r4wb_mem where, r4w
     seq_pos_ = current_;
     last_block_ = nullptr;
     return n;
+}
+
+// Borrowed form of generate_block: the ring's pinned chunk is the caller's block (no host copy).  A chunk's slot is rewritten
+// only after the consumer has moved two chunks on, so the pointer outlives the next call; the contract says "until the next
+// call".  Blocks the ring does not serve (odd sizes) are rendered into a pinned bounce buffer of the handle.
+const void* Scenario::generate_block_view(uint64_t n_req, r4wb_fmt fmt, uint64_t* n_out)
+{
+    const ScenConst& sc = md_.sc;
+    const uint64_t remaining = sc.total > current_ ? sc.total - current_ : 0;
+    const uint64_t n = std::min(remaining, n_req);
+    *n_out = n;
+    if (n == 0) return nullptr;
+    if ((unsigned)fmt > (unsigned)R4WB_FMT_CU8) fail(R4WB_ERR_INVALID_PARAMETER, "unknown sample format %d", (int)fmt);
+    if (seq_canonical_ && current_ % sc.B == 0 && (n == sc.B || n == remaining) && n <= sc.B && ring_enabled()) {
+        ring_block(n, nullptr, fmt);
+        return last_block_;
+    }
+    if (n > (1ull << 24)) fail(R4WB_ERR_NOT_SUPPORTED, "generate_block: at most 2^24 samples per reference block");
+    const size_t need = (size_t)n * fmt_bytes(fmt);
+    if (need > view_cap_) {
+        if (view_buf_) cudaFreeHost(view_buf_);
+        view_buf_ = nullptr; view_cap_ = 0;
+        R4WB_CUDA(cudaMallocHost(&view_buf_, need));
+        view_cap_ = need;
+    }
+    generate_block(n, view_buf_, R4WB_MEM_HOST, fmt);
+    return view_buf_;
 }
 
 uint64_t Scenario::generate_rest(void* dst, uint64_t cap, r4wb_mem where, r4wb_fmt fmt)

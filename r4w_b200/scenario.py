@@ -112,6 +112,21 @@ class GnssScenario:
                                                            _lib.MEM_HOST, fmt, C.byref(written)))
         return out[: written.value]
 
+    def generate_block_view(self, block_size: int, dtype=np.complex64) -> np.ndarray:
+        """generate_block without the host copy: a read-only array over the library's pinned block (for canonical
+        block sizes the render-ahead ring itself), valid until the next call on this scenario.  For sinks that
+        only read the block (file / socket writers: main.rs:4488-4500)."""
+        fmt = _lib.FMT_CF64 if np.dtype(dtype) == np.complex128 else _lib.FMT_CF32
+        dt = np.complex128 if fmt == _lib.FMT_CF64 else np.complex64
+        written, ptr = C.c_uint64(0), C.c_void_p(0)
+        _lib.check(_lib.lib().r4wb_scenario_generate_block_view(self._h, int(block_size), fmt, C.byref(ptr), C.byref(written)))
+        if written.value == 0:
+            return np.empty(0, dt)
+        buf = (C.c_char * (written.value * np.dtype(dt).itemsize)).from_address(ptr.value)
+        out = np.frombuffer(buf, dtype=dt, count=written.value)
+        out.flags.writeable = False
+        return out
+
     def generate(self, dtype=np.complex64) -> np.ndarray:
         """generate (scenario.rs:549-561): `while !is_done {generate_block(block_size())}` — everything from
         current_sample to the end, rendered in one call; leaves the scenario done."""

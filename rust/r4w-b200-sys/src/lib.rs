@@ -247,6 +247,7 @@ extern "C" {
     pub fn r4wb_scenario_reset(h: *mut r4wb_scenario) -> c_int;
     pub fn r4wb_scenario_current_sample(h: *const r4wb_scenario) -> u64;
     pub fn r4wb_scenario_generate_block(h: *mut r4wb_scenario, n: u64, dst: *mut c_void, mem: c_int, fmt: c_int, written: *mut u64) -> c_int;
+    pub fn r4wb_scenario_generate_block_view(h: *mut r4wb_scenario, n: u64, fmt: c_int, block: *mut *const c_void, written: *mut u64) -> c_int;
     pub fn r4wb_scenario_generate(h: *mut r4wb_scenario, first: u64, n: u64, dst: *mut c_void, mem: c_int, fmt: c_int) -> c_int;
     pub fn r4wb_scenario_generate_rest(h: *mut r4wb_scenario, dst: *mut c_void, cap: u64, mem: c_int, fmt: c_int, written: *mut u64) -> c_int;
     pub fn r4wb_scenario_write_file(h: *mut r4wb_scenario, path: *const c_char, fmt: c_int, samples: *mut u64, bytes: *mut u64, power_sum: *mut f64) -> c_int;

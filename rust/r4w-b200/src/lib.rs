@@ -202,6 +202,19 @@ impl GnssScenario {
         out
     }
 
+    /// The sink form of `generate_block`: the block as the interleaved f32 pairs the CLI's cf32 writer emits
+    /// (main.rs:4488-4500, core/io/format.rs:197-200), borrowed from the library's pinned render-ahead ring: no host
+    /// copy.  The slice lives until the next call on this scenario (the `&mut self` borrow enforces it).
+    pub fn generate_block_cf32(&mut self, block_size: usize) -> &[[f32; 2]] {
+        let mut written = 0u64;
+        let mut block: *const std::ffi::c_void = std::ptr::null();
+        check(unsafe { sys::r4wb_scenario_generate_block_view(self.h, block_size as u64, sys::R4WB_FMT_CF32, &mut block, &mut written) });
+        if written == 0 {
+            return &[];
+        }
+        unsafe { std::slice::from_raw_parts(block.cast::<[f32; 2]>(), written as usize) }
+    }
+
     /// scenario.rs:549: everything from the current position to the end (the CLI loop's concatenation), rendered in one
     /// call; leaves the scenario done like the reference's `while !self.is_done()` loop
     pub fn generate(&mut self) -> Vec<IQSample> {

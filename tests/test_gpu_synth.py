@@ -143,6 +143,39 @@ def test_block_loop_is_served_from_the_render_ahead_ring(gpu, oracle):
         assert a.size == b.size == bs and _relrms(a, b) <= TOL
 
 
+def test_block_view_hands_out_the_ring(gpu):
+    """r4wb_scenario_generate_block_view: the same blocks as generate_block without the host copy — read-only views of the
+    pinned ring for canonical sizes (the previous view survives the next call), a pinned bounce buffer for odd sizes, same
+    advance / last_power_sum / end-of-scenario behaviour"""
+    cfg = _cfg("e1c_8prn_60s_cn34_orbital")
+    cfg.output.duration_s = 0.3002                               # 300.2 blocks: two ring chunks and a partial last block
+    sc = gpu.GnssScenario(cfg, noise=True)
+    whole = gpu.GnssScenario(cfg, noise=True).generate_range(0, sc.total_samples())
+    pos, prev, prev_pos = 0, None, 0
+    while not sc.is_done():
+        v = sc.generate_block_view(5000)
+        assert not v.flags.writeable and v.dtype == np.complex64
+        assert np.array_equal(v, whole[pos:pos + v.size])
+        if prev is not None:
+            assert np.array_equal(prev, whole[prev_pos:prev_pos + prev.size])     # still intact one call later
+        assert sc.last_power_sum() == pytest.approx(float(np.sum(np.abs(v.astype(np.complex128)) ** 2)), rel=1e-5)
+        prev, prev_pos = v, pos
+        pos += v.size
+    assert pos == sc.total_samples() and prev.size == 1000
+    assert sc.generate_block_view(5000).size == 0
+    # mixed with the copying call, cf64, and odd sizes (bounce buffer; the reference's own partition)
+    sc.reset()
+    a = sc.generate_block(5000)
+    b = sc.generate_block_view(5000).copy()
+    c = sc.generate_block_view(5000, dtype=np.complex128).copy()
+    assert np.array_equal(np.concatenate([a, b]), whole[:10_000]) and np.array_equal(c, whole[10_000:15_000].astype(np.complex128))
+    ref = gpu.GnssScenario(cfg, noise=True)
+    for _ in range(3):
+        ref.generate_block(5000)
+    for bs in (777, 5000, 70_000):
+        assert np.array_equal(sc.generate_block_view(bs), ref.generate_block(bs))
+
+
 def test_streams_are_restored_and_ordered(gpu):
     """device-tensor calls run on torch's current stream and leave the library on the default stream; a table built on one
     stream is safe to use from another (stale thread-local stream, unsynchronised table reuse)"""
