@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
+#include <chrono>
 #include <cstring>
 #include <condition_variable>
 #include <cerrno>
@@ -208,19 +209,37 @@ void Scenario::build_canonical_table(uint64_t blk_begin, uint64_t blk_end, uint6
     cudaStream_t st = current_stream();
     tab_valid_ = false;
     if (per_) per_->planned = false;
+    // R4WB_PROLOGUE_TRACE=1: wall clock of the stages on stderr (measurement aid; cudaMalloc / cudaFree of the ~GB tables of
+    // a 600 s file vary from a few ms to over a second between processes on the same box, the kernels do not)
+    static const bool trace = [] { const char* e = std::getenv("R4WB_PROLOGUE_TRACE"); return e && e[0] == '1'; }();
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+    const auto t_begin = now();
+    auto t_alloc = t_begin, t_phase = t_begin;
     d_tab_.reserve(std::max<size_t>(1, (size_t)nblk * sc.n_sats));
     d_hdr_.reserve(std::max<size_t>(1, nblk));
     // dynamic satellites: the reference's sequentially accumulated f64 carrier phase, reproduced exactly (synth_math.cuh:
     // block_phase_q / phase_after_block) unless the caller asked for the closed form; needs the table to start at block 0
     const bool exact_phase = md_.any_dynamic && !(sc.flags & R4WB_FLAG_CLOSED_FORM_PHASE) && blk_begin == 0 && sc.n_sats > 0;
-    DevBuf<double> dop, papprox;                    // scratch of this build only
-    DevBuf<unsigned char> pscratch;
+    // The scratch of the exact-phase pass (per-block Doppler pair, approximate phase, the scan's work arrays: ~75 B per table
+    // entry) lives only until the tile records (128 B per entry) are written, on the same stream: it is carved out of the
+    // tile-record buffer, so a cold table costs three device allocations and no free (cudaFree synchronises the device, and
+    // both calls were the unpredictable part of the cold path: 2-20 ms usually, over a second on a busy host)
+    const SynthArgs a_tiles = base_args(d_tab_.p, d_hdr_.p, sc.B);
+    const size_t ne = (size_t)nblk * sc.n_sats;
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const size_t scratch_bytes = exact_phase ? al(2 * ne * sizeof(double)) + al(ne * sizeof(double)) + phase_exact_scratch_bytes(sc.n_sats, (uint32_t)nblk, (uint32_t)sc.B) : 0;
+    d_tiles_.reserve(std::max<size_t>(std::max<size_t>(1, (size_t)nblk * a_tiles.tiles_per_block * sc.n_sats), (scratch_bytes + sizeof(TileRec) - 1) / sizeof(TileRec)));
+    double *dop = nullptr, *papprox = nullptr;
+    unsigned char* pscratch = nullptr;
     if (exact_phase) {
-        const size_t ne = (size_t)nblk * sc.n_sats;
-        dop.reserve(2 * ne); papprox.reserve(ne);
-        pscratch.reserve(phase_exact_scratch_bytes(sc.n_sats, (uint32_t)nblk, (uint32_t)sc.B));
+        unsigned char* sp = reinterpret_cast<unsigned char*>(d_tiles_.p);
+        dop = reinterpret_cast<double*>(sp); sp += al(2 * ne * sizeof(double));
+        papprox = reinterpret_cast<double*>(sp); sp += al(ne * sizeof(double));
+        pscratch = sp;
     }
-    launch_block_params(sc, d_sat_.p, d_segments_.p, blk_begin, (uint32_t)nblk, d_tab_.p, d_hdr_.p, dop.p, papprox.p, st);
+    if (trace) t_alloc = now();
+    launch_block_params(sc, d_sat_.p, d_segments_.p, blk_begin, (uint32_t)nblk, d_tab_.p, d_hdr_.p, dop, papprox, st);
     if (sc.n_sats == 0) {   // headers still needed
         std::vector<BlockHdr> h(nblk);
         for (uint64_t b = 0; b < nblk; ++b) {
@@ -231,18 +250,15 @@ void Scenario::build_canonical_table(uint64_t blk_begin, uint64_t blk_end, uint6
         R4WB_CUDA(cudaStreamSynchronize(st));
     }
     if (md_.any_dynamic || md_.any_var_visibility) launch_phase_scan(d_sat_.p, sc.n_sats, (uint32_t)nblk, d_tab_.p, st);
-    if (exact_phase) {
-        phase_parallel_ = launch_phase_exact(sc, d_sat_.p, (uint32_t)nblk, d_tab_.p, dop.p, papprox.p, pscratch.p, st);
-        R4WB_CUDA(cudaStreamSynchronize(st));       // the scratch buffers are freed on return
-    }
+    if (exact_phase) phase_parallel_ = launch_phase_exact(sc, d_sat_.p, (uint32_t)nblk, d_tab_.p, dop, papprox, pscratch, st);
+    if (trace) { cudaStreamSynchronize(st); t_phase = now(); }
     tab_blk0_ = blk_begin;
     tab_blk1_ = blk_end;
     tab_valid_ = true;
     // per-tile records for the canonical tiling (block size B); k_tile_params counts the records whose carrier model the
     // lattice kernel cannot follow (large Doppler rate), read back once per table
     {
-        SynthArgs a = base_args(d_tab_.p, d_hdr_.p, sc.B);
-        d_tiles_.reserve(std::max<size_t>(1, (size_t)nblk * a.tiles_per_block * sc.n_sats));
+        SynthArgs a = a_tiles;                      // the records overwrite the phase scratch (stream order)
         tab_lat_bad_ = 0;
         if (md_.lat.q != 0) {
             a.stats = d_stats_.p;
@@ -253,6 +269,11 @@ void Scenario::build_canonical_table(uint64_t blk_begin, uint64_t blk_end, uint6
         if (md_.lat.q != 0) {
             R4WB_CUDA(cudaMemcpyAsync(&tab_lat_bad_, d_stats_.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
             R4WB_CUDA(cudaStreamSynchronize(st));
+        }
+        if (trace) {
+            cudaStreamSynchronize(st);
+            std::fprintf(stderr, "[r4wb prologue] %llu blocks: allocations %.1f ms, block params + phase %.1f ms, tile records %.1f ms\n",
+                         (unsigned long long)nblk, ms(t_begin, t_alloc), ms(t_alloc, t_phase), ms(t_phase, now()));
         }
     }
 }
