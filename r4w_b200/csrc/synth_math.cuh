@@ -344,6 +344,67 @@ R4WB_HD void block_phase_q(double ds, double de, uint32_t n, double fs, int k, l
     *Q = q; *tie = t;
 }
 
+// The same Q without visiting every sample.  Every operation of ref_phase_inc is a correctly rounded, monotone function of
+// its argument, so x_i = inc_i 2^(52-k) is monotone in i (direction = sign of de - ds) and y_i = rint(x_i) is a monotone STEP
+// function: over one 1 ms block the Doppler moves by ~1e-3 Hz and x by 0..a few dozen units.  With j running in the direction
+// of non-decreasing y, and i_v = the first j with y_j >= v for every level v in (y_0, y_last],
+//     Q = sum_j y_j = n y_0 + sum_v (n - i_v).
+// Each i_v is estimated by linear interpolation and then PROVEN with the exact increment chain at i_v - 1 and i_v (moved until
+// both hold), so Q is the brute-force sum bit for bit while the chain runs 2 + ~2 steps times instead of n.  A tie
+// (x exactly half-way) can only sit on a sample next to a step or on the first / last sample — all of them are evaluated — and
+// marks the block for the sample-by-sample walk, as in block_phase_q.  Returns false when the block has more than
+// max_steps levels (start of the file, where the ulp is tiny): the caller then sums sample by sample.
+// div: 0 = a / fs by division, 1 = Markstein with inv_fs (verified by the host for this fs; see k_phase_q)
+R4WB_HD bool block_phase_q_steps(double ds, double de, uint32_t n, double fs, double inv_fs, int div, int k, uint32_t max_steps,
+                                 long long* Q, bool* tie)
+{
+    if (n == 0) { *Q = 0; *tie = false; return true; }
+    const double nf = (double)n;
+    const double dd = add_rn(de, -ds);
+    const double scale = scalbn(1.0, 52 - k), magic = 6755399441055744.0;    // 1.5 2^52: rint for |x| < 2^51
+    const bool rev = dd < 0.0;
+    bool t = false;
+    double x_last_eval = 0.0;
+    auto Y = [&](uint32_t j) -> long long {
+        const uint32_t i = rev ? n - 1u - j : j;
+        const double frac = div_rn((double)i, nf);
+        const double a = mul_rn(6.283185307179586, add_rn(ds, mul_rn(frac, dd)));
+        double inc;
+        if (div) {
+            const double q0 = mul_rn(a, inv_fs);
+            inc = fma(fma(-q0, fs, a), inv_fs, q0);
+        } else {
+            inc = div_rn(a, fs);
+        }
+        const double x = mul_rn(inc, scale);
+        const double y = add_rn(add_rn(x, magic), -magic);
+        if (fabs(add_rn(x, -y)) == 0.5) t = true;
+        x_last_eval = x;
+        return (long long)y;
+    };
+    const long long y0 = Y(0);
+    const double x0 = x_last_eval;
+    if (!(fabs(x0) < 1125899906842624.0)) return false;                       // 2^50: outside the rint trick (never in practice)
+    const long long yl = Y(n - 1u);
+    const double xl = x_last_eval;
+    if (yl < y0 || (unsigned long long)(yl - y0) > (unsigned long long)max_steps) return false;
+    long long q = (long long)n * y0;
+    if (yl > y0) {
+        const double slope = ((double)(n - 1u)) / (xl - x0);                  // xl - x0 > 0 here
+        for (long long v = y0 + 1; v <= yl; ++v) {
+            double est = ceil(((double)v - 0.5 - x0) * slope);
+            if (!(est >= 1.0)) est = 1.0;
+            if (est > (double)(n - 1u)) est = (double)(n - 1u);
+            uint32_t j = (uint32_t)est;
+            while (Y(j) < v) ++j;                                             // y_{n-1} = yl >= v: stops by n - 1
+            while (Y(j - 1u) >= v) --j;                                       // y_0 < v: stops by j = 1
+            q += (long long)(n - j);
+        }
+    }
+    *Q = q; *tie = t;
+    return true;
+}
+
 // true when a phase that starts the block at `ph` provably stays inside binade k for every sample of the block
 R4WB_HD bool phase_stays_in_binade(double ph, const PhaseQ& r)
 {

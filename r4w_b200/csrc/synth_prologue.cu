@@ -88,7 +88,8 @@ __global__ void __launch_bounds__(1024) k_phase_scan(const SatConst* __restrict_
 // multiple of that binade's ulp (PhaseQ.Q) — associative — so only the few blocks per satellite that cross a binade, hold an
 // exact tie or start near zero ("walk" blocks, on the order of a hundred of 600 000) are sequential:
 //   k_phase_prefix   CTA per satellite: scan of the real-number block advances -> predicted start phase / binade of every block
-//   k_phase_q        thread per (block, satellite): Q = sum over the block of rint(inc_i / ulp); walk flag from the prediction
+//   k_phase_q        thread per (block, satellite): Q = sum over the block of rint(inc_i / ulp), from the positions of the steps of
+//                    that monotone sequence (block_phase_q_steps); walk flag from the prediction
 //   k_phase_runs     CTA per satellite: wrapping prefix sum of Q over the non-walk blocks + ordered list of the walk blocks
 //   k_phase_chain    warp per satellite: hops from walk block to walk block (run advance = difference of two prefix entries,
 //                    exact), walks each walk block sample by sample (the reference's own loop) -> phase at the start of every run
@@ -134,7 +135,9 @@ __global__ void k_phase_frac(uint32_t n, double* __restrict__ frac)
 // the binade over the block, a tie, or a start below 2^8 rad)
 // fast_div: a / fs as q = a y, r = fma(-q, fs, a), q' = fma(r, y, q) with y = RN(1 / fs) — the correctly rounded quotient
 // (Markstein), three FP64 instructions instead of the ~35 of a division; the host verifies it for the scenario's fs first
-__global__ void k_phase_q(double fs, double inv_fs, int fast_div, const SatConst* __restrict__ sats, uint32_t n_sats, uint32_t nblk,
+constexpr uint32_t kPhaseQMaxSteps = 256;
+
+__global__ void k_phase_q(double fs, double inv_fs, int fast_div, int step_form, const SatConst* __restrict__ sats, uint32_t n_sats, uint32_t nblk,
                           const BlockSat* __restrict__ tab, const double* __restrict__ dop, const double* __restrict__ pstart,
                           const double* __restrict__ frac, uint32_t frac_n, PhaseQ* __restrict__ out)
 {
@@ -152,32 +155,38 @@ __global__ void k_phase_q(double fs, double inv_fs, int fast_div, const SatConst
             r.k = ilogb(p);
             if (r.k >= 8) {
                 bool tie = false;
-                if (e.n == frac_n) {
-                    // The same increments as block_phase_q (i / n from the table), rounded to the ulp of binade k without leaving
-                    // FP64: x = inc 2^(52-k) (exact), y = rint(x) by the 1.5 2^52 trick (|x| < 2^37 here), sum of the y exact in a
-                    // double (< 2^50).  rint differs from block_phase_q's floor + (r > 0.5) only at an exact tie, and a block
-                    // with a tie is walked sample by sample anyway.
-                    double qd = 0.0;
-                    const double dd = add_rn(de, -ds);
-                    const double scale = scalbn(1.0, 52 - r.k), magic = 6755399441055744.0;
-                    for (uint32_t i = 0; i < e.n; ++i) {
-                        const double dopp = add_rn(ds, mul_rn(frac[i], dd));
-                        const double a = mul_rn(6.283185307179586, dopp);
-                        double inc;
-                        if (fast_div) {
-                            const double q0 = mul_rn(a, inv_fs);
-                            inc = fma(fma(-q0, fs, a), inv_fs, q0);
-                        } else {
-                            inc = div_rn(a, fs);
+                // Q from the step positions of the monotone sequence rint(inc_i / ulp) (block_phase_q_steps: ~2 + 2 levels exact
+                // increment chains instead of n); blocks with more than kPhaseQMaxSteps levels — the first second or two of a
+                // file, where the ulp is tiny — are summed sample by sample
+                if (!step_form || !block_phase_q_steps(ds, de, e.n, fs, inv_fs, fast_div, r.k, kPhaseQMaxSteps, &r.Q, &tie)) {
+                    tie = false;
+                    if (e.n == frac_n) {
+                        // The same increments as block_phase_q (i / n from the table), rounded to the ulp of binade k without
+                        // leaving FP64: x = inc 2^(52-k) (exact), y = rint(x) by the 1.5 2^52 trick (|x| < 2^37 here), sum of the
+                        // y exact in a double (< 2^50).  rint differs from block_phase_q's floor + (r > 0.5) only at an exact
+                        // tie, and a block with a tie is walked sample by sample anyway.
+                        double qd = 0.0;
+                        const double dd = add_rn(de, -ds);
+                        const double scale = scalbn(1.0, 52 - r.k), magic = 6755399441055744.0;
+                        for (uint32_t i = 0; i < e.n; ++i) {
+                            const double dopp = add_rn(ds, mul_rn(frac[i], dd));
+                            const double a = mul_rn(6.283185307179586, dopp);
+                            double inc;
+                            if (fast_div) {
+                                const double q0 = mul_rn(a, inv_fs);
+                                inc = fma(fma(-q0, fs, a), inv_fs, q0);
+                            } else {
+                                inc = div_rn(a, fs);
+                            }
+                            const double x = mul_rn(inc, scale);
+                            const double y = add_rn(add_rn(x, magic), -magic);
+                            if (fabs(add_rn(x, -y)) == 0.5) tie = true;
+                            qd = add_rn(qd, y);
                         }
-                        const double x = mul_rn(inc, scale);
-                        const double y = add_rn(add_rn(x, magic), -magic);
-                        if (fabs(add_rn(x, -y)) == 0.5) tie = true;
-                        qd = add_rn(qd, y);
+                        r.Q = (long long)qd;
+                    } else {
+                        block_phase_q(ds, de, e.n, fs, r.k, &r.Q, &tie);
                     }
-                    r.Q = (long long)qd;
-                } else {
-                    block_phase_q(ds, de, e.n, fs, r.k, &r.Q, &tie);
                 }
                 r.ok = tie ? 0u : 1u;
             }
@@ -378,7 +387,9 @@ bool launch_phase_exact(const ScenConst& sc, const SatConst* d_sats, uint32_t nb
         }
         checked_ok = ok; checked_fs = sc.fs;
     }
-    k_phase_q<<<(unsigned)((ne + 127) / 128), 128, 0, st>>>(sc.fs, 1.0 / sc.fs, checked_ok, d_sats, ns, nblk, d_tab, d_dop, S.pstart, S.frac,
+    // A/B hook: R4WB_PHASE_Q_BRUTE=1 sums every block's increments sample by sample instead of locating the steps
+    static const int step_form = [] { const char* e = std::getenv("R4WB_PHASE_Q_BRUTE"); return (e && e[0] == '1') ? 0 : 1; }();
+    k_phase_q<<<(unsigned)((ne + 127) / 128), 128, 0, st>>>(sc.fs, 1.0 / sc.fs, checked_ok, step_form, d_sats, ns, nblk, d_tab, d_dop, S.pstart, S.frac,
                                                              (uint32_t)sc.B, S.pq);
     R4WB_LAUNCH_CHECK();
     static const bool serial = [] { const char* e = std::getenv("R4WB_PHASE_SERIAL"); return e && e[0] == '1'; }();

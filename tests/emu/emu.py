@@ -40,6 +40,7 @@ def lib():
         L.emu_scenario_generate_block.argtypes = [vp, u64, vp, C.POINTER(u64)]
         L.emu_block_params.argtypes = [vp, u64, C.c_uint32, vp]
         L.emu_phase_model_check.argtypes = [C.c_double, C.c_double, C.c_double, u64, vp]; L.emu_phase_model_check.restype = None
+        L.emu_phase_q_steps_check.argtypes = [u64, C.c_uint32, C.c_double, C.c_int, C.c_int, C.c_uint32, C.c_uint32, vp]; L.emu_phase_q_steps_check.restype = None
         L.emu_fft.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]
         L.emu_pcps.argtypes = [C.c_int, u64, C.c_double, C.c_double, C.c_double, vp, C.c_int, u64, vp, u64, vp, vp]
         _lib = L
@@ -122,6 +123,14 @@ def pcps(code_length: int, fs: float, dmax: float, dstep: float, x: np.ndarray, 
                    grid.ctypes.data_as(C.c_void_p) if want_grid else None)
     res = (out[0], out[1], out[2], int(out[3]))
     return res + (grid,) if want_grid else res
+
+
+def phase_q_steps_check(seed: int, cases: int, span_hz: float, k_lo: int, k_hi: int, n: int = 5000, max_steps: int = 1024):
+    """-> (cases where the step-function form of the block's integer phase sum differs from the per-sample sum, cases it
+    declined, largest number of levels, cases with an exact tie)"""
+    out = np.zeros(4, np.float64)
+    lib().emu_phase_q_steps_check(seed, cases, span_hz, k_lo, k_hi, n, max_steps, out.ctypes.data_as(C.c_void_p))
+    return int(out[0]), int(out[1]), int(out[2]), int(out[3])
 
 
 def phase_model_check(d0: float, rate: float, jerk: float, blocks: int):

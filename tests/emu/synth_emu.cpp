@@ -321,7 +321,13 @@ void emu_phase_model_check(double d0, double rate, double jerk, uint64_t blocks,
         block_phase_approx(ds, de, n, fs, &r.approx, &r.span);
         if (approx_sum != 0.0) {
             r.k = ilogb(approx_sum);
-            if (r.k >= 8) { bool tie; block_phase_q(ds, de, n, fs, r.k, &r.Q, &tie); r.ok = tie ? 0u : 1u; }
+            if (r.k >= 8) {
+                bool tie;
+                block_phase_q(ds, de, n, fs, r.k, &r.Q, &tie);
+                r.ok = tie ? 0u : 1u;
+                long long q2 = 0; bool tie2 = false;                              // the step-function form must agree wherever it answers
+                if (block_phase_q_steps(ds, de, n, fs, 1.0 / fs, (int)(b & 1u), r.k, 1024u, &q2, &tie2) && (tie2 != tie || (!tie && q2 != r.Q))) ++mism;
+            }
         }
         if (!phase_stays_in_binade(ph, r)) ++walked;
         ph = phase_after_block(ph, r, ds, de, n, fs);
@@ -329,6 +335,38 @@ void emu_phase_model_check(double d0, double rate, double jerk, uint64_t blocks,
         if (ph != ph_ref) { ++mism; ph = ph_ref; }
     }
     out[0] = (double)mism; out[1] = (double)walked; out[2] = ph_ref; out[3] = ph_ref - approx_sum;
+}
+
+// block_phase_q_steps (the step-function form k_phase_q uses) against block_phase_q (every sample) on `cases` random blocks:
+// Doppler +-6 kHz, change over the block up to +-span_hz (both signs, zero crossings included), binade k in [k_lo, k_hi], both
+// division forms.  out[0] = cases where Q or the tie flag differ (must be 0), out[1] = cases the step form declined (more
+// than max_steps levels), out[2] = largest number of levels seen, out[3] = cases with a tie.
+void emu_phase_q_steps_check(uint64_t seed, uint32_t cases, double span_hz, int k_lo, int k_hi, uint32_t n, uint32_t max_steps, double* out)
+{
+    const double fs = 5e6, inv_fs = 1.0 / fs;
+    uint64_t st = seed * 0x9E3779B97F4A7C15ull + 0x632BE59BD9B4E019ull;
+    auto rnd = [&]() { st ^= st << 13; st ^= st >> 7; st ^= st << 17; return (double)(st >> 11) * (1.0 / 9007199254740992.0); };
+    uint64_t bad = 0, declined = 0, ties = 0;
+    long long max_levels = 0;
+    for (uint32_t c = 0; c < cases; ++c) {
+        double ds = (rnd() * 2.0 - 1.0) * 6000.0;
+        if (c % 17 == 0) ds = (rnd() * 2.0 - 1.0) * span_hz * 0.5;                 // zero crossings
+        double de = ds + (rnd() * 2.0 - 1.0) * span_hz;
+        if (c % 23 == 0) de = ds;
+        if (c % 29 == 0) { ds = ldexp(floor(ldexp(ds, 20)), -20); de = ds; }       // few mantissa bits: plateaus, ties more likely
+        const int k = k_lo + (int)(rnd() * (double)(k_hi - k_lo + 1));
+        long long q_ref = 0, q = 0;
+        bool tie_ref = false, tie = false;
+        block_phase_q(ds, de, n, fs, k, &q_ref, &tie_ref);
+        if (tie_ref) ++ties;
+        const int div = (int)(c & 1u);
+        if (!block_phase_q_steps(ds, de, n, fs, inv_fs, div, k, max_steps, &q, &tie)) { ++declined; continue; }
+        if (tie != tie_ref || (!tie && q != q_ref)) ++bad;                         // with a tie the block is walked and Q unused (rint vs round-half-down)
+        // levels, for the statistics
+        const double x0 = scalbn(ref_phase_inc(ds, de, 0, (double)n, fs), 52 - k), x1 = scalbn(ref_phase_inc(ds, de, n - 1, (double)n, fs), 52 - k);
+        max_levels = std::max(max_levels, (long long)fabs(x1 - x0));
+    }
+    out[0] = (double)bad; out[1] = (double)declined; out[2] = (double)max_levels; out[3] = (double)ties;
 }
 
 int emu_scenario_create(const r4wb_scenario_cfg* cfg, void** out)

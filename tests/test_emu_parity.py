@@ -284,6 +284,21 @@ def test_antenna_patterns_replay_matches_oracle(oracle, emu, kind):
     assert _relrms(got, want) <= TOL
 
 
+@pytest.mark.parametrize("span_hz,k_lo,k_hi,n,max_steps", [(2e-3, 14, 26, 5000, 1024), (5e-2, 17, 30, 5000, 1024), (2e-3, 8, 13, 5000, 1024),
+                                                            (1.0, 20, 24, 5000, 64), (2e-3, 16, 24, 1234, 1024), (0.5, 30, 40, 5000, 1024)])
+def test_phase_q_step_form_equals_per_sample_sum(emu, span_hz, k_lo, k_hi, n, max_steps):
+    """k_phase_q's block sum Q = sum_i rint(inc_i / ulp) is formed from the step positions of the monotone sequence rint(inc_i / ulp)
+    (block_phase_q_steps: each step located by interpolation and proven with the exact increment chain on both sides) instead of
+    visiting the 5000 samples; it must equal the per-sample sum (block_phase_q) bit for bit, tie flag included — rising, falling
+    and constant Doppler, zero crossings, coarse-mantissa Dopplers (plateaus), both division forms, few and many levels"""
+    bad, declined, levels, ties = emu.phase_q_steps_check(20260, 3000, span_hz, k_lo, k_hi, n, max_steps)
+    assert bad == 0
+    if (span_hz, k_lo) == (2e-3, 14):
+        assert declined == 0 and levels >= 50        # the production regime: every block answered, dozens of levels exercised
+    if max_steps == 64:
+        assert declined > 0                          # blocks with more levels than allowed are handed back, not guessed
+
+
 @pytest.mark.parametrize("d0,rate,jerk,blocks", [(2779.31, -0.42, 0.0, 20000), (-2831.7, 0.35, 0.0, 20000), (35.0, -0.9, 0.0, 60000),
                                                  (-457.3938, 0.0, 1e-4, 20000), (0.0, 0.0, 0.0, 50)])
 def test_exact_phase_model_equals_sequential_accumulation(emu, d0, rate, jerk, blocks):

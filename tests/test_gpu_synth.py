@@ -467,6 +467,13 @@ def test_parallel_exact_phase_equals_serial_walk(gpu):
     assert _run_py(_PHASE_HASH, {}) == _run_py(_PHASE_HASH, {"R4WB_PHASE_SERIAL": "1"})
 
 
+def test_phase_q_step_form_equals_per_sample_sum_on_device(gpu):
+    """k_phase_q forms each block's integer phase sum from the step positions of the rounded increments (block_phase_q_steps); with
+    R4WB_PHASE_Q_BRUTE=1 it visits all 5000 samples of all 4.8 M (block, satellite) entries as round 2's first version did:
+    byte-identical IQ at the start, in the middle and at the end of the 600 s file"""
+    assert _run_py(_PHASE_HASH, {}) == _run_py(_PHASE_HASH, {"R4WB_PHASE_Q_BRUTE": "1"})
+
+
 def test_class_table_path_equals_arithmetic_path(gpu):
     """k_synth with the boundary-age class table and with the arithmetic floor sums: byte-identical IQ (noise on)"""
     off = {"R4WB_SYNTH_LATTICE": "0"}                      # keep both runs on k_synth (the lattice kernel needs the class table)
