@@ -24,7 +24,8 @@ void launch_synth_direct(const SynthArgs& a, r4wb_fmt fmt, cudaStream_t st);
 void launch_block_params(const ScenConst&, const SatConst*, const PhaseSegment*, uint64_t, uint32_t, BlockSat*, BlockHdr*, double*, double*, cudaStream_t);
 bool launch_phase_exact(const ScenConst&, const SatConst*, uint32_t, BlockSat*, const double*, const double*, unsigned char* scratch, cudaStream_t);
 size_t phase_exact_scratch_bytes(uint32_t n_sats, uint32_t nblk, uint32_t B);
-void launch_phase_scan(const SatConst*, uint32_t, uint32_t, BlockSat*, cudaStream_t);
+void launch_phase_scan(const SatConst*, uint32_t, uint32_t, BlockSat*, void* scratch, cudaStream_t);
+size_t scan_scratch_bytes(uint32_t n_sats, uint32_t nblk);
 void launch_tile_params(const SynthArgs& a, uint32_t tb_begin, uint32_t tb_count, uint32_t tile_samples, TileRec* out, cudaStream_t st);
 // lattice kernel (synth_lattice.cu)
 bool lat_supported(const SynthArgs& a);
@@ -228,12 +229,13 @@ void Scenario::build_canonical_table(uint64_t blk_begin, uint64_t blk_end, uint6
     const SynthArgs a_tiles = base_args(d_tab_.p, d_hdr_.p, sc.B);
     const size_t ne = (size_t)nblk * sc.n_sats;
     auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
-    const size_t scratch_bytes = exact_phase ? al(2 * ne * sizeof(double)) + al(ne * sizeof(double)) + phase_exact_scratch_bytes(sc.n_sats, (uint32_t)nblk, (uint32_t)sc.B) : 0;
+    const size_t scan_bytes = scan_scratch_bytes(sc.n_sats, (uint32_t)nblk);           // k_phase_scan's chunk carries: first in the buffer
+    const size_t scratch_bytes = scan_bytes + (exact_phase ? al(2 * ne * sizeof(double)) + al(ne * sizeof(double)) + phase_exact_scratch_bytes(sc.n_sats, (uint32_t)nblk, (uint32_t)sc.B) : 0);
     d_tiles_.reserve(std::max<size_t>(std::max<size_t>(1, (size_t)nblk * a_tiles.tiles_per_block * sc.n_sats), (scratch_bytes + sizeof(TileRec) - 1) / sizeof(TileRec)));
     double *dop = nullptr, *papprox = nullptr;
     unsigned char* pscratch = nullptr;
     if (exact_phase) {
-        unsigned char* sp = reinterpret_cast<unsigned char*>(d_tiles_.p);
+        unsigned char* sp = reinterpret_cast<unsigned char*>(d_tiles_.p) + scan_bytes;
         dop = reinterpret_cast<double*>(sp); sp += al(2 * ne * sizeof(double));
         papprox = reinterpret_cast<double*>(sp); sp += al(ne * sizeof(double));
         pscratch = sp;
@@ -249,7 +251,7 @@ void Scenario::build_canonical_table(uint64_t blk_begin, uint64_t blk_end, uint6
         R4WB_CUDA(cudaMemcpyAsync(d_hdr_.p, h.data(), nblk * sizeof(BlockHdr), cudaMemcpyHostToDevice, st));
         R4WB_CUDA(cudaStreamSynchronize(st));
     }
-    if (md_.any_dynamic || md_.any_var_visibility) launch_phase_scan(d_sat_.p, sc.n_sats, (uint32_t)nblk, d_tab_.p, st);
+    if (md_.any_dynamic || md_.any_var_visibility) launch_phase_scan(d_sat_.p, sc.n_sats, (uint32_t)nblk, d_tab_.p, d_tiles_.p, st);
     if (exact_phase) phase_parallel_ = launch_phase_exact(sc, d_sat_.p, (uint32_t)nblk, d_tab_.p, dop, papprox, pscratch, st);
     if (trace) { cudaStreamSynchronize(st); t_phase = now(); }
     tab_blk0_ = blk_begin;

@@ -313,6 +313,11 @@ R4WB_HD double ref_phase_inc(double ds, double de, uint32_t i, double n_f64, dou
     return div_rn(mul_rn(6.283185307179586, dop), fs);
 }
 
+// Smallest binade the integer-sum model is formed for.  Below it the phase crosses a binade (or an increment lands exactly
+// half-way between two multiples of the ulp: probability ~2^(-8.6-k) per sample) in most blocks anyway, so they are walked
+// sample by sample.  x = inc 2^(52-k) stays below 2^41 (rint trick: 2^51; the per-sample sum is formed in int64).
+constexpr int kPhaseMinBinade = 5;
+
 struct PhaseQ {
     long long Q;        // sum over the block of rint(inc_i / 2^(k-52))
     double approx;      // real-number sum of the block's increments (0 when the satellite is not visible)

@@ -132,7 +132,7 @@ __global__ void k_phase_frac(uint32_t n, double* __restrict__ frac)
 
 // One thread per (block, satellite): the integer sum of the block's increments rounded to the ulp of the predicted binade.
 // PhaseQ.ok: bit0 = Q usable while the phase stays in binade k, bit1 = "walk" block (predicted phase does not provably stay inside
-// the binade over the block, a tie, or a start below 2^8 rad)
+// the binade over the block, a tie, or a start below 2^kPhaseMinBinade rad)
 // fast_div: a / fs as q = a y, r = fma(-q, fs, a), q' = fma(r, y, q) with y = RN(1 / fs) — the correctly rounded quotient
 // (Markstein), three FP64 instructions instead of the ~35 of a division; the host verifies it for the scenario's fs first
 constexpr uint32_t kPhaseQMaxSteps = 256;
@@ -153,7 +153,7 @@ __global__ void k_phase_q(double fs, double inv_fs, int fast_div, int step_form,
         const double p = pstart[idx];
         if (p != 0.0) {
             r.k = ilogb(p);
-            if (r.k >= 8) {
+            if (r.k >= kPhaseMinBinade) {
                 bool tie = false;
                 // Q from the step positions of the monotone sequence rint(inc_i / ulp) (block_phase_q_steps: ~2 + 2 levels exact
                 // increment chains instead of n); blocks with more than kPhaseQMaxSteps levels — the first second or two of a
@@ -161,11 +161,11 @@ __global__ void k_phase_q(double fs, double inv_fs, int fast_div, int step_form,
                 if (!step_form || !block_phase_q_steps(ds, de, e.n, fs, inv_fs, fast_div, r.k, kPhaseQMaxSteps, &r.Q, &tie)) {
                     tie = false;
                     if (e.n == frac_n) {
-                        // The same increments as block_phase_q (i / n from the table), rounded to the ulp of binade k without
-                        // leaving FP64: x = inc 2^(52-k) (exact), y = rint(x) by the 1.5 2^52 trick (|x| < 2^37 here), sum of the
-                        // y exact in a double (< 2^50).  rint differs from block_phase_q's floor + (r > 0.5) only at an exact
-                        // tie, and a block with a tie is walked sample by sample anyway.
-                        double qd = 0.0;
+                        // The same increments as block_phase_q (i / n from the table), rounded to the ulp of binade k:
+                        // x = inc 2^(52-k) (exact), y = rint(x) by the 1.5 2^52 trick (|x| < 2^41 here), summed in int64.
+                        // rint differs from block_phase_q's floor + (r > 0.5) only at an exact tie, and a block with a tie
+                        // is walked sample by sample anyway.
+                        long long qd = 0;
                         const double dd = add_rn(de, -ds);
                         const double scale = scalbn(1.0, 52 - r.k), magic = 6755399441055744.0;
                         for (uint32_t i = 0; i < e.n; ++i) {
@@ -181,9 +181,9 @@ __global__ void k_phase_q(double fs, double inv_fs, int fast_div, int step_form,
                             const double x = mul_rn(inc, scale);
                             const double y = add_rn(add_rn(x, magic), -magic);
                             if (fabs(add_rn(x, -y)) == 0.5) tie = true;
-                            qd = add_rn(qd, y);
+                            qd += (long long)y;
                         }
-                        r.Q = (long long)qd;
+                        r.Q = qd;
                     } else {
                         block_phase_q(ds, de, e.n, fs, r.k, &r.Q, &tie);
                     }
@@ -336,6 +336,165 @@ __global__ void __launch_bounds__(32) k_phase_exact(double fs, const SatConst* _
     }
 }
 
+
+// ---- chunked scans over the blocks of every satellite ---------------------------------------------------------------------------
+// The three per-satellite scans of the prologue (phase advance / last visible block, approximate phase, integer run sums) each
+// ran as one 1024-thread CTA per satellite: 8 SMs busy, every thread striding through its own 1/1024 of the table.  Here the
+// blocks are cut into chunks of 1024: k_chunk_reduce (grid chunks x satellites) -> per-chunk totals, k_chunk_carry (one CTA per
+// satellite) -> exclusive carries of the chunks, k_chunk_apply (grid chunks x satellites) -> exclusive scan inside the chunk plus
+// the carry.  An Op supplies the value type T, identity(), comb() (associative), load(block, sat), store(block, sat, exclusive
+// prefix) and finish(sat, total).  Integer sums wrap identically in any order; the one floating-point scan (approximate phase)
+// only predicts binades and is verified by k_phase_fill.
+constexpr uint32_t kScanChunk = 1024;
+
+template <class Op>
+__global__ void __launch_bounds__(kScanChunk) k_chunk_reduce(Op op, uint32_t n_sats, uint32_t nblk, typename Op::T* __restrict__ partial)
+{
+    using T = typename Op::T;
+    __shared__ T sh[kScanChunk];
+    const uint32_t c = blockIdx.x, s = blockIdx.y, t = threadIdx.x;
+    const uint32_t b = c * kScanChunk + t;
+    sh[t] = b < nblk ? op.load(b, s) : Op::identity();
+    __syncthreads();
+    for (uint32_t half = kScanChunk / 2; half > 0; half >>= 1) {
+        if (t < half) sh[t] = Op::comb(sh[t], sh[t + half]);
+        __syncthreads();
+    }
+    if (t == 0) partial[(size_t)c * n_sats + s] = sh[0];
+}
+
+// partial[c][s]: totals in, exclusive carries out
+template <class Op>
+__global__ void __launch_bounds__(1024) k_chunk_carry(Op op, uint32_t n_sats, uint32_t n_chunks, typename Op::T* __restrict__ partial)
+{
+    using T = typename Op::T;
+    __shared__ T sh[1024];
+    const uint32_t s = blockIdx.x, t = threadIdx.x;
+    const uint32_t per = (n_chunks + 1023u) / 1024u;
+    const uint32_t lo = min(n_chunks, t * per), hi = min(n_chunks, lo + per);
+    T sum = Op::identity();
+    for (uint32_t c = lo; c < hi; ++c) sum = Op::comb(sum, partial[(size_t)c * n_sats + s]);
+    sh[t] = sum;
+    __syncthreads();
+    for (int off = 1; off < 1024; off <<= 1) {
+        T v = Op::identity();
+        if ((int)t >= off) v = sh[t - off];
+        __syncthreads();
+        if ((int)t >= off) sh[t] = Op::comb(v, sh[t]);
+        __syncthreads();
+    }
+    T run = t > 0 ? sh[t - 1] : Op::identity();
+    for (uint32_t c = lo; c < hi; ++c) {
+        const T v = partial[(size_t)c * n_sats + s];
+        partial[(size_t)c * n_sats + s] = run;
+        run = Op::comb(run, v);
+    }
+    if (t == 1023) op.finish(s, sh[1023]);
+}
+
+template <class Op>
+__global__ void __launch_bounds__(kScanChunk) k_chunk_apply(Op op, uint32_t n_sats, uint32_t nblk, const typename Op::T* __restrict__ carry)
+{
+    using T = typename Op::T;
+    __shared__ T sh[kScanChunk];
+    const uint32_t c = blockIdx.x, s = blockIdx.y, t = threadIdx.x;
+    const uint32_t b = c * kScanChunk + t;
+    const T mine = b < nblk ? op.load(b, s) : Op::identity();
+    sh[t] = mine;
+    __syncthreads();
+    for (int off = 1; off < (int)kScanChunk; off <<= 1) {
+        T v = Op::identity();
+        if ((int)t >= off) v = sh[t - off];
+        __syncthreads();
+        if ((int)t >= off) sh[t] = Op::comb(v, sh[t]);
+        __syncthreads();
+    }
+    if (b >= nblk) return;
+    T ex = carry[(size_t)c * n_sats + s];
+    if (t > 0) ex = Op::comb(ex, sh[t - 1]);
+    op.store(b, s, ex, mine);
+}
+
+template <class Op>
+static void chunk_scan(const Op& op, uint32_t n_sats, uint32_t nblk, void* scratch, cudaStream_t st)
+{
+    using T = typename Op::T;
+    if (nblk == 0 || n_sats == 0) return;
+    const uint32_t n_chunks = (nblk + kScanChunk - 1) / kScanChunk;
+    T* partial = reinterpret_cast<T*>(scratch);
+    k_chunk_reduce<Op><<<dim3(n_chunks, n_sats), kScanChunk, 0, st>>>(op, n_sats, nblk, partial);
+    R4WB_LAUNCH_CHECK();
+    k_chunk_carry<Op><<<n_sats, 1024, 0, st>>>(op, n_sats, n_chunks, partial);
+    R4WB_LAUNCH_CHECK();
+    k_chunk_apply<Op><<<dim3(n_chunks, n_sats), kScanChunk, 0, st>>>(op, n_sats, nblk, partial);
+    R4WB_LAUNCH_CHECK();
+}
+
+// bytes chunk_scan needs for any of the Ops below (T is at most 16 bytes)
+size_t scan_scratch_bytes(uint32_t n_sats, uint32_t nblk)
+{
+    const size_t n_chunks = ((size_t)nblk + kScanChunk - 1) / kScanChunk;
+    return ((n_chunks * std::max(1u, n_sats) * 16) + 255) & ~(size_t)255;
+}
+
+// k_phase_scan as an Op: exclusive sum of the block advances (dynamic satellites) and the last visible block before each block
+struct ScanAdvanceOp {
+    struct T { uint64_t sum; int last; int pad; };
+    const SatConst* sats; BlockSat* tab; uint32_t n_sats;
+    __device__ static T identity() { return T{0ull, -1, 0}; }
+    __device__ static T comb(const T& a, const T& b) { return T{a.sum + b.sum, max(a.last, b.last), 0}; }
+    __device__ T load(uint32_t b, uint32_t s) const
+    {
+        const BlockSat& e = tab[(size_t)b * n_sats + s];
+        return T{sats[s].static_phase ? 0ull : e.phi, (e.flags & 1u) ? (int)b : -1, 0};
+    }
+    __device__ void store(uint32_t b, uint32_t s, const T& ex, const T&) const
+    {
+        BlockSat& e = tab[(size_t)b * n_sats + s];
+        if (!sats[s].static_phase) e.phi = ex.sum;
+        e.prev = ex.last >= 0 ? (int32_t)((uint32_t)ex.last * n_sats + s) : -1;
+    }
+    __device__ void finish(uint32_t, const T&) const {}
+};
+
+// k_phase_prefix as an Op: predicted (real-number) phase at the start of every block
+struct ScanApproxOp {
+    using T = double;
+    const double* papprox; double* pstart; uint32_t n_sats;
+    __device__ static T identity() { return 0.0; }
+    __device__ static T comb(const T& a, const T& b) { return a + b; }
+    __device__ T load(uint32_t b, uint32_t s) const { return papprox[(size_t)b * n_sats + s]; }
+    __device__ void store(uint32_t b, uint32_t s, const T& ex, const T&) const { pstart[(size_t)b * n_sats + s] = ex; }
+    __device__ void finish(uint32_t, const T&) const {}
+};
+
+// k_phase_runs as an Op: wrapping sum of Q over the non-walk blocks before each block, ordered list of the walk blocks
+struct ScanRunsOp {
+    struct T { unsigned long long sum; uint32_t cnt; uint32_t pad; };
+    const SatConst* sats; const PhaseQ* pq; unsigned long long* prefq; uint32_t* wlist; uint32_t* nwalk; uint32_t n_sats, nblk;
+    __device__ static T identity() { return T{0ull, 0u, 0u}; }
+    __device__ static T comb(const T& a, const T& b) { return T{a.sum + b.sum, a.cnt + b.cnt, 0u}; }
+    __device__ T load(uint32_t b, uint32_t s) const
+    {
+        if (sats[s].static_phase) return identity();
+        const PhaseQ& r = pq[(size_t)b * n_sats + s];
+        return (r.ok & 2u) ? T{0ull, 1u, 0u} : T{(unsigned long long)r.Q, 0u, 0u};
+    }
+    __device__ void store(uint32_t b, uint32_t s, const T& ex, const T& mine) const
+    {
+        if (sats[s].static_phase) return;
+        prefq[(size_t)b * n_sats + s] = ex.sum;
+        if (mine.cnt) wlist[(size_t)s * nblk + ex.cnt] = b;
+    }
+    __device__ void finish(uint32_t s, const T& total) const { nwalk[s] = total.cnt; }
+};
+
+static bool scan_per_satellite()
+{
+    static const bool v = [] { const char* e = std::getenv("R4WB_SCAN_PER_SAT"); return e && e[0] == '1'; }();   // A/B hook: round 2's first scans
+    return v;
+}
+
 // scratch of the exact-phase pass (caller-owned, sized by phase_exact_scratch_bytes)
 struct PhaseScratch {
     double* pstart; PhaseQ* pq; double* frac; unsigned long long* prefq; uint32_t* wlist; uint32_t* nwalk; double* runph; uint32_t* bad;
@@ -345,7 +504,8 @@ size_t phase_exact_scratch_bytes(uint32_t n_sats, uint32_t nblk, uint32_t B)
 {
     const size_t ne = (size_t)nblk * n_sats;
     auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
-    return al(ne * 8) + al(ne * sizeof(PhaseQ)) + al((size_t)B * 8) + al(ne * 8) + al(ne * 4) + al((size_t)n_sats * 4 + 4) + al((ne + n_sats) * 8) + 256;
+    return al(ne * 8) + al(ne * sizeof(PhaseQ)) + al((size_t)B * 8) + al(ne * 8) + al(ne * 4) + al((size_t)n_sats * 4 + 4) + al((ne + n_sats) * 8) + 256 +
+           scan_scratch_bytes(n_sats, nblk);
 }
 
 // returns false when the parallel pass found a violation of its own premise and the serial kernel was run instead
@@ -365,10 +525,15 @@ bool launch_phase_exact(const ScenConst& sc, const SatConst* d_sats, uint32_t nb
     S.wlist = reinterpret_cast<uint32_t*>(p); p += al(ne * 4);
     S.nwalk = reinterpret_cast<uint32_t*>(p); p += al((size_t)ns * 4 + 4);
     S.runph = reinterpret_cast<double*>(p); p += al((ne + ns) * 8);
-    S.bad = reinterpret_cast<uint32_t*>(p);
+    S.bad = reinterpret_cast<uint32_t*>(p); p += 256;
+    void* scan_scratch = p;
 
-    k_phase_prefix<<<ns, 1024, 0, st>>>(ns, nblk, d_papprox, S.pstart);
-    R4WB_LAUNCH_CHECK();
+    if (scan_per_satellite()) {
+        k_phase_prefix<<<ns, 1024, 0, st>>>(ns, nblk, d_papprox, S.pstart);
+        R4WB_LAUNCH_CHECK();
+    } else {
+        chunk_scan(ScanApproxOp{d_papprox, S.pstart, ns}, ns, nblk, scan_scratch, st);
+    }
     k_phase_frac<<<(unsigned)((sc.B + 255) / 256), 256, 0, st>>>((uint32_t)sc.B, S.frac);
     R4WB_LAUNCH_CHECK();
     // exact-division shortcut, checked on the host for this sample rate over the magnitudes 2 pi |Doppler| can take
@@ -396,8 +561,12 @@ bool launch_phase_exact(const ScenConst& sc, const SatConst* d_sats, uint32_t nb
     uint32_t bad = 0;
     if (!serial) {
         R4WB_CUDA(cudaMemsetAsync(S.bad, 0, sizeof(uint32_t), st));
-        k_phase_runs<<<ns, 1024, 0, st>>>(d_sats, ns, nblk, S.pq, S.prefq, S.wlist, S.nwalk);
-        R4WB_LAUNCH_CHECK();
+        if (scan_per_satellite()) {
+            k_phase_runs<<<ns, 1024, 0, st>>>(d_sats, ns, nblk, S.pq, S.prefq, S.wlist, S.nwalk);
+            R4WB_LAUNCH_CHECK();
+        } else {
+            chunk_scan(ScanRunsOp{d_sats, S.pq, S.prefq, S.wlist, S.nwalk, ns, nblk}, ns, nblk, scan_scratch, st);
+        }
         k_phase_chain<<<ns, 32, 0, st>>>(sc.fs, d_sats, ns, nblk, d_tab, d_dop, S.prefq, S.wlist, S.nwalk, S.runph);
         R4WB_LAUNCH_CHECK();
         k_phase_fill<<<(unsigned)((ne + 127) / 128), 128, 0, st>>>(d_sats, ns, nblk, d_tab, S.pq, S.prefq, S.wlist, S.nwalk, S.runph, S.bad);
@@ -422,11 +591,16 @@ void launch_block_params(const ScenConst& sc, const SatConst* d_sats, const Phas
     R4WB_LAUNCH_CHECK();
 }
 
-void launch_phase_scan(const SatConst* d_sats, uint32_t n_sats, uint32_t nblk, BlockSat* d_tab, cudaStream_t st)
+// scratch: scan_scratch_bytes(n_sats, nblk) of device memory
+void launch_phase_scan(const SatConst* d_sats, uint32_t n_sats, uint32_t nblk, BlockSat* d_tab, void* scratch, cudaStream_t st)
 {
     if (nblk == 0 || n_sats == 0) return;
-    k_phase_scan<<<n_sats, 1024, 0, st>>>(d_sats, n_sats, nblk, d_tab);
-    R4WB_LAUNCH_CHECK();
+    if (scan_per_satellite()) {
+        k_phase_scan<<<n_sats, 1024, 0, st>>>(d_sats, n_sats, nblk, d_tab);
+        R4WB_LAUNCH_CHECK();
+    } else {
+        chunk_scan(ScanAdvanceOp{d_sats, d_tab, n_sats}, n_sats, nblk, scratch, st);
+    }
 }
 
 }  // namespace r4wb

@@ -67,6 +67,7 @@ struct Emu {
             }
         }
         if (exact_phase) {
+            const bool steps_diag = std::getenv("R4WB_EMU_PHASE_STEPS") != nullptr;
             std::vector<PhaseQ> pq((size_t)nblk * ns);
             for (uint32_t s = 0; s < ns; ++s) {
                 if (md.sats[s].static_phase) continue;
@@ -86,10 +87,27 @@ struct Emu {
                     PhaseQ& r = pq[b * ns + s];
                     if (!(e.flags & 1u) || start[b] == 0.0) continue;
                     r.k = ilogb(start[b]);
-                    if (r.k < 8) continue;
+                    if (r.k < kPhaseMinBinade) continue;
                     bool tie;
-                    block_phase_q(dop[2 * (b * ns + s)], dop[2 * (b * ns + s) + 1], e.n, sc.fs, r.k, &r.Q, &tie);
+                    // the replay sums every sample (the independent check of the device's step form); R4WB_EMU_PHASE_STEPS=1
+                    // switches to the step form so that a whole 600 s table can be replayed for statistics
+                    if (!(steps_diag && block_phase_q_steps(dop[2 * (b * ns + s)], dop[2 * (b * ns + s) + 1], e.n, sc.fs, 1.0 / sc.fs, 0, r.k, 256u, &r.Q, &tie)))
+                        block_phase_q(dop[2 * (b * ns + s)], dop[2 * (b * ns + s) + 1], e.n, sc.fs, r.k, &r.Q, &tie);
                     r.ok = tie ? 0u : 1u;
+                }
+                if (steps_diag) {                                        // why blocks are walked (diagnostic)
+                    uint64_t n_small = 0, n_tie = 0, n_pred = 0, n_vis = 0;
+                    for (uint64_t b = 0; b < nblk; ++b) {
+                        const BlockSat& e = tab[b * ns + s];
+                        if (!(e.flags & 1u)) continue;
+                        ++n_vis;
+                        const PhaseQ& r = pq[b * ns + s];
+                        if (start[b] == 0.0 || r.k < kPhaseMinBinade) ++n_small;
+                        else if (!r.ok) ++n_tie;
+                        else if (!phase_stays_in_binade(start[b], r)) ++n_pred;
+                    }
+                    std::fprintf(stderr, "[emu phase] sat %u: %llu visible blocks, walk: start below the first binade %llu, tie %llu, binade margin %llu\n", s,
+                                 (unsigned long long)n_vis, (unsigned long long)n_small, (unsigned long long)n_tie, (unsigned long long)n_pred);
                 }
                 double ph = 0.0;                                         // k_phase_exact
                 for (uint64_t b = 0; b < nblk; ++b) {
@@ -321,7 +339,7 @@ void emu_phase_model_check(double d0, double rate, double jerk, uint64_t blocks,
         block_phase_approx(ds, de, n, fs, &r.approx, &r.span);
         if (approx_sum != 0.0) {
             r.k = ilogb(approx_sum);
-            if (r.k >= 8) {
+            if (r.k >= kPhaseMinBinade) {
                 bool tie;
                 block_phase_q(ds, de, n, fs, r.k, &r.Q, &tie);
                 r.ok = tie ? 0u : 1u;

@@ -474,6 +474,13 @@ def test_phase_q_step_form_equals_per_sample_sum_on_device(gpu):
     assert _run_py(_PHASE_HASH, {}) == _run_py(_PHASE_HASH, {"R4WB_PHASE_Q_BRUTE": "1"})
 
 
+def test_chunked_prologue_scans_equal_per_satellite_scans(gpu):
+    """the prologue's three scans over the blocks of a satellite (phase advance / last visible block, predicted phase, integer run
+    sums + walk list) as chunk reduce / carry / apply over the whole GPU against one CTA per satellite (R4WB_SCAN_PER_SAT=1):
+    byte-identical IQ at the start, in the middle and at the end of the 600 s file"""
+    assert _run_py(_PHASE_HASH, {}) == _run_py(_PHASE_HASH, {"R4WB_SCAN_PER_SAT": "1"})
+
+
 def test_class_table_path_equals_arithmetic_path(gpu):
     """k_synth with the boundary-age class table and with the arithmetic floor sums: byte-identical IQ (noise on)"""
     off = {"R4WB_SYNTH_LATTICE": "0"}                      # keep both runs on k_synth (the lattice kernel needs the class table)
