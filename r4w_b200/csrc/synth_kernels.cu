@@ -30,28 +30,78 @@ __global__ void k_tile_params(SynthArgs a, uint32_t tb_begin, uint32_t tb_count,
 {
     const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint64_t total = (uint64_t)tb_count * a.tiles_per_block * a.n_sats;
-    if (idx >= total) return;
-    const uint32_t s = (uint32_t)(idx % a.n_sats);
-    const uint32_t tile = (uint32_t)(idx / a.n_sats);
-    const uint32_t tb = tb_begin + tile / a.tiles_per_block, chunk = tile % a.tiles_per_block;
+    const bool live = idx < total;                      // no early exit: the literal-FIR part below is warp-cooperative
+    const uint32_t lane = threadIdx.x & 31u;
     const SynthK KK = make_synth_k(a.delta46, a.kmul, a.cj, a.dsum0, a.spc, a.lut_den, a.ystride);
-    const BlockSat* row = a.tab + (size_t)tb * a.n_sats;
-    const BlockHdr hd = a.hdr[tb];
+    uint32_t s = 0, tb = 0, chunk = 0;
     TileRec r;
-    r.ts = tile_sat(row[s], a.tab, chunk * tile_samples, KK.d8);
+    bool literal = false;                               // first 8 outputs by the reference's own 63-tap loop
+    if (live) {
+        s = (uint32_t)(idx % a.n_sats);
+        const uint32_t tile = (uint32_t)(idx / a.n_sats);
+        tb = tb_begin + tile / a.tiles_per_block; chunk = tile % a.tiles_per_block;
+        const BlockSat* row = a.tab + (size_t)tb * a.n_sats;
+        const BlockHdr hd = a.hdr[tb];
+        r.ts = tile_sat(row[s], a.tab, chunk * tile_samples, KK.d8);
+        const bool fix = chunk == 0 && (r.ts.flags & 9u) == 9u;
+        literal = fix && ((row[s].flags & 2u) || (row[s].prev >= 0 && (a.tab[row[s].prev].flags & 2u)));   // fir_block_start's own test
 #pragma unroll 1
-    for (int i = 0; i < 8; ++i) {
-        float y = 0.0f;
-        if (chunk == 0 && (r.ts.flags & 9u) == 9u && (uint32_t)i < hd.n)
-            y = fir_block_start(row[s], a.tab, a.perbits + (size_t)s * kPerWords, a.taps, a.etab, i, KK, a.satcode[s]);
-        r.yfix[i] = y;
+        for (int i = 0; i < 8; ++i) {
+            float y = 0.0f;
+            if (fix && !literal && (uint32_t)i < hd.n)
+                y = fir_block_start(row[s], a.tab, a.perbits + (size_t)s * kPerWords, a.taps, a.etab, i, KK, a.satcode[s]);
+            r.yfix[i] = y;
+        }
+        r.lat = TileLat{};
+        if (a.lat.q != 0 && chunk == 0) {
+            r.lat = tile_lat(row[s], a.lat, a.perbits + (size_t)s * kPerWords, a.spc, a.satcode[s]);
+            if (a.stats && (r.ts.flags & 1u) && !lat_rotation_ok(r.ts)) atomicAdd(a.stats, 1u);
+        }
     }
-    r.lat = TileLat{};
-    if (a.lat.q != 0 && chunk == 0) {
-        r.lat = tile_lat(row[s], a.lat, a.perbits + (size_t)s * kPerWords, a.spc, a.satcode[s]);
-        if (a.stats && (r.ts.flags & 1u) && !lat_rotation_ok(r.ts)) atomicAdd(a.stats, 1u);
+    // Records with a half-chip boundary inside the f64 rounding band (about one in 150) need fir_direct for their 8 outputs:
+    // 8 x 63 literal chip-index evaluations.  Done per lane, one such record made its whole warp wait for ~120 000
+    // instructions (93 % of this kernel's time).  The 8 windows span oversamples [-62, 56] of the block: the warp resolves
+    // those 119 signs once (lane l: oversamples l - 62 + 32 r), ballots publish them, and lanes 0..7 add the 63 taps of output
+    // i in the reference's order — the same f32 sums as fir_direct, bit for bit.
+    unsigned m = __ballot_sync(0xffffffffu, literal);
+    while (m) {
+        const int src = __ffs((int)m) - 1;
+        m &= m - 1u;
+        const uint32_t s_src = __shfl_sync(0xffffffffu, s, src), tb_src = __shfl_sync(0xffffffffu, tb, src);
+        const BlockSat& cur = a.tab[(size_t)tb_src * a.n_sats + s_src];
+        const uint32_t* per = a.perbits + (size_t)s_src * kPerWords;
+        const SatCode cd = a.satcode[s_src];
+        const uint32_t n_blk = a.hdr[tb_src].n;
+        const long long base = -(long long)(kTaps - 1);
+        unsigned neg[4], val[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int sgn = tap_sign(cur, a.tab, per, base + (long long)lane + 32 * q, 0, a.delta46, a.spc, cd);
+            neg[q] = __ballot_sync(0xffffffffu, sgn == 1);
+            val[q] = __ballot_sync(0xffffffffu, sgn >= 0);
+        }
+        float acc = 0.0f;
+        if (lane < 8u && lane < n_blk) {
+            const unsigned long long negA = neg[0] | ((unsigned long long)neg[1] << 32), negB = neg[2] | ((unsigned long long)neg[3] << 32);
+            const unsigned long long valA = val[0] | ((unsigned long long)val[1] << 32), valB = val[2] | ((unsigned long long)val[3] << 32);
+            const int lo = kOversample * (int)lane;                            // window of output `lane`: span indices lo .. lo + 62
+            unsigned long long wn, wv;
+            if (lo == 0) { wn = negA; wv = valA; }
+            else { wn = (negA >> lo) | (negB << (64 - lo)); wv = (valA >> lo) | (valB << (64 - lo)); }   // lo <= 56
+            for (int k = 0; k < kTaps; ++k) {                                  // the reference's order; an absent tap adds nothing
+                const int j = kTaps - 1 - k;
+                if (!((wv >> j) & 1ull)) continue;
+                const float t = a.taps[k];
+                acc += ((wn >> j) & 1ull) ? -t : t;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float v = __shfl_sync(0xffffffffu, acc, i);
+            if ((int)lane == src) r.yfix[i] = v;
+        }
     }
-    out[((size_t)tb * a.tiles_per_block + chunk) * a.n_sats + s] = r;
+    if (live) out[((size_t)tb * a.tiles_per_block + chunk) * a.n_sats + s] = r;
 }
 
 void launch_tile_params(const SynthArgs& a, uint32_t tb_begin, uint32_t tb_count, uint32_t tile_samples, TileRec* out, cudaStream_t st)
