@@ -12,6 +12,8 @@
 #include <cmath>
 #include <cstdlib>
 
+#include <mutex>
+
 #include "synth_math.cuh"
 
 namespace r4wb {
@@ -537,8 +539,10 @@ bool launch_phase_exact(const ScenConst& sc, const SatConst* d_sats, uint32_t nb
     k_phase_frac<<<(unsigned)((sc.B + 255) / 256), 256, 0, st>>>((uint32_t)sc.B, S.frac);
     R4WB_LAUNCH_CHECK();
     // exact-division shortcut, checked on the host for this sample rate over the magnitudes 2 pi |Doppler| can take
+    static std::mutex checked_mu;                     // tables are built from several host threads (r4wb_init_devices)
     static double checked_fs = 0.0;
     static int checked_ok = 0;
+    std::unique_lock<std::mutex> checked_lock(checked_mu);
     if (checked_fs != sc.fs) {
         const double y = 1.0 / sc.fs;
         uint64_t s = 88172645463325252ull;
@@ -552,9 +556,11 @@ bool launch_phase_exact(const ScenConst& sc, const SatConst* d_sats, uint32_t nb
         }
         checked_ok = ok; checked_fs = sc.fs;
     }
+    const int fast_div = checked_ok;
+    checked_lock.unlock();
     // A/B hook: R4WB_PHASE_Q_BRUTE=1 sums every block's increments sample by sample instead of locating the steps
     static const int step_form = [] { const char* e = std::getenv("R4WB_PHASE_Q_BRUTE"); return (e && e[0] == '1') ? 0 : 1; }();
-    k_phase_q<<<(unsigned)((ne + 127) / 128), 128, 0, st>>>(sc.fs, 1.0 / sc.fs, checked_ok, step_form, d_sats, ns, nblk, d_tab, d_dop, S.pstart, S.frac,
+    k_phase_q<<<(unsigned)((ne + 127) / 128), 128, 0, st>>>(sc.fs, 1.0 / sc.fs, fast_div, step_form, d_sats, ns, nblk, d_tab, d_dop, S.pstart, S.frac,
                                                              (uint32_t)sc.B, S.pq);
     R4WB_LAUNCH_CHECK();
     static const bool serial = [] { const char* e = std::getenv("R4WB_PHASE_SERIAL"); return e && e[0] == '1'; }();
