@@ -56,6 +56,25 @@ def test_kernel_equals_host_replay(gpu, emu):
     assert _relrms(a, b) < 2e-6
 
 
+def test_literal_fir_records_equal_host_replay(gpu, emu):
+    """records with a half-chip boundary inside the f64 rounding band (block flag bit 1, about one (block, satellite) in 750) take
+    the reference's literal 63-tap loop for the first 8 outputs of their block and of the next one; k_tile_params evaluates that
+    loop with the whole warp (119 signs resolved once, ballots, lanes 0-7 add the taps in the reference's order).  The host
+    replay runs fir_direct per output: the first samples of exactly those blocks must agree like every other sample"""
+    cfg = _cfg("e1c_8prn_60s_cn34_orbital")
+    em = emu.EmuScenario(cfg, noise=False)
+    flagged = [37, 85, 129, 278, 365, 381]                      # found with the host replay (tools: scan block_params(b, s)[8] & 2)
+    for b in flagged:
+        assert any(int(em.block_params(b, s)[8]) & 2 for s in range(8)), b
+    sc = gpu.GnssScenario(cfg, noise=False)
+    for b in flagged:
+        first = b * 5000 - 40                                   # tail of the block before, the flagged block, head of the next
+        a, e = sc.generate_range(first, 5100), em.generate_range(first, 5100)
+        assert _relrms(a, e) < 2e-6, b
+        for lo in (40, 5040):                                   # the 8 literal outputs of the flagged block and of its successor
+            assert np.max(np.abs(a[lo:lo + 8] - e[lo:lo + 8])) < 2e-5 * np.max(np.abs(e)), (b, lo)
+
+
 def test_golden_fixture(gpu):
     """committed oracle output (tests/golden/, made by tools/make_golden.py in the build container)"""
     import os
